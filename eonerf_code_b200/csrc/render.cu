@@ -1,0 +1,555 @@
+// Per-ray volume rendering kernels: transmittance / weights / accumulation (the nerfacc v0.5.2 operator
+// trio the reference calls), the fused EO-NeRF compositing, the sun-ray shadow pass and the irradiance +
+// radiometric epilogue — forward and backward.
+//
+// Reference call sites (relative to /root/reference):
+//   radiance_fields/eonerf.py:186-193,229-246   weights + five accumulate_along_rays + beta_min
+//   sat_rendering.py:87-118                      compute_geometric_shadows
+//   sat_rendering.py:265-312                     irradiance model, radiometric normalisation, 21-column packing
+//
+// Layout: samples are packed ray after ray; ray r owns [ray_offsets[r], ray_offsets[r+1]).  One warp owns
+// one ray: the 32 lanes read 32 consecutive samples (coalesced 128-byte requests), the per-ray exclusive
+// prefix sum of sigma*delta is a shuffle scan with a carry between 32-sample chunks, and every per-ray
+// reduction is a butterfly — no atomics, deterministic.
+//
+// The exclusive scan is a *true* exclusive scan (inclusive scan shifted by one lane): the last interval
+// of a camera ray is 1e10 long (eonerf.py:220), "inclusive minus self" would cancel catastrophically.
+#include "common.cuh"
+
+namespace eonerf {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ int64_t warp_ray() {
+  return (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+}
+
+// exclusive prefix (within the warp) of v; `total` receives the warp total
+__device__ __forceinline__ float warp_exclusive_sum(float v, int lane, float& total) {
+  float inc = warp_inclusive_sum(v, lane);
+  total = __shfl_sync(kFull, inc, 31);
+  float up = __shfl_up_sync(kFull, inc, 1);
+  return lane == 0 ? 0.0f : up;
+}
+
+struct SampleW {
+  float tau, T, alpha, w;
+};
+
+// tau = sigma*(te-ts); T = exp(-prefix); alpha = 1-exp(-tau); w = T*alpha      (nerfacc volrend.py)
+__device__ __forceinline__ SampleW sample_weight(float ts, float te, float sigma, float prefix) {
+  SampleW s;
+  s.tau = sigma * (te - ts);
+  s.T = expf(-prefix);
+  s.alpha = 1.0f - expf(-s.tau);
+  s.w = s.T * s.alpha;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// render_weight_from_density / render_transmittance_from_density
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) weights_fwd_kernel(EonerfWeightsFwdArgs a) {
+  int lane = threadIdx.x & 31;
+  int64_t ray = warp_ray();
+  if (ray >= a.n_rays) return;
+  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+  float carry = 0.f;
+  for (int64_t base = beg; base < end; base += 32) {
+    int64_t i = base + lane;
+    bool ok = i < end;
+    float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
+    float sg = ok ? __ldg(a.sigmas + i) : 0.f;
+    float tau = sg * (te - ts), tot;
+    float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+    carry += tot;
+    if (ok) {
+      SampleW s = sample_weight(ts, te, sg, pre);
+      if (a.weights) a.weights[i] = s.w;
+      if (a.trans) a.trans[i] = s.T;
+      if (a.alphas) a.alphas[i] = s.alpha;
+    }
+  }
+}
+
+// d/d sigma_j = delta_j * ( ga_j * exp(-tau_j) - sum_{i>j} gT_i * T_i )
+//   with gT_i = g_trans_i + g_w_i*alpha_i, ga_i = g_alpha_i + g_w_i*T_i.
+// Two forward sweeps: the first one accumulates S = sum_i gT_i*T_i, the second one turns the running
+// inclusive prefix into the exclusive suffix S - prefix (all terms are O(1): no 1e10 enters this sum).
+__global__ void __launch_bounds__(256) weights_bwd_kernel(EonerfWeightsBwdArgs a) {
+  int lane = threadIdx.x & 31;
+  int64_t ray = warp_ray();
+  if (ray >= a.n_rays) return;
+  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+  float S = 0.f;
+  {
+    float carry = 0.f;
+    for (int64_t base = beg; base < end; base += 32) {
+      int64_t i = base + lane;
+      bool ok = i < end;
+      float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
+      float sg = ok ? __ldg(a.sigmas + i) : 0.f;
+      float tau = sg * (te - ts), tot;
+      float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+      carry += tot;
+      float v = 0.f;
+      if (ok) {
+        SampleW s = sample_weight(ts, te, sg, pre);
+        float gT = (a.g_trans ? __ldg(a.g_trans + i) : 0.f) + (a.g_weights ? __ldg(a.g_weights + i) * s.alpha : 0.f);
+        v = gT * s.T;
+      }
+      S += warp_sum(v);
+    }
+  }
+  float carry = 0.f, run = 0.f;
+  for (int64_t base = beg; base < end; base += 32) {
+    int64_t i = base + lane;
+    bool ok = i < end;
+    float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
+    float sg = ok ? __ldg(a.sigmas + i) : 0.f;
+    float tau = sg * (te - ts), tot;
+    float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+    carry += tot;
+    SampleW s = sample_weight(ts, te, sg, pre);
+    float gw = (ok && a.g_weights) ? __ldg(a.g_weights + i) : 0.f;
+    float gT = ((ok && a.g_trans) ? __ldg(a.g_trans + i) : 0.f) + gw * s.alpha;
+    float ga = ((ok && a.g_alphas) ? __ldg(a.g_alphas + i) : 0.f) + gw * s.T;
+    float v = ok ? gT * s.T : 0.f;
+    float inc = warp_inclusive_sum(v, lane);
+    float suffix = S - (run + inc);
+    run += __shfl_sync(kFull, inc, 31);
+    if (ok) a.g_sigmas[i] = (te - ts) * (ga * expf(-s.tau) - suffix);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// accumulate_along_rays   out[r, c] = sum_{i in r} w_i * v_{i,c}
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) accumulate_fwd_kernel(EonerfAccumFwdArgs a) {
+  int lane = threadIdx.x & 31;
+  int64_t ray = warp_ray();
+  if (ray >= a.n_rays) return;
+  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+  int C = a.n_channels;
+  if (C <= 4) {  // lanes over samples
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t i = beg + lane; i < end; i += 32) {
+      float w = __ldg(a.weights + i);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) acc[c] += w * (a.values ? __ldg(a.values + i * C + c) : 1.0f);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float s = warp_sum(acc[c]);
+      if (c < C && lane == 0) a.out[ray * C + c] = s;
+    }
+  } else {  // lanes over channels
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      int c = c0 + lane;
+      float acc = 0.f;
+      if (c < C)
+        for (int64_t i = beg; i < end; ++i) acc += __ldg(a.weights + i) * __ldg(a.values + i * C + c);
+      if (c < C) a.out[ray * C + c] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) accumulate_bwd_kernel(EonerfAccumBwdArgs a) {
+  int lane = threadIdx.x & 31;
+  int64_t ray = warp_ray();
+  if (ray >= a.n_rays) return;
+  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+  int C = a.n_channels;
+  for (int64_t i = beg + lane; i < end; i += 32) {
+    float w = __ldg(a.weights + i), gw = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float g = __ldg(a.g_out + ray * C + c);
+      gw += g * (a.values ? __ldg(a.values + i * C + c) : 1.0f);
+      if (a.g_values) a.g_values[i * C + c] = w * g;
+    }
+    if (a.g_weights) a.g_weights[i] = gw;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused EO-NeRF compositing (eonerf.py:229-246)
+// comp row: 0:3 albedo, 3 depth, 4 beta(+beta_min), 5 transient_s, 6:9 ambient, 9 sum(w), 10:12 zero
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) composite_fwd_kernel(EonerfCompositeFwdArgs a) {
+  int lane = threadIdx.x & 31;
+  int64_t ray = warp_ray();
+  if (ray >= a.n_rays) return;
+  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // albedo3, depth, beta, ts, sumw
+  float carry = 0.f;
+  for (int64_t base = beg; base < end; base += 32) {
+    int64_t i = base + lane;
+    bool ok = i < end;
+    float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
+    float sg = ok ? __ldg(a.sigma + i) : 0.f;
+    float tau = sg * (te - ts), tot;
+    float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+    carry += tot;
+    if (ok) {
+      SampleW s = sample_weight(ts, te, sg, pre);
+      if (a.albedo) {
+        acc[0] += s.w * __ldg(a.albedo + 3 * i);
+        acc[1] += s.w * __ldg(a.albedo + 3 * i + 1);
+        acc[2] += s.w * __ldg(a.albedo + 3 * i + 2);
+      }
+      acc[3] += s.w * __ldg(a.z_mid + i);
+      if (a.transient_beta) acc[4] += s.w * __ldg(a.transient_beta + i);
+      if (a.transient_s) acc[5] += s.w * __ldg(a.transient_s + i);
+      acc[6] += s.w;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 7; ++c) acc[c] = warp_sum(acc[c]);
+  if (lane == 0) {
+    float* o = a.comp + ray * EONERF_COMP_COLS;
+    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+    o[4] = acc[4] + a.beta_min;
+    o[5] = acc[5];
+    // ambient is constant along the ray (sun direction is per ray): sum_i w_i*a = a*sum_i w_i
+    for (int c = 0; c < 3; ++c) o[6 + c] = a.ambient_ray ? acc[6] * __ldg(a.ambient_ray + 3 * ray + c) : 0.f;
+    o[9] = acc[6];
+    o[10] = 0.f; o[11] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) composite_bwd_kernel(EonerfCompositeBwdArgs a) {
+  int lane = threadIdx.x & 31;
+  int64_t ray = warp_ray();
+  if (ray >= a.n_rays) return;
+  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+  const float* g = a.g_comp + ray * EONERF_COMP_COLS;
+  float ga0 = __ldg(g), ga1 = __ldg(g + 1), ga2 = __ldg(g + 2), gd = __ldg(g + 3), gb = __ldg(g + 4), gs = __ldg(g + 5);
+  // per-ray constant part of G_i: ambient and the sum-of-weights column
+  float gconst = __ldg(g + 9);
+  if (a.ambient_ray)
+    for (int c = 0; c < 3; ++c) gconst += __ldg(g + 6 + c) * __ldg(a.ambient_ray + 3 * ray + c);
+
+  auto G_of = [&](int64_t i) {
+    float G = gconst + gd * __ldg(a.z_mid + i);
+    if (a.albedo) G += ga0 * __ldg(a.albedo + 3 * i) + ga1 * __ldg(a.albedo + 3 * i + 1) + ga2 * __ldg(a.albedo + 3 * i + 2);
+    if (a.transient_beta) G += gb * __ldg(a.transient_beta + i);
+    if (a.transient_s) G += gs * __ldg(a.transient_s + i);
+    return G;
+  };
+
+  float S = 0.f, sumw = 0.f;
+  {
+    float carry = 0.f;
+    for (int64_t base = beg; base < end; base += 32) {
+      int64_t i = base + lane;
+      bool ok = i < end;
+      float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
+      float sg = ok ? __ldg(a.sigma + i) : 0.f;
+      float tau = sg * (te - ts), tot;
+      float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+      carry += tot;
+      float v = 0.f, w = 0.f;
+      if (ok) {
+        SampleW s = sample_weight(ts, te, sg, pre);
+        w = s.w;
+        v = G_of(i) * s.w;
+      }
+      S += warp_sum(v);
+      sumw += warp_sum(w);
+    }
+  }
+  if (lane == 0 && a.g_ambient_ray)
+    for (int c = 0; c < 3; ++c) a.g_ambient_ray[3 * ray + c] = __ldg(g + 6 + c) * sumw;
+
+  float carry = 0.f, run = 0.f;
+  for (int64_t base = beg; base < end; base += 32) {
+    int64_t i = base + lane;
+    bool ok = i < end;
+    float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
+    float sg = ok ? __ldg(a.sigma + i) : 0.f;
+    float tau = sg * (te - ts), tot;
+    float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+    carry += tot;
+    SampleW s = sample_weight(ts, te, sg, pre);
+    float G = ok ? G_of(i) : 0.f;
+    float v = ok ? G * s.w : 0.f;
+    float inc = warp_inclusive_sum(v, lane);
+    float suffix = S - (run + inc);
+    run += __shfl_sync(kFull, inc, 31);
+    if (ok) {
+      // T_{j+1} = T_j * exp(-tau_j)
+      a.g_sigma[i] = (te - ts) * (G * s.T * expf(-s.tau) - suffix);
+      if (a.g_albedo) {
+        a.g_albedo[3 * i] = s.w * ga0;
+        a.g_albedo[3 * i + 1] = s.w * ga1;
+        a.g_albedo[3 * i + 2] = s.w * ga2;
+      }
+      if (a.g_transient_beta) a.g_transient_beta[i] = s.w * gb;
+      if (a.g_transient_s) a.g_transient_s[i] = s.w * gs;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sun-ray shadow pass (sat_rendering.py:87-118)
+// ------------------------------------------------------------------------------------------------
+__global__ void sun_rays_kernel(EonerfSunRaysArgs a) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n_rays) return;
+  const float* o = a.origins + r * a.origins_stride;
+  const float* d = a.viewdirs + r * a.viewdirs_stride;
+  const float* s = a.sundirs + r * a.sundirs_stride;
+  float depth = __ldg(a.depth + r * a.depth_stride);
+  float* out = a.sun_rays + 6 * r;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    out[c] = __fadd_rn(__ldg(o + c), __fmul_rn(depth, __ldg(d + c)));   // :90 (two separately rounded ops)
+    out[3 + c] = __fmul_rn(-1.0f, __ldg(s + c));                        // :91
+  }
+}
+
+// geo_shadow[r] = transmittance in front of the LAST kept sample of sun ray r (:106-116), 1 if none
+__global__ void __launch_bounds__(256) shadow_fwd_kernel(EonerfShadowFwdArgs a) {
+  int lane = threadIdx.x & 31;
+  int64_t ray = warp_ray();
+  if (ray >= a.n_rays) return;
+  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+  float acc = 0.f;
+  for (int64_t i = beg + lane; i < end - 1; i += 32)
+    acc += __ldg(a.sigma + i) * (__ldg(a.t_ends + i) - __ldg(a.t_starts + i));
+  acc = warp_sum(acc);
+  if (lane == 0) a.geo_shadow[ray] = (end > beg) ? expf(-acc) : 1.0f;
+}
+
+__global__ void __launch_bounds__(256) shadow_bwd_kernel(EonerfShadowBwdArgs a) {
+  int lane = threadIdx.x & 31;
+  int64_t ray = warp_ray();
+  if (ray >= a.n_rays) return;
+  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+  float k = -__ldg(a.geo_shadow + ray) * __ldg(a.g_geo_shadow + ray);
+  for (int64_t i = beg + lane; i < end; i += 32)
+    a.g_sigma[i] = (i < end - 1) ? k * (__ldg(a.t_ends + i) - __ldg(a.t_starts + i)) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) sun_origin_bwd_kernel(EonerfSunOriginBwdArgs a) {
+  int lane = threadIdx.x & 31;
+  int64_t ray = warp_ray();
+  if (ray >= a.n_rays) return;
+  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  for (int64_t i = beg + lane; i < end; i += 32) {
+    gx += __ldg(a.g_x + 3 * i);
+    gy += __ldg(a.g_x + 3 * i + 1);
+    gz += __ldg(a.g_x + 3 * i + 2);
+  }
+  gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
+  if (lane == 0) {
+    const float* d = a.viewdirs + ray * a.viewdirs_stride;
+    a.g_depth[ray * a.g_depth_stride] += gx * __ldg(d) + gy * __ldg(d + 1) + gz * __ldg(d + 2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Irradiance + radiometric epilogue (sat_rendering.py:265-312)
+// ------------------------------------------------------------------------------------------------
+struct Radiometric {
+  float A[3], b[3];
+  int64_t img;
+};
+
+template <class Args>
+__device__ __forceinline__ Radiometric load_radiometric(const Args& a, int64_t r) {
+  Radiometric m;
+  m.img = a.eval_mode ? __ldg(a.img_idx) : __ldg(a.img_idx + r * a.img_idx_stride);   // :288-291
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    m.A[c] = a.radiometric ? __ldg(a.radiometric + m.img * 9 + c) : 1.0f;
+    m.b[c] = a.radiometric ? __ldg(a.radiometric + m.img * 9 + 3 + c) : 0.0f;
+  }
+  return m;
+}
+
+__global__ void epilogue_fwd_kernel(EonerfEpilogueFwdArgs a) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n_rays) return;
+  const float* c = a.comp + r * EONERF_COMP_COLS;
+  float* o = a.out + r * EONERF_OUT_COLS;
+  Radiometric m = load_radiometric(a, r);
+  float ts = c[5];
+  float geo = a.geo_shadow ? __ldg(a.geo_shadow + r) : 1.0f;
+  float s = a.geo_shadow ? geo * ts : 1.0f;                       // :269-276
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float alb = c[k], amb = c[6 + k] * 0.2f;                       // :265
+    float rgb = alb * s + (1.0f - s) * (amb * alb);                // :294
+    rgb = m.A[k] * rgb + m.b[k];                                   // :304
+    o[k] = fminf(fmaxf(rgb, 0.0f), 1.0f);                          // :305
+    o[4 + k] = alb;
+    o[7 + k] = amb;
+    o[18 + k] = m.A[k] * alb + m.b[k];                             // :306
+  }
+  o[3] = c[3];
+  o[10] = geo;
+  o[11] = ts;
+  o[12] = c[4];
+  o[13] = 1.0f;                                                    // entropy (eonerf.py:246)
+  o[14] = __ldg(a.pts_per_ray + r);
+  o[15] = a.sc_pts_per_ray ? __ldg(a.sc_pts_per_ray + r) : 1.0f;   // :272
+  o[16] = 1.0f; o[17] = 1.0f;                                      // opacity_after_surface (:283)
+}
+
+__global__ void epilogue_bwd_kernel(EonerfEpilogueBwdArgs a) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n_rays) return;
+  const float* c = a.comp + r * EONERF_COMP_COLS;
+  const float* go = a.g_out + r * EONERF_OUT_COLS;
+  float* gc = a.g_comp + r * EONERF_COMP_COLS;
+  Radiometric m = load_radiometric(a, r);
+  float ts = c[5];
+  float geo = a.geo_shadow ? __ldg(a.geo_shadow + r) : 1.0f;
+  float s = a.geo_shadow ? geo * ts : 1.0f;
+  float g_s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float alb = c[k], amb = c[6 + k] * 0.2f;
+    float rgb0 = alb * s + (1.0f - s) * (amb * alb);
+    float pre = m.A[k] * rgb0 + m.b[k];
+    float g_pre = (pre >= 0.0f && pre <= 1.0f) ? __ldg(go + k) : 0.0f;   // clip backward, bounds inclusive
+    float g_sl = __ldg(go + 18 + k);
+    float g_rgb0 = g_pre * m.A[k];
+    gc[k] = g_rgb0 * (s + (1.0f - s) * amb) + __ldg(go + 4 + k) + g_sl * m.A[k];
+    gc[6 + k] = 0.2f * (g_rgb0 * (1.0f - s) * alb + __ldg(go + 7 + k));
+    g_s += g_rgb0 * alb * (1.0f - amb);
+    if (a.g_radiometric && a.radiometric) {
+      atomicAdd(a.g_radiometric + m.img * 9 + k, g_pre * rgb0 + g_sl * alb);
+      atomicAdd(a.g_radiometric + m.img * 9 + 3 + k, g_pre + g_sl);
+    }
+  }
+  gc[3] = __ldg(go + 3);
+  gc[4] = __ldg(go + 12);
+  if (a.geo_shadow) {
+    gc[5] = g_s * geo + __ldg(go + 11);
+    if (a.g_geo_shadow) a.g_geo_shadow[r] = g_s * ts + __ldg(go + 10);
+  } else {
+    gc[5] = __ldg(go + 11);
+  }
+  gc[9] = 0.f; gc[10] = 0.f; gc[11] = 0.f;
+}
+
+}  // namespace eonerf
+
+using namespace eonerf;
+
+#define RAY_BLOCKS(n) div_up((n), kWarpsPerBlock)
+
+extern "C" int eonerf_weights_fwd(const EonerfWeightsFwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->ray_offsets && a->n_rays >= 0, "weights_fwd: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->sigmas), "weights_fwd: null input");
+  weights_fwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_weights_bwd(const EonerfWeightsBwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->ray_offsets && a->n_rays >= 0, "weights_bwd: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->sigmas && a->g_sigmas), "weights_bwd: null input");
+  weights_bwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_accumulate_fwd(const EonerfAccumFwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->ray_offsets && a->n_rays >= 0 && a->n_channels >= 1, "accumulate_fwd: bad arguments");
+  EO_REQUIRE(a->values || a->n_channels == 1, "accumulate_fwd: values==NULL needs n_channels==1");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->out && (a->n_pts == 0 || a->weights), "accumulate_fwd: null pointer");
+  accumulate_fwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_accumulate_bwd(const EonerfAccumBwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->ray_offsets && a->n_rays >= 0 && a->n_channels >= 1, "accumulate_bwd: bad arguments");
+  EO_REQUIRE(a->values || a->n_channels == 1, "accumulate_bwd: values==NULL needs n_channels==1");
+  if (a->n_rays == 0 || a->n_pts == 0) return EONERF_OK;
+  EO_REQUIRE(a->g_out && a->weights, "accumulate_bwd: null pointer");
+  accumulate_bwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_composite_fwd(const EonerfCompositeFwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->ray_offsets && a->comp && a->n_rays >= 0, "composite_fwd: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->z_mid && a->sigma), "composite_fwd: null input");
+  composite_fwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_composite_bwd(const EonerfCompositeBwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->ray_offsets && a->g_comp && a->n_rays >= 0, "composite_bwd: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->z_mid && a->sigma && a->g_sigma),
+             "composite_bwd: null pointer");
+  composite_bwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_sun_rays(const EonerfSunRaysArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->n_rays >= 0, "sun_rays: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->origins && a->viewdirs && a->sundirs && a->depth && a->sun_rays, "sun_rays: null pointer");
+  sun_rays_kernel<<<div_up(a->n_rays, 256), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_shadow_fwd(const EonerfShadowFwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->ray_offsets && a->geo_shadow && a->n_rays >= 0, "shadow_fwd: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->sigma), "shadow_fwd: null input");
+  shadow_fwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_shadow_bwd(const EonerfShadowBwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->ray_offsets && a->n_rays >= 0, "shadow_bwd: bad arguments");
+  if (a->n_rays == 0 || a->n_pts == 0) return EONERF_OK;
+  EO_REQUIRE(a->t_starts && a->t_ends && a->geo_shadow && a->g_geo_shadow && a->g_sigma, "shadow_bwd: null pointer");
+  shadow_bwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_sun_origin_bwd(const EonerfSunOriginBwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->ray_offsets && a->n_rays >= 0, "sun_origin_bwd: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->viewdirs && a->g_depth && (a->n_pts == 0 || a->g_x), "sun_origin_bwd: null pointer");
+  sun_origin_bwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_epilogue_fwd(const EonerfEpilogueFwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->n_rays >= 0, "epilogue_fwd: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->comp && a->pts_per_ray && a->img_idx && a->out, "epilogue_fwd: null pointer");
+  epilogue_fwd_kernel<<<div_up(a->n_rays, 256), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+extern "C" int eonerf_epilogue_bwd(const EonerfEpilogueBwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->n_rays >= 0, "epilogue_bwd: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->comp && a->img_idx && a->g_out && a->g_comp, "epilogue_bwd: null pointer");
+  epilogue_bwd_kernel<<<div_up(a->n_rays, 256), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}

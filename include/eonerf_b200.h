@@ -1,0 +1,346 @@
+/*
+ * eonerf_b200.h — C ABI of the B200-native EO-NeRF per-ray rendering hot path.
+ *
+ * Drop-in boundary.  The reference has no FFI of its own for this path: its only
+ * native code is the un-vendored nerfacc v0.5.2 extension (/root/reference/setup_env.sh:10) reached
+ * through three Python operators, everything else is ATen.  Each entry point below names the
+ * reference interface it replaces (file:line relative to /root/reference).
+ *
+ * Conventions
+ *   - plain C, POD argument structs, raw *device* pointers + int64 sizes; no torch types.
+ *   - the caller owns ALL memory (inputs, outputs, workspaces); the library never allocates device
+ *     memory and never synchronises; work is enqueued on the `stream` argument (a cudaStream_t).
+ *   - contiguous row-major fp32 / int64 unless a `*_stride` (in elements) is given.
+ *   - return 0 on success, a negative EONERF_E* code on failure; eonerf_last_error() gives the
+ *     message of the last failure on the calling thread.  There is no CPU fallback: a missing
+ *     device or a device that is not sm_100 is an error.
+ */
+#ifndef EONERF_B200_H
+#define EONERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EONERF_ABI_VERSION 4
+
+#define EONERF_OK 0
+#define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
+#define EONERF_ECUDA (-2)    /* CUDA runtime or launch error     */
+#define EONERF_EDEVICE (-3)  /* not an sm_100 device             */
+
+typedef void* eonerf_stream_t; /* cudaStream_t */
+
+int eonerf_abi_version(void);
+const char* eonerf_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), else EONERF_EDEVICE. */
+int eonerf_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stratified sampling + cube mask + order-preserving compaction.
+ * Replaces satnerf_sampling / perturb_z_vals / filter_pts_outside_cube
+ *   (sat_rendering.py:18-22,46-54,56-84) and count_number_of_pts_per_nerfacc_ray (:10-16).
+ * Bit-exact with the reference given the same uniforms `u` and the same `z_steps`
+ * (= torch.linspace(0,1,n), passed in because its rounding is torch's own).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* origins;   int64_t origins_stride;   /* [B,3] rows, stride in floats (11 for a ray table) */
+  const float* viewdirs;  int64_t viewdirs_stride;
+  const float* near;      int64_t near_stride;      /* [B] or NULL (=0)  (sat_rendering.py:60-61) */
+  const float* u;                                   /* [B,n] uniforms in [0,1) (torch.rand_like, :52) */
+  const float* z_steps;                             /* [n] */
+  int64_t n_rays;
+  int32_t n_samples;                                /* n = int(2/render_step_size) (:64) */
+  /* outputs; capacity of the three packed arrays is B*(n-1) */
+  int64_t* ray_indices;                             /* [P] */
+  float* t_starts;                                  /* [P] */
+  float* t_ends;                                    /* [P] */
+  float* pts_per_ray;                               /* [B] fp32 counts (the reference returns fp32, :14) */
+  int64_t* ray_offsets;                             /* [B+1] exclusive prefix of the counts (packed info) */
+  int64_t* stats;                                   /* [2]: P, number of rays with 0 samples */
+} EonerfSampleArgs;
+int eonerf_sample_compact(const EonerfSampleArgs* a, eonerf_stream_t stream);
+
+/* ray_offsets[B+1] from sorted ray_indices[P] (nerfacc pack_info; used when the operator-level API is
+ * called with ray_indices only: radiance_fields/eonerf.py:229-235). */
+int eonerf_pack_info(const int64_t* ray_indices, int64_t n_pts, int64_t n_rays, int64_t* ray_offsets,
+                     eonerf_stream_t stream);
+
+/* t_ends[last sample of every non-empty ray] = value   (radiance_fields/eonerf.py:218-220: 1e10) */
+int eonerf_set_last_t_end(float* t_ends, const int64_t* ray_offsets, int64_t n_rays, float value,
+                          eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * nerfacc v0.5.2 volume rendering operators (flattened samples + packed info).
+ * Replace render_transmittance_from_density / render_weight_from_density / accumulate_along_rays
+ *   (call sites radiance_fields/eonerf.py:186-193,229-242; sat_rendering.py:106-110).
+ * Deterministic: one warp owns one ray, no atomics.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* t_starts; const float* t_ends; const float* sigmas;  /* [P] */
+  const int64_t* ray_offsets; int64_t n_rays; int64_t n_pts;
+  float* weights; float* trans; float* alphas;                       /* [P] each, any may be NULL */
+} EonerfWeightsFwdArgs;
+int eonerf_weights_fwd(const EonerfWeightsFwdArgs* a, eonerf_stream_t stream);
+
+typedef struct {
+  const float* t_starts; const float* t_ends; const float* sigmas;  /* [P] */
+  const int64_t* ray_offsets; int64_t n_rays; int64_t n_pts;
+  const float* g_weights; const float* g_trans; const float* g_alphas; /* [P] each, any may be NULL */
+  float* g_sigmas;                                                   /* [P] */
+} EonerfWeightsBwdArgs;
+int eonerf_weights_bwd(const EonerfWeightsBwdArgs* a, eonerf_stream_t stream);
+
+typedef struct {
+  const float* weights;       /* [P] */
+  const float* values;        /* [P,C] or NULL (C=1, value 1) */
+  int32_t n_channels;
+  const int64_t* ray_offsets; int64_t n_rays; int64_t n_pts;
+  float* out;                 /* [B,C] */
+} EonerfAccumFwdArgs;
+int eonerf_accumulate_fwd(const EonerfAccumFwdArgs* a, eonerf_stream_t stream);
+
+typedef struct {
+  const float* weights; const float* values; int32_t n_channels;
+  const int64_t* ray_offsets; int64_t n_rays; int64_t n_pts;
+  const float* g_out;         /* [B,C] */
+  float* g_weights;           /* [P] or NULL */
+  float* g_values;            /* [P,C] or NULL */
+} EonerfAccumBwdArgs;
+int eonerf_accumulate_bwd(const EonerfAccumBwdArgs* a, eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused EO-NeRF compositing of one chunk of rays.
+ * Replaces the weights + five accumulate_along_rays calls + beta_min of EONerfMLP.rendering
+ *   (radiance_fields/eonerf.py:229-246).  Per-ray output row `comp[B,12]`:
+ *     0:3 albedo, 3 depth, 4 beta (+0.05), 5 transient_s, 6:9 ambient (NOT yet x0.2), 9 sum of weights,
+ *     10,11 unused (0).
+ * ---------------------------------------------------------------------------------------------- */
+#define EONERF_COMP_COLS 12
+typedef struct {
+  const float* t_starts; const float* t_ends;   /* [P]; t_ends already holds 1e10 at each ray's last sample */
+  const float* z_mid;                           /* [P] (t_starts+t_ends)/2 computed BEFORE the 1e10 write (eonerf.py:206) */
+  const float* sigma;                           /* [P] */
+  const float* albedo;                          /* [P,3] */
+  const float* transient_s;                     /* [P] */
+  const float* transient_beta;                  /* [P] */
+  const float* ambient_ray;                     /* [B,3] per-ray ambient colour (constant along a ray, eonerf.py:163-164,204) */
+  const int64_t* ray_offsets; int64_t n_rays; int64_t n_pts;
+  float beta_min;                               /* 0.05, eonerf.py:87,243 */
+  float* comp;                                  /* [B,12] */
+} EonerfCompositeFwdArgs;
+int eonerf_composite_fwd(const EonerfCompositeFwdArgs* a, eonerf_stream_t stream);
+
+typedef struct {
+  const float* t_starts; const float* t_ends; const float* z_mid; const float* sigma;
+  const float* albedo; const float* transient_s; const float* transient_beta; const float* ambient_ray;
+  const int64_t* ray_offsets; int64_t n_rays; int64_t n_pts;
+  const float* g_comp;                          /* [B,12] */
+  float* g_sigma;                               /* [P] */
+  float* g_albedo;                              /* [P,3] */
+  float* g_transient_s;                         /* [P] */
+  float* g_transient_beta;                      /* [P] */
+  float* g_ambient_ray;                         /* [B,3] */
+} EonerfCompositeBwdArgs;
+int eonerf_composite_bwd(const EonerfCompositeBwdArgs* a, eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sun-direction shadow pass.  Replaces compute_geometric_shadows (sat_rendering.py:87-118) around the
+ * density query: ray set-up (:90-91), transmittance at the last kept sample (:106-116) and their backward.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* origins;  int64_t origins_stride;
+  const float* viewdirs; int64_t viewdirs_stride;
+  const float* sundirs;  int64_t sundirs_stride;
+  const float* depth;    int64_t depth_stride;   /* [B] */
+  int64_t n_rays;
+  float* sun_rays;                               /* [B,6]: origin = o + depth*d (:90), dir = -1*sun (:91) */
+} EonerfSunRaysArgs;
+int eonerf_sun_rays(const EonerfSunRaysArgs* a, eonerf_stream_t stream);
+
+typedef struct {
+  const float* t_starts; const float* t_ends; const float* sigma;  /* [Q] */
+  const int64_t* ray_offsets; int64_t n_rays; int64_t n_pts;
+  float* geo_shadow;                              /* [B]: T before the last kept sample; 1 if the ray has none */
+} EonerfShadowFwdArgs;
+int eonerf_shadow_fwd(const EonerfShadowFwdArgs* a, eonerf_stream_t stream);
+
+typedef struct {
+  const float* t_starts; const float* t_ends;     /* [Q] */
+  const int64_t* ray_offsets; int64_t n_rays; int64_t n_pts;
+  const float* geo_shadow; const float* g_geo_shadow; /* [B] */
+  float* g_sigma;                                 /* [Q] */
+} EonerfShadowBwdArgs;
+int eonerf_shadow_bwd(const EonerfShadowBwdArgs* a, eonerf_stream_t stream);
+
+/* d depth[r] += sum_c (sum_{i in ray r} g_x[i,c]) * viewdir[r,c]   (chain rule through sat_rendering.py:90) */
+typedef struct {
+  const float* g_x;                               /* [Q,3] gradient wrt the sun-sample positions */
+  const int64_t* ray_offsets; int64_t n_rays; int64_t n_pts;
+  const float* viewdirs; int64_t viewdirs_stride;
+  float* g_depth; int64_t g_depth_stride;         /* [B] (strided), accumulated into */
+} EonerfSunOriginBwdArgs;
+int eonerf_sun_origin_bwd(const EonerfSunOriginBwdArgs* a, eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Irradiance model + radiometric normalisation + 21-column packing.
+ * Replaces sat_rendering.py:265,269-276,288-312.
+ * ---------------------------------------------------------------------------------------------- */
+#define EONERF_OUT_COLS 21
+typedef struct {
+  const float* comp;                /* [B,12] from eonerf_composite_fwd */
+  const float* geo_shadow;          /* [B] or NULL (= 1, epoch_idx < 2: s = 1, sat_rendering.py:269-272) */
+  const float* pts_per_ray;         /* [B] */
+  const float* sc_pts_per_ray;      /* [B] or NULL (= 1) */
+  const int64_t* img_idx; int64_t img_idx_stride;  /* [B] */
+  int32_t eval_mode;                /* 1: use img_idx[0] for every ray (sat_rendering.py:288-289) */
+  const float* radiometric;         /* [n_img,9] or NULL (A=1,b=0) */
+  int64_t n_images;
+  int64_t n_rays;
+  float* out;                       /* [B,21] */
+} EonerfEpilogueFwdArgs;
+int eonerf_epilogue_fwd(const EonerfEpilogueFwdArgs* a, eonerf_stream_t stream);
+
+typedef struct {
+  const float* comp; const float* geo_shadow;
+  const int64_t* img_idx; int64_t img_idx_stride; int32_t eval_mode;
+  const float* radiometric; int64_t n_images; int64_t n_rays;
+  const float* g_out;               /* [B,21] */
+  float* g_comp;                    /* [B,12] */
+  float* g_geo_shadow;              /* [B] or NULL */
+  float* g_radiometric;             /* [n_img,9] accumulated into (fp32 atomics), or NULL */
+} EonerfEpilogueBwdArgs;
+int eonerf_epilogue_bwd(const EonerfEpilogueBwdArgs* a, eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Radiance-field MLP.  Replaces EONerfMLP.forward / query_density (radiance_fields/eonerf.py:141-170),
+ * MLP.forward (radiance_fields/mlp.py:87-101), SinusoidalEncoder.forward (mlp.py:190-208) and, for
+ * BASELINE config 2, VanillaNeRFRadianceField.forward (mlp.py:245-250) — forward and backward.
+ *
+ * precision: EONERF_PREC_FP32  SIMT fp32 kernels (exactness mode, used for tight parity tests)
+ *            EONERF_PREC_BF16  tcgen05/TMEM tensor-core kernels, bf16 operands, fp32 accumulation
+ * ---------------------------------------------------------------------------------------------- */
+#define EONERF_PREC_FP32 0
+#define EONERF_PREC_BF16 1
+
+#define EONERF_FIELD_EONERF 0
+#define EONERF_FIELD_VANILLA 1
+
+/* Pointers to the fp32 master parameters (checkpoint layout).  The same struct
+ * is used for gradients.  Weight matrices are [out,in] row-major as in nn.Linear. */
+typedef struct {
+  float* trunk_w[8]; float* trunk_b[8];     /* base_mlp.hidden_layers.{0..7}: (256,63) (256,256)x4 (256,319) (256,256)x2 */
+  float* sigma_w; float* sigma_b;           /* (1,256) (1) */
+  float* bott_w; float* bott_b;             /* (256,256) (256) */
+  float* head0_w; float* head0_b;           /* eonerf: albedo_mlp.hidden_layers.0 (128,256); vanilla: rgb_layer.hidden_layers.0 (128,283) */
+  float* head1_w; float* head1_b;           /* (3,128) (3) */
+  float* trans_w[4]; float* trans_b[4];     /* transient_mlp.hidden_layers.{0..3}: (128,260) (128,128)x3  (eonerf only) */
+  float* ts_w; float* ts_b;                 /* transient_scalar (1,128) (1) */
+  float* tb_w; float* tb_b;                 /* transient_beta   (1,128) (1) */
+  float* amb0_w; float* amb0_b;             /* ambient_mlp.hidden_layers.0 (128,27) (128) */
+  float* amb1_w; float* amb1_b;             /* ambient_mlp.output_layer   (3,128) (3) */
+  float* transient_emb;                     /* (n_img,4) */
+  int64_t n_images;
+} EonerfFieldParams;
+
+/* bytes of the prepared-parameter blob / of the forward stash / of the backward scratch */
+int64_t eonerf_field_prepared_bytes(int32_t field, int32_t precision);
+int64_t eonerf_field_stash_bytes(int32_t field, int32_t precision, int64_t n_pts, int64_t n_images, int32_t density_only);
+int64_t eonerf_field_scratch_bytes(int32_t field, int32_t precision, int64_t n_pts, int64_t n_images);
+
+/* Convert the fp32 master weight matrices into the kernels' operand layouts: K padded to a multiple of
+ * 8 elements, W [out,Kp] and W^T [Kp,out], fp32 or bf16.  Call once per optimiser step. */
+int eonerf_field_prepare(int32_t field, int32_t precision, const EonerfFieldParams* params, void* prepared,
+                         eonerf_stream_t stream);
+
+typedef struct {
+  int32_t field; int32_t precision;
+  const EonerfFieldParams* params;  /* fp32 masters: biases, the 1- and 3-wide heads, the embedding */
+  const void* prepared;
+  int64_t n_pts;
+  /* sample positions: either explicit x[N,3] ... */
+  const float* x;
+  /* ... or derived from rays: x = o[ri] + d[ri]*z_mid, z_mid = (t_starts+t_ends)/2 (eonerf.py:202-207) */
+  const float* origins;  int64_t origins_stride;
+  const float* viewdirs; int64_t viewdirs_stride;
+  const int64_t* ray_indices;      /* [N] */
+  const float* t_starts; const float* t_ends;   /* [N]; read BEFORE any 1e10 write */
+  float* z_mid;                    /* [N] out (may be NULL) */
+  /* conditioning: image index per ray [B] (looked up through ray_indices) when ray_indices != NULL,
+   * else per sample [N] */
+  const int64_t* img_idx; int64_t img_idx_stride;
+  const float* cond_dirs; int64_t cond_dirs_stride; /* vanilla field only: per-sample view directions [N,3] */
+  int32_t density_only;            /* 1: query_density (trunk + sigma), eonerf.py:141-145 */
+  void* stash;                     /* activations kept for backward */
+  /* outputs, fp32 */
+  float* sigma;                    /* [N] */
+  float* rgb;                      /* [N,3] albedo (eonerf) / rgb (vanilla) */
+  float* transient_s;              /* [N] */
+  float* transient_beta;           /* [N] */
+} EonerfFieldFwdArgs;
+int eonerf_field_fwd(const EonerfFieldFwdArgs* a, eonerf_stream_t stream);
+
+typedef struct {
+  int32_t field; int32_t precision;
+  const EonerfFieldParams* params;
+  const void* prepared;
+  int64_t n_pts;
+  int32_t density_only;
+  const void* stash;               /* written by the matching eonerf_field_fwd */
+  void* scratch;
+  const float* sigma; const float* rgb; const float* transient_s; const float* transient_beta; /* forward outputs */
+  const float* g_sigma; const float* g_rgb; const float* g_transient_s; const float* g_transient_beta; /* may be NULL (=0) */
+  const EonerfFieldParams* grads;  /* fp32 gradients, same shapes as params, ACCUMULATED into; NULL: skip parameter gradients */
+  float* g_x;                      /* [N,3] gradient wrt positions, or NULL */
+} EonerfFieldBwdArgs;
+int eonerf_field_bwd(const EonerfFieldBwdArgs* a, eonerf_stream_t stream);
+
+/* Per-ray ambient colour sigmoid(W1 relu(W0 enc4(sun) + b0) + b1) (eonerf.py:163-164), fwd + bwd.
+ * Tiny (B rows); always fp32. */
+typedef struct {
+  const float* sundirs; int64_t sundirs_stride; int64_t n_rays;
+  const float* w0; const float* b0; const float* w1; const float* b1;   /* (128,27) (128) (3,128) (3) */
+  float* hidden;                   /* [B,128] stash */
+  float* ambient;                  /* [B,3] */
+} EonerfAmbientFwdArgs;
+int eonerf_ambient_fwd(const EonerfAmbientFwdArgs* a, eonerf_stream_t stream);
+
+typedef struct {
+  const float* sundirs; int64_t sundirs_stride; int64_t n_rays;
+  const float* w0; const float* w1;
+  const float* hidden; const float* ambient; const float* g_ambient;   /* [B,128] [B,3] [B,3] */
+  float* g_w0; float* g_b0; float* g_w1; float* g_b1;                    /* accumulated into (atomics) */
+} EonerfAmbientBwdArgs;
+int eonerf_ambient_bwd(const EonerfAmbientBwdArgs* a, eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Building block exposed for tests and micro-benchmarks: Y = act(X W^T + b) on the tensor cores
+ * (tcgen05 / TMEM / TMA) or the SIMT path.  X [M,K] and W [N,K] are bf16 (BF16) or fp32 (FP32).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t precision;
+  const void* x; int64_t ldx; const void* w; int64_t ldw; const float* bias;
+  int64_t m; int32_t n; int32_t k;
+  int32_t act;                      /* 0 none, 1 relu */
+  void* y; int64_t ldy;
+} EonerfLinearArgs;
+int eonerf_linear_fwd(const EonerfLinearArgs* a, eonerf_stream_t stream);
+
+/* dW[N,K] (fp32) = dY[M,N]^T X[M,K], reduced over M (split over CTAs, deterministic two-stage).
+ * `partials` must hold eonerf_dw_partials_bytes(n,k) bytes. */
+typedef struct {
+  int32_t precision;
+  const void* dy; int64_t lddy; const void* x; int64_t ldx;
+  int64_t m; int32_t n; int32_t k;
+  float* partials;
+  float* dw; int64_t lddw;          /* accumulated into */
+} EonerfDwArgs;
+int64_t eonerf_dw_partials_bytes(int32_t n, int32_t k);
+int eonerf_linear_dw(const EonerfDwArgs* a, eonerf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EONERF_B200_H */

@@ -1,0 +1,181 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz by running the unmodified reference Python.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+The fixtures are committed; the GPU box never runs this script.  While generating, every fixture is
+also checked against oracle/eonerf_oracle.py so a drift between reference and restatement fails here.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import eonerf_oracle as O          # noqa: E402
+from oracle import ref_harness                 # noqa: E402
+from eonerf_code_b200.datasets.synthetic import make_rays  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def param_fingerprint(p):
+    return np.array([float(v.double().sum()) for v in p.values()] +
+                    [float(v.double().abs().sum()) for v in p.values()])
+
+
+def ref_model(ref, p, n_img):
+    m = ref.eonerf.EONerfMLP(n_img, radiometric_normalization=True)
+    missing, unexpected = m.load_state_dict(p, strict=False)
+    assert not unexpected and all("scales" in k for k in missing), (missing, unexpected)
+    return m
+
+
+def gen_sampling(ref):
+    out = {}
+    for tag, (B, n_arg, variant, seed) in {"n64": (48, 64, "spread", 1), "n96": (40, 96, "spread", 2),
+                                          "n128_inside": (24, 128, "inside", 3)}.items():
+        rays, ts, _ = make_rays(B, 7, seed=seed, variant=variant)
+        if tag == "n64":
+            rays[5, 0:3] = torch.tensor([3.0, 3.0, 1.0])     # a ray that never enters the cube -> 0 samples
+            rays[6, 6] = 0.25                                 # non-zero t_near
+        step = (torch.tensor(2.0) / n_arg).item()             # fp32 quotient, train_eonerf.py:50-53
+        n = int(2 / step)
+        g = torch.Generator().manual_seed(100 + seed)
+        u = torch.rand(B, n, generator=g)
+        sr = ref.satellite.define_satrays_from_tensors(rays, ts)
+        with ref_harness.FixedRand([u]):
+            ri, t0, t1 = ref.sat_rendering.satnerf_sampling(sr.origins, sr.viewdirs, {"render_step_size": step},
+                                                            near=sr.t_near)
+        ppr = ref.sat_rendering.count_number_of_pts_per_nerfacc_ray(sr, ri)
+        ori, ot0, ot1, _ = O.satnerf_sampling(sr.origins, sr.viewdirs, n, u, near=sr.t_near)
+        assert torch.equal(ri, ori) and torch.equal(t0, ot0) and torch.equal(t1, ot1), tag
+        assert torch.equal(ppr, O.pts_per_ray(ori, B))
+        out.update({f"{tag}_rays": rays.numpy(), f"{tag}_u": u.numpy(), f"{tag}_step": np.float64(step),
+                    f"{tag}_n": np.int64(n), f"{tag}_ray_indices": ri.numpy(), f"{tag}_t_starts": t0.numpy(),
+                    f"{tag}_t_ends": t1.numpy(), f"{tag}_pts_per_ray": ppr.numpy(),
+                    f"{tag}_z_steps": torch.linspace(0, 1, n).numpy()})
+        print(f"sampling {tag}: n={n} kept {ri.numel()} of {B * (n - 1)}; empty rays {(ppr == 0).sum().item()}")
+    np.savez_compressed(os.path.join(GOLD, "sampling.npz"), **out)
+
+
+def gen_field(ref):
+    n_img, N = 5, 300
+    p = O.init_params(n_img, seed=11, bias_scale=0.1)
+    m = ref_model(ref, p, n_img)
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(N, 3, generator=g) * 2 - 1
+    sun = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=1)
+    img = torch.randint(0, n_img, (N, 1), generator=g)
+    with torch.no_grad():
+        ref_out = m(x, sun, img)
+        ora_out = O.field_forward(p, x, sun, img)
+        dens = m.query_density(x)
+    for a, b in zip(ref_out, ora_out):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+    # input gradient of the density (needed by the shadow pass, sat_rendering.py:90)
+    xg = x.clone().requires_grad_(True)
+    m.query_density(xg).sum().backward()
+    names = ["sigma", "albedo", "ambient", "transient_s", "transient_beta"]
+    np.savez_compressed(os.path.join(GOLD, "field.npz"), n_img=n_img, seed=11, bias_scale=0.1,
+                        fingerprint=param_fingerprint(p), x=x.numpy(), sun=sun.numpy(), img=img.numpy(),
+                        density=dens.numpy(), d_density_dx=xg.grad.numpy(),
+                        **{k: v.numpy() for k, v in zip(names, ref_out)})
+    print("field: ok", [tuple(o.shape) for o in ref_out])
+
+
+def gen_render(ref):
+    fixtures = {}
+    for tag, (B, n_arg, epoch, ev, variant) in {"train_e2": (64, 32, 2, False, "spread"),
+                                                "train_e0": (32, 32, 0, False, "spread"),
+                                                "eval_e5": (32, 48, 5, True, "inside")}.items():
+        n_img = 6
+        p = O.init_params(n_img, seed=21, bias_scale=0.05)
+        m = ref_model(ref, p, n_img)
+        rays, ts, pixels = make_rays(B, n_img, seed=5, variant=variant)
+        step = (torch.tensor(2.0) / n_arg).item()
+        n = int(2 / step)
+        g = torch.Generator().manual_seed(31)
+        u_cam, u_sun = torch.rand(B, n, generator=g), torch.rand(B, n, generator=g)
+        sr = ref.satellite.define_satrays_from_tensors(rays, ts)
+        m.train(not ev)
+        with ref_harness.FixedRand([u_cam, u_sun]):
+            res, nren = ref.sat_rendering.render_image(m, None, sr, None, None, epoch_idx=epoch, chunk=B,
+                                                       render_step_size=step, eval=ev)
+        out_ref = torch.cat([res[k] for k in O.OUT_KEYS], 1)
+        if epoch < 2:
+            loss = torch.nn.functional.mse_loss(res["rgb"], pixels)
+        else:
+            loss, _ = ref.metrics.uncertainty_aware_loss(pixels, res["rgb"], res["beta"])
+        m.zero_grad()
+        loss.backward()
+        gref = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in m.named_parameters()}
+
+        osr = O.satrays_from_table(rays, ts)
+        if ev:
+            with torch.no_grad():
+                out_o, nren_o = O.render_chunk(p, osr, n, epoch, u_cam, u_sun, eval=True)
+            gora, loss_o = None, O.loss_from_out(out_o, pixels, epoch)
+        else:
+            loss_o, out_o, gora, nren_o = O.train_step_grads(p, osr, pixels, n, epoch, u_cam, u_sun)
+        assert nren == nren_o
+        assert torch.allclose(out_ref.detach(), out_o, rtol=1e-5, atol=1e-6), (out_ref.detach() - out_o).abs().max()
+        assert torch.allclose(loss.detach(), loss_o, rtol=1e-5)
+        fx = {f"{tag}_rays": rays.numpy(), f"{tag}_ts": ts.numpy(), f"{tag}_pixels": pixels.numpy(),
+              f"{tag}_u_cam": u_cam.numpy(), f"{tag}_u_sun": u_sun.numpy(), f"{tag}_n": np.int64(n),
+              f"{tag}_epoch": np.int64(epoch), f"{tag}_eval": np.int64(ev), f"{tag}_n_img": np.int64(n_img),
+              f"{tag}_out": out_ref.detach().numpy(), f"{tag}_loss": loss.detach().numpy(),
+              f"{tag}_n_rendering_samples": np.int64(nren), f"{tag}_fingerprint": param_fingerprint(p)}
+        if gora is not None:
+            for k in gref:
+                a, b = gref[k], gora[k]
+                assert torch.allclose(a, b, rtol=2e-4, atol=1e-7), (k, (a - b).abs().max(), a.abs().max())
+            fx[f"{tag}_grad_norms"] = np.array([float(gref[k].double().norm()) for k in gref])
+            fx[f"{tag}_grad_heads"] = np.stack([np.resize(gref[k].flatten()[:16].numpy(), 16) for k in gref])
+            fx[f"{tag}_grad_names"] = np.array(list(gref.keys()))
+        fixtures.update(fx)
+        print(f"render {tag}: n={n} n_rendering_samples={nren} loss={float(loss):.6f}")
+
+    # only_depth branch (sat_rendering.py:227-249)
+    B, n_img, n = 32, 6, 32
+    p = O.init_params(n_img, seed=21, bias_scale=0.05)
+    m = ref_model(ref, p, n_img)
+    rays, ts, _ = make_rays(B, n_img, seed=6, variant="spread")
+    u = torch.rand(B, n, generator=torch.Generator().manual_seed(32))
+    sr = ref.satellite.define_satrays_from_tensors(rays, ts)
+    with torch.no_grad(), ref_harness.FixedRand([u]):
+        res, nren = ref.sat_rendering.render_image(m, None, sr, None, None, epoch_idx=3, chunk=B,
+                                                   render_step_size=2.0 / n, only_depth=True)
+    osr = O.satrays_from_table(rays, ts)
+    ri, t0, t1, _ = O.satnerf_sampling(osr.origins, osr.viewdirs, n, u, near=osr.t_near)
+    with torch.no_grad():
+        d_o = O.render_depth(p, osr, t0, t1, ri)
+    assert torch.allclose(res["depth"], d_o, rtol=1e-5, atol=1e-6)
+    fixtures.update({"depth_rays": rays.numpy(), "depth_ts": ts.numpy(), "depth_u": u.numpy(),
+                     "depth_n": np.int64(n), "depth_out": res["depth"].numpy(),
+                     "depth_n_rendering_samples": np.int64(nren)})
+    np.savez_compressed(os.path.join(GOLD, "render.npz"), **fixtures)
+
+
+def gen_volrend(ref):
+    """nerfacc-form weights vs the reference's own dense dead-code twin weights_from_sigma (eonerf.py:37-54)."""
+    g = torch.Generator().manual_seed(41)
+    B, n = 16, 24
+    z = torch.sort(torch.rand(B, n, generator=g) * 2, dim=1).values
+    sig = torch.rand(B, n, generator=g) * 30
+    w_dense, t_dense, a_dense = ref.eonerf.weights_from_sigma(z, sig)
+    np.savez_compressed(os.path.join(GOLD, "volrend.npz"), z=z.numpy(), sigma=sig.numpy(),
+                        weights=w_dense.numpy(), trans=t_dense.numpy(), alphas=a_dense.numpy())
+    print("volrend: ok")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    os.makedirs(GOLD, exist_ok=True)
+    ref = ref_harness.load()
+    gen_sampling(ref)
+    gen_field(ref)
+    gen_volrend(ref)
+    gen_render(ref)
+    print("golden fixtures written to", GOLD)

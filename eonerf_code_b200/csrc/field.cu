@@ -1,0 +1,847 @@
+// Radiance-field MLP: EONerfMLP.forward / query_density (/root/reference/radiance_fields/eonerf.py:141-170),
+// MLP.forward (radiance_fields/mlp.py:87-101), SinusoidalEncoder.forward (mlp.py:190-208) and
+// VanillaNeRFRadianceField.forward (mlp.py:245-250) — forward and backward, layer by layer.
+//
+// Data layout in HBM (row-major, one row per sample, element type T = fp32 or bf16):
+//   stash  xf   fp32 [N,3]     sample positions (pos-enc backward needs full precision)
+//          cls  i32  [N]       image index per sample (class of the folded transient-embedding bias)
+//          H0..H3    T [N,256] post-ReLU trunk activations
+//          H4E       T [N,320] = [ h4 (256) | posenc(x) (63) | 0 ]   the skip concat of mlp.py:92-97 is a view:
+//                               layer 0 reads columns 256:320, layer 5 reads all 320 (K = 320)
+//          H5..H7    T [N,256]
+//          BOTT      T [N,256] bottleneck (vanilla: [N,288] = [bottleneck | posenc4(viewdir) (27) | 0])
+//          HD0       T [N,256] = [ albedo hidden (128) | transient hidden 0 (128) ]  (vanilla: [N,128])
+//          T1..T3    T [N,128] transient hidden 1..3
+//   The 4-d transient embedding (eonerf.py:165-167) never becomes a column: W[:,256:260]·emb[img] + b is a
+//   per-image bias row of a [n_img,256] table (`class_bias`) selected by `cls` in the GEMM epilogue.
+//
+// Every dense contraction goes through gemm_nt / gemm_tn (gemm.cuh): tcgen05 tensor cores in bf16 mode.
+// The 1- and 3-wide heads (sigma, albedo, transient scalar/beta) are warp-per-row fp32 dot products.
+#include <type_traits>
+
+#include "gemm.cuh"
+
+namespace eonerf {
+
+constexpr int kW = 256;       // trunk width (eonerf.py:73-75; --fc_units is never read)
+constexpr int kEnc = 64;      // 63 pos-enc columns + 1 zero pad
+constexpr int kH4E = kW + kEnc;
+constexpr int kHid = 128;
+constexpr int kDirEnc = 32;   // 27 view-enc columns + 5 zero pad
+constexpr float kHalfPi = 1.57079637050628662109375f;   // fl32(0.5*pi): torch adds the python scalar in fp32 (mlp.py:203)
+
+static inline int64_t align_up(int64_t v, int64_t a = 256) { return (v + a - 1) / a * a; }
+
+struct StashLayout {
+  int64_t xf, cls, h[8], bott, hd0, t[3], total;
+  int ld_bott, ld_hd0;
+};
+
+static StashLayout stash_layout(int field, int precision, int64_t n, int density_only) {
+  StashLayout L{};
+  int64_t es = elem_size(precision), off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes); return o; };
+  L.xf = take(n * 3 * 4);
+  L.cls = take(n * 4);
+  for (int i = 0; i < 8; ++i) L.h[i] = take(n * (i == 4 ? kH4E : kW) * es);
+  L.ld_bott = field == EONERF_FIELD_VANILLA ? kW + kDirEnc : kW;
+  L.ld_hd0 = field == EONERF_FIELD_VANILLA ? kHid : 2 * kHid;
+  if (!density_only) {
+    L.bott = take(n * L.ld_bott * es);
+    L.hd0 = take(n * L.ld_hd0 * es);
+    if (field == EONERF_FIELD_EONERF)
+      for (int i = 0; i < 3; ++i) L.t[i] = take(n * kHid * es);
+  }
+  L.total = off;
+  return L;
+}
+
+struct ScratchLayout {
+  int64_t ga, gb, gc, gat, g1, g2, dpre, dcb, total;
+};
+
+static ScratchLayout scratch_layout(int field, int precision, int64_t n, int64_t n_images) {
+  ScratchLayout L{};
+  int64_t es = elem_size(precision), off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes); return o; };
+  L.ga = take(n * kW * es);
+  L.gb = take(n * kH4E * es);
+  L.gc = take(n * (kW + kDirEnc) * es);
+  L.gat = take(n * 2 * kHid * es);
+  L.g1 = take(n * kHid * es);
+  L.g2 = take(n * kHid * es);
+  L.dpre = take(n * 8 * 4);
+  L.dcb = take((n_images > 0 ? n_images : 1) * kHid * 4);
+  L.total = off;
+  return L;
+}
+
+// prepared blob: for every matrix W [out, Kp] then W^T [Kp, out] in T, then the fp32 class-bias table
+struct PrepLayout {
+  int64_t w[8], wt[8];       // trunk
+  int64_t bott, bott_t;
+  int64_t hd0, hd0_t;        // eonerf: [256,256] = [albedo_mlp.0 ; transient_mlp.0[:, :256]]   vanilla: [128,288]
+  int64_t tr[3], tr_t[3];    // transient_mlp.{1,2,3}
+  int64_t class_bias;        // fp32 [n_img,256] = [ albedo_mlp.0.bias | transient_mlp.0.bias + W[:,256:260] emb[img] ]
+  int64_t total;
+};
+
+static int trunk_kp(int i) { return i == 0 ? kEnc : (i == 5 ? kH4E : kW); }
+static int trunk_k(int i) { return i == 0 ? 63 : (i == 5 ? 319 : kW); }
+
+static PrepLayout prep_layout(int field, int precision, int64_t n_images) {
+  PrepLayout L{};
+  int64_t es = elem_size(precision), off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes); return o; };
+  for (int i = 0; i < 8; ++i) { L.w[i] = take(kW * trunk_kp(i) * es); L.wt[i] = take(kW * trunk_kp(i) * es); }
+  L.bott = take(kW * kW * es); L.bott_t = take(kW * kW * es);
+  int64_t hd0 = field == EONERF_FIELD_VANILLA ? kHid * (kW + kDirEnc) : 2 * kHid * kW;
+  L.hd0 = take(hd0 * es); L.hd0_t = take(hd0 * es);
+  for (int i = 0; i < 3; ++i) { L.tr[i] = take(kHid * kHid * es); L.tr_t[i] = take(kHid * kHid * es); }
+  L.class_bias = take((n_images > 0 ? n_images : 1) * 2 * kHid * 4);
+  L.total = off;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepare: W fp32 [rows, k] (ld = ldw) -> dst [rows, kp] (zero padded) and dst_t [kp, rows]
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void convert_weight_kernel(const float* __restrict__ w, int64_t ldw, int rows, int k, int kp,
+                                      T* __restrict__ dst, int dst_row0, T* __restrict__ dst_t, int ld_t) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * kp) return;
+  int r = idx / kp, c = idx % kp;
+  float v = c < k ? __ldg(w + (int64_t)r * ldw + c) : 0.f;
+  dst[(int64_t)(dst_row0 + r) * kp + c] = from_f32<T>(v);
+  dst_t[(int64_t)c * ld_t + dst_row0 + r] = from_f32<T>(v);
+}
+
+static int convert_weight(int precision, const float* w, int64_t ldw, int rows, int k, int kp, void* dst, int dst_row0,
+                          void* dst_t, int ld_t, cudaStream_t s) {
+  int n = rows * kp;
+  if (precision == EONERF_PREC_FP32)
+    convert_weight_kernel<float><<<div_up(n, 256), 256, 0, s>>>(w, ldw, rows, k, kp, (float*)dst, dst_row0, (float*)dst_t, ld_t);
+  else
+    convert_weight_kernel<__nv_bfloat16><<<div_up(n, 256), 256, 0, s>>>(w, ldw, rows, k, kp, (__nv_bfloat16*)dst, dst_row0,
+                                                                       (__nv_bfloat16*)dst_t, ld_t);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+// class_bias[img, 0:128] = albedo_mlp.0.bias ; class_bias[img, 128:256] = transient_mlp.0.bias + W[:,256:260] emb[img]
+__global__ void class_bias_kernel(const float* __restrict__ ba0, const float* __restrict__ wt0, const float* __restrict__ bt0,
+                                  const float* __restrict__ emb, int64_t n_images, float* __restrict__ cb) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_images * 2 * kHid) return;
+  int img = idx / (2 * kHid), j = idx % (2 * kHid);
+  float v;
+  if (j < kHid) {
+    v = __ldg(ba0 + j);
+  } else {
+    int r = j - kHid;
+    v = __ldg(bt0 + r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v = fmaf(__ldg(wt0 + r * 260 + 256 + e), __ldg(emb + img * 4 + e), v);
+  }
+  cb[idx] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encode: positions (optionally derived from rays), image class, pos-enc columns of H4E
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) encode_kernel(EonerfFieldFwdArgs a, float* __restrict__ xf, int32_t* __restrict__ cls,
+                                                     T* __restrict__ h4e) {
+  // 64 consecutive threads own one sample: thread c writes pos-enc column c (coalesced 64*sizeof(T) bytes)
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t p = gid >> 6;
+  int c = (int)(gid & 63);
+  if (p >= a.n_pts) return;
+  float x[3];
+  int64_t ray = a.ray_indices ? __ldg(a.ray_indices + p) : -1;
+  if (a.x) {
+    x[0] = __ldg(a.x + 3 * p); x[1] = __ldg(a.x + 3 * p + 1); x[2] = __ldg(a.x + 3 * p + 2);
+  } else {
+    float ts = __ldg(a.t_starts + p), te = __ldg(a.t_ends + p);
+    float zm = __fdiv_rn(__fadd_rn(ts, te), 2.0f);                       // eonerf.py:206
+    const float* o = a.origins + ray * a.origins_stride;
+    const float* d = a.viewdirs + ray * a.viewdirs_stride;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) x[k] = __fadd_rn(__ldg(o + k), __fmul_rn(__ldg(d + k), zm));   // eonerf.py:207
+    if (c == 0 && a.z_mid) a.z_mid[p] = zm;
+  }
+  if (c < 3) xf[3 * p + c] = x[c];
+  if (c == 3 && cls) {
+    int64_t img = 0;
+    if (a.img_idx) img = a.ray_indices ? __ldg(a.img_idx + ray * a.img_idx_stride) : __ldg(a.img_idx + p * a.img_idx_stride);
+    cls[p] = (int32_t)img;
+  }
+  // mlp.py:199-205: [x, sin(2^k x) (freq-major, xyz-minor) k=0..9, sin(2^k x + pi/2)]
+  float v;
+  if (c < 3) v = x[c];
+  else if (c < 63) {
+    int e = c - 3;
+    int half = e >= 30;
+    e -= half * 30;
+    float xb = x[e % 3] * (float)(1 << (e / 3));
+    v = sinf(half ? __fadd_rn(xb, kHalfPi) : xb);
+  } else v = 0.f;
+  h4e[p * kH4E + kW + c] = from_f32<T>(v);
+}
+
+// view-direction encoding (L=4) -> BOTT[:, 256:288]  (vanilla field, mlp.py:153-165)
+template <class T>
+__global__ void __launch_bounds__(256) encode_dirs_kernel(const float* __restrict__ dirs, int64_t stride, int64_t n,
+                                                          T* __restrict__ dst, int64_t ld, int col0) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t p = gid >> 5;
+  int c = (int)(gid & 31);
+  if (p >= n) return;
+  float v = 0.f;
+  if (c < 3) v = __ldg(dirs + p * stride + c);
+  else if (c < 27) {
+    int e = c - 3;
+    int half = e >= 12;
+    e -= half * 12;
+    float xb = __ldg(dirs + p * stride + e % 3) * (float)(1 << (e / 3));
+    v = sinf(half ? __fadd_rn(xb, kHalfPi) : xb);
+  }
+  dst[p * ld + col0 + c] = from_f32<T>(v);
+}
+
+// g_x[c] = g_enc[c] + sum_k 2^k ( cos(2^k x_c) g_enc[3+3k+c] + cos(2^k x_c + pi/2) g_enc[33+3k+c] )
+// g_enc = ge0 (layer-0 input gradient) + ge5 (columns 256:319 of the layer-5 input gradient)
+template <class T>
+__global__ void __launch_bounds__(256) posenc_bwd_kernel(const float* __restrict__ xf, const T* __restrict__ ge0, int64_t ld0,
+                                                         const T* __restrict__ ge5, int64_t ld5, int64_t n,
+                                                         float* __restrict__ g_x) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t p = gid / 3;
+  int c = (int)(gid % 3);
+  if (p >= n) return;
+  float x = __ldg(xf + 3 * p + c);
+  auto ge = [&](int col) { return to_f32<T>(ge0[p * ld0 + col]) + to_f32<T>(ge5[p * ld5 + col]); };
+  float g = ge(c);
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    float s = (float)(1 << k), xb = x * s;
+    g += s * (cosf(xb) * ge(3 + 3 * k + c) + cosf(__fadd_rn(xb, kHalfPi)) * ge(33 + 3 * k + c));
+  }
+  g_x[3 * p + c] = g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// narrow heads: y_j = act_j( x . w_j + b_j ),  j < J <= 3      (warp per row, fp32 math)
+// act: 0 identity, 1 relu, 2 sigmoid (nn.Sigmoid), 3 softplus (nn.Softplus beta=1 threshold=20)
+// ------------------------------------------------------------------------------------------------
+struct Head {
+  const float* w; const float* b; int act;
+  float* out; int64_t out_stride;          // fwd: out[m*out_stride]
+  const float* y; const float* g;          // bwd: forward output and incoming gradient (same stride)
+};
+struct Heads {
+  int J; Head h[3];
+};
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  switch (act) {
+    case 1: return fmaxf(v, 0.f);
+    case 2: return 1.0f / (1.0f + expf(-v));
+    case 3: return v > 20.0f ? v : log1pf(expf(v));
+    default: return v;
+  }
+}
+// derivative expressed through the forward output y
+__device__ __forceinline__ float act_bwd(float y, int act) {
+  switch (act) {
+    case 1: return y > 0.f ? 1.f : 0.f;
+    case 2: return y * (1.0f - y);
+    case 3: return -expm1f(-y);            // sigmoid(pre) = 1 - exp(-softplus(pre)); -> 1 above the threshold
+    default: return 1.f;
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) heads_fwd_kernel(const T* __restrict__ x, int64_t ldx, int K, int64_t M, Heads H) {
+  int lane = threadIdx.x & 31;
+  int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int k = lane; k < K; k += 32) {
+    float xv = to_f32<T>(x[m * ldx + k]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (j < H.J) acc[j] = fmaf(xv, __ldg(H.h[j].w + k), acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j >= H.J) break;
+    float v = warp_sum(acc[j]);
+    if (lane == 0) H.h[j].out[m * H.h[j].out_stride] = act_fwd(v + __ldg(H.h[j].b), H.h[j].act);
+  }
+}
+
+// dpre[m, col0+j] = g_j * act'(y_j);  optionally dx[m,k] = (sum_j dpre_j w_j[k]) * (x[m,k] > 0)
+template <class T>
+__global__ void __launch_bounds__(256) heads_bwd_kernel(const T* __restrict__ x, int64_t ldx, int K, int64_t M, Heads H,
+                                                        float* __restrict__ dpre, int col0, T* __restrict__ dx, int64_t lddx) {
+  int lane = threadIdx.x & 31;
+  int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  float d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j >= H.J) break;
+    float g = H.h[j].g ? __ldg(H.h[j].g + m * H.h[j].out_stride) : 0.f;
+    d[j] = g * act_bwd(__ldg(H.h[j].y + m * H.h[j].out_stride), H.h[j].act);
+    if (lane == 0) dpre[m * 8 + col0 + j] = d[j];
+  }
+  if (!dx) return;
+  for (int k = lane; k < K; k += 32) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (j < H.J) v = fmaf(d[j], __ldg(H.h[j].w + k), v);
+    if (!(to_f32<T>(x[m * ldx + k]) > 0.f)) v = 0.f;
+    dx[m * lddx + k] = from_f32<T>(v);
+  }
+}
+
+// dw_j[k] += sum_m dpre[m,col0+j] x[m,k];  db_j += sum_m dpre[m,col0+j]
+struct HeadGrads {
+  float* dw[3]; float* db[3];
+};
+template <class T>
+__global__ void __launch_bounds__(256) heads_dw_kernel(const T* __restrict__ x, int64_t ldx, int K, int64_t M, int J,
+                                                       const float* __restrict__ dpre, int col0, HeadGrads G, int rows_per_block) {
+  int k = threadIdx.x;
+  int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  float acc[3] = {0.f, 0.f, 0.f}, bs[3] = {0.f, 0.f, 0.f};
+  for (int64_t m = m0; m < m1; ++m) {
+    float xv = k < K ? to_f32<T>(x[m * ldx + k]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j >= J) break;
+      float d = __ldg(dpre + m * 8 + col0 + j);
+      acc[j] = fmaf(d, xv, acc[j]);
+      bs[j] += d;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j >= J) break;
+    if (k < K) atomicAdd(G.dw[j] + k, acc[j]);
+    if (k == 0) atomicAdd(G.db[j], bs[j]);
+  }
+}
+
+// C[m,n] = (row[m*stride] * col[n]) masked by mask[m,n] > 0    (density-only backward: d h7)
+template <class T>
+__global__ void __launch_bounds__(256) rank1_mask_kernel(const float* __restrict__ row, int64_t stride, const float* __restrict__ col,
+                                                         const T* __restrict__ mask, int64_t ld_mask, int64_t M, int N,
+                                                         T* __restrict__ C, int64_t ldc) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t m = gid / N;
+  int n = (int)(gid % N);
+  if (m >= M) return;
+  float v = __ldg(row + m * stride) * __ldg(col + n);
+  if (!(to_f32<T>(mask[m * ld_mask + n]) > 0.f)) v = 0.f;
+  C[m * ldc + n] = from_f32<T>(v);
+}
+
+// dcb[img, j] += sum_{rows of class img} g[row, j]  (j < 128): block-private table in shared memory
+template <class T>
+__global__ void __launch_bounds__(128) class_grad_kernel(const T* __restrict__ g, int64_t ldg, const int32_t* __restrict__ cls,
+                                                         int64_t M, int64_t n_images, float* __restrict__ dcb, int rows_per_block,
+                                                         int use_smem) {
+  extern __shared__ float tab[];
+  int j = threadIdx.x;
+  int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  if (use_smem) {
+    for (int64_t i = j; i < n_images * kHid; i += kHid) tab[i] = 0.f;
+    __syncthreads();
+    for (int64_t m = m0; m < m1; ++m) tab[(int64_t)__ldg(cls + m) * kHid + j] += to_f32<T>(g[m * ldg + j]);   // thread j owns column j
+    __syncthreads();
+    for (int64_t i = j; i < n_images * kHid; i += kHid)
+      if (tab[i] != 0.f) atomicAdd(dcb + i, tab[i]);
+  } else {
+    for (int64_t m = m0; m < m1; ++m) atomicAdd(dcb + (int64_t)__ldg(cls + m) * kHid + j, to_f32<T>(g[m * ldg + j]));
+  }
+}
+
+// d emb[img,e] += sum_j dcb[img,j] W[j,256+e];   dW[j,256+e] += sum_img dcb[img,j] emb[img,e]
+__global__ void emb_grad_kernel(const float* __restrict__ dcb, const float* __restrict__ wt0, const float* __restrict__ emb,
+                                int64_t n_images, float* __restrict__ g_emb, float* __restrict__ g_wt0) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n_images * 4) {
+    int img = idx / 4, e = idx % 4;
+    float v = 0.f;
+    for (int j = 0; j < kHid; ++j) v = fmaf(__ldg(dcb + img * kHid + j), __ldg(wt0 + j * 260 + 256 + e), v);
+    if (g_emb) g_emb[idx] += v;
+  }
+  if (idx < kHid * 4 && g_wt0) {
+    int j = idx / 4, e = idx % 4;
+    float v = 0.f;
+    for (int64_t img = 0; img < n_images; ++img) v = fmaf(__ldg(dcb + img * kHid + j), __ldg(emb + img * 4 + e), v);
+    g_wt0[j * 260 + 256 + e] += v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side helpers
+// ------------------------------------------------------------------------------------------------
+#define EO_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != EONERF_OK) return _r; \
+  } while (0)
+
+template <class F>
+static int by_type(int precision, F&& f) {
+  if (precision == EONERF_PREC_FP32) return f((float*)nullptr);
+  return f((__nv_bfloat16*)nullptr);
+}
+
+static int run_heads_fwd(int precision, const void* x, int64_t ldx, int K, int64_t M, const Heads& H, cudaStream_t s) {
+  if (M == 0) return EONERF_OK;
+  return by_type(precision, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    heads_fwd_kernel<T><<<div_up(M, 8), 256, 0, s>>>((const T*)x, ldx, K, M, H);
+    EO_LAUNCH_CHECK();
+    return EONERF_OK;
+  });
+}
+
+static int run_heads_bwd(int precision, const void* x, int64_t ldx, int K, int64_t M, const Heads& H, float* dpre, int col0,
+                         void* dx, int64_t lddx, cudaStream_t s) {
+  if (M == 0) return EONERF_OK;
+  return by_type(precision, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    heads_bwd_kernel<T><<<div_up(M, 8), 256, 0, s>>>((const T*)x, ldx, K, M, H, dpre, col0, (T*)dx, lddx);
+    EO_LAUNCH_CHECK();
+    return EONERF_OK;
+  });
+}
+
+static int run_heads_dw(int precision, const void* x, int64_t ldx, int K, int64_t M, int J, const float* dpre, int col0,
+                        const HeadGrads& G, cudaStream_t s) {
+  if (M == 0) return EONERF_OK;
+  int rows = 256;
+  while (div_up(M, rows) > 4 * 148 && rows < 4096) rows *= 2;
+  return by_type(precision, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    heads_dw_kernel<T><<<div_up(M, rows), 256, 0, s>>>((const T*)x, ldx, K, M, J, dpre, col0, G, rows);
+    EO_LAUNCH_CHECK();
+    return EONERF_OK;
+  });
+}
+
+static inline char* at(const void* base, int64_t off) { return (char*)base + off; }
+
+static int field_prepare_impl(int field, int precision, const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
+  PrepLayout L = prep_layout(field, precision, p->n_images);
+  for (int i = 0; i < 8; ++i)
+    EO_TRY(convert_weight(precision, p->trunk_w[i], trunk_k(i), kW, trunk_k(i), trunk_kp(i), at(prepared, L.w[i]), 0,
+                          at(prepared, L.wt[i]), kW, s));
+  EO_TRY(convert_weight(precision, p->bott_w, kW, kW, kW, kW, at(prepared, L.bott), 0, at(prepared, L.bott_t), kW, s));
+  if (field == EONERF_FIELD_EONERF) {
+    EO_TRY(convert_weight(precision, p->head0_w, kW, kHid, kW, kW, at(prepared, L.hd0), 0, at(prepared, L.hd0_t), 2 * kHid, s));
+    EO_TRY(convert_weight(precision, p->trans_w[0], 260, kHid, kW, kW, at(prepared, L.hd0), kHid, at(prepared, L.hd0_t), 2 * kHid, s));
+    for (int i = 0; i < 3; ++i)
+      EO_TRY(convert_weight(precision, p->trans_w[i + 1], kHid, kHid, kHid, kHid, at(prepared, L.tr[i]), 0,
+                            at(prepared, L.tr_t[i]), kHid, s));
+    int n = (int)(p->n_images * 2 * kHid);
+    class_bias_kernel<<<div_up(n, 256), 256, 0, s>>>(p->head0_b, p->trans_w[0], p->trans_b[0], p->transient_emb, p->n_images,
+                                                      (float*)at(prepared, L.class_bias));
+    EO_LAUNCH_CHECK();
+  } else {
+    EO_TRY(convert_weight(precision, p->head0_w, 283, kHid, 283, kW + kDirEnc, at(prepared, L.hd0), 0, at(prepared, L.hd0_t), kHid, s));
+  }
+  return EONERF_OK;
+}
+
+static int field_fwd_impl(const EonerfFieldFwdArgs* a, cudaStream_t s) {
+  const int prec = a->precision, field = a->field;
+  const int64_t N = a->n_pts;
+  if (N == 0) return EONERF_OK;
+  const EonerfFieldParams* p = a->params;
+  StashLayout S = stash_layout(field, prec, N, a->density_only);
+  PrepLayout W = prep_layout(field, prec, p->n_images);
+  const int es = elem_size(prec);
+  char* st = (char*)a->stash;
+  const char* pr = (const char*)a->prepared;
+  bool want_cls = field == EONERF_FIELD_EONERF && !a->density_only;
+
+  EO_TRY(by_type(prec, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    encode_kernel<T><<<div_up(N * 64, 256), 256, 0, s>>>(*a, (float*)(st + S.xf), want_cls ? (int32_t*)(st + S.cls) : nullptr,
+                                                          (T*)(st + S.h[4]));
+    EO_LAUNCH_CHECK();
+    return EONERF_OK;
+  }));
+
+  // trunk: base_mlp (mlp.py:87-101), skip concat after layer index 4
+  for (int i = 0; i < 8; ++i) {
+    GemmNT g;
+    g.M = N; g.N = kW; g.K = trunk_kp(i);
+    if (i == 0) { g.A = st + S.h[4] + (int64_t)kW * es; g.lda = kH4E; }
+    else { g.A = st + S.h[i - 1]; g.lda = (i == 5) ? kH4E : kW; }
+    g.B = pr + W.w[i]; g.ldb = trunk_kp(i);
+    g.C = st + S.h[i]; g.ldc = (i == 4) ? kH4E : kW;
+    g.bias = p->trunk_b[i]; g.relu = 1;
+    EO_TRY(gemm_nt(prec, g, s));
+  }
+  {  // sigma head: softplus (eonerf.py:106,145) / relu (vanilla, mlp.py:250)
+    Heads H{};
+    H.J = 1;
+    H.h[0] = Head{p->sigma_w, p->sigma_b, field == EONERF_FIELD_EONERF ? 3 : 1, a->sigma, 1, nullptr, nullptr};
+    EO_TRY(run_heads_fwd(prec, st + S.h[7], kW, kW, N, H, s));
+  }
+  if (a->density_only) return EONERF_OK;
+
+  {  // bottleneck (no activation)
+    GemmNT g;
+    g.M = N; g.N = kW; g.K = kW;
+    g.A = st + S.h[7]; g.lda = kW; g.B = pr + W.bott; g.ldb = kW;
+    g.C = st + S.bott; g.ldc = S.ld_bott; g.bias = p->bott_b;
+    EO_TRY(gemm_nt(prec, g, s));
+  }
+  if (field == EONERF_FIELD_EONERF) {
+    {  // [albedo_mlp.0 | transient_mlp.0] in one GEMM; the embedding enters through the per-image bias row
+      GemmNT g;
+      g.M = N; g.N = 2 * kHid; g.K = kW;
+      g.A = st + S.bott; g.lda = kW; g.B = pr + W.hd0; g.ldb = kW;
+      g.C = st + S.hd0; g.ldc = 2 * kHid;
+      g.row_class = (const int32_t*)(st + S.cls); g.class_bias = (const float*)(pr + W.class_bias); g.ld_class = 2 * kHid;
+      g.relu = 1;
+      EO_TRY(gemm_nt(prec, g, s));
+    }
+    {
+      Heads H{};
+      H.J = 3;
+      for (int j = 0; j < 3; ++j) H.h[j] = Head{p->head1_w + j * kHid, p->head1_b + j, 2, a->rgb + j, 3, nullptr, nullptr};
+      EO_TRY(run_heads_fwd(prec, st + S.hd0, 2 * kHid, kHid, N, H, s));
+    }
+    for (int i = 0; i < 3; ++i) {
+      GemmNT g;
+      g.M = N; g.N = kHid; g.K = kHid;
+      if (i == 0) { g.A = st + S.hd0 + (int64_t)kHid * es; g.lda = 2 * kHid; }
+      else { g.A = st + S.t[i - 1]; g.lda = kHid; }
+      g.B = pr + W.tr[i]; g.ldb = kHid;
+      g.C = st + S.t[i]; g.ldc = kHid; g.bias = p->trans_b[i + 1]; g.relu = 1;
+      EO_TRY(gemm_nt(prec, g, s));
+    }
+    {
+      Heads H{};
+      H.J = 2;
+      H.h[0] = Head{p->ts_w, p->ts_b, 2, a->transient_s, 1, nullptr, nullptr};
+      H.h[1] = Head{p->tb_w, p->tb_b, 3, a->transient_beta, 1, nullptr, nullptr};
+      EO_TRY(run_heads_fwd(prec, st + S.t[2], kHid, kHid, N, H, s));
+    }
+  } else {
+    EO_REQUIRE(a->cond_dirs, "field_fwd: the vanilla field needs cond_dirs");
+    EO_TRY(by_type(prec, [&](auto* tag) {
+      using T = std::remove_pointer_t<decltype(tag)>;
+      encode_dirs_kernel<T><<<div_up(N * 32, 256), 256, 0, s>>>(a->cond_dirs, a->cond_dirs_stride, N, (T*)(st + S.bott), S.ld_bott, kW);
+      EO_LAUNCH_CHECK();
+      return EONERF_OK;
+    }));
+    GemmNT g;
+    g.M = N; g.N = kHid; g.K = kW + kDirEnc;
+    g.A = st + S.bott; g.lda = S.ld_bott; g.B = pr + W.hd0; g.ldb = kW + kDirEnc;
+    g.C = st + S.hd0; g.ldc = kHid; g.bias = p->head0_b; g.relu = 1;
+    EO_TRY(gemm_nt(prec, g, s));
+    Heads H{};
+    H.J = 3;
+    for (int j = 0; j < 3; ++j) H.h[j] = Head{p->head1_w + j * kHid, p->head1_b + j, 2, a->rgb + j, 3, nullptr, nullptr};
+    EO_TRY(run_heads_fwd(prec, st + S.hd0, kHid, kHid, N, H, s));
+  }
+  return EONERF_OK;
+}
+
+static int field_bwd_impl(const EonerfFieldBwdArgs* a, cudaStream_t s) {
+  const int prec = a->precision, field = a->field;
+  const int64_t N = a->n_pts;
+  if (N == 0) return EONERF_OK;
+  const EonerfFieldParams* p = a->params;
+  const EonerfFieldParams* G = a->grads;
+  StashLayout S = stash_layout(field, prec, N, a->density_only);
+  PrepLayout W = prep_layout(field, prec, p->n_images);
+  ScratchLayout C = scratch_layout(field, prec, N, p->n_images);
+  const int es = elem_size(prec);
+  const char* st = (const char*)a->stash;
+  const char* pr = (const char*)a->prepared;
+  char* sc = (char*)a->scratch;
+  float* dpre = (float*)(sc + C.dpre);
+  char *ga = sc + C.ga, *gb = sc + C.gb, *gc = sc + C.gc;
+
+  auto dW = [&](const void* dY, int64_t lddy, int n, const void* X, int64_t ldx, int k, float* dw, int64_t lddw, float* db) {
+    if (!G) return (int)EONERF_OK;
+    GemmTN t;
+    t.A = dY; t.lda = lddy; t.X = X; t.ldx = ldx; t.M = N; t.N = n; t.K = k; t.D = dw; t.ldd = lddw; t.dbias = db;
+    return gemm_tn(prec, t, s);
+  };
+
+  const int sigma_act = field == EONERF_FIELD_EONERF ? 3 : 1;
+  if (!a->density_only) {
+    char *gat = sc + C.gat, *g1 = sc + C.g1, *g2 = sc + C.g2;
+    if (field == EONERF_FIELD_EONERF) {
+      {  // transient_scalar / transient_beta heads -> d t3
+        Heads H{};
+        H.J = 2;
+        H.h[0] = Head{p->ts_w, p->ts_b, 2, nullptr, 1, a->transient_s, a->g_transient_s};
+        H.h[1] = Head{p->tb_w, p->tb_b, 3, nullptr, 1, a->transient_beta, a->g_transient_beta};
+        EO_TRY(run_heads_bwd(prec, st + S.t[2], kHid, kHid, N, H, dpre, 4, g1, kHid, s));
+        if (G) {
+          HeadGrads hg{{G->ts_w, G->tb_w, nullptr}, {G->ts_b, G->tb_b, nullptr}};
+          EO_TRY(run_heads_dw(prec, st + S.t[2], kHid, kHid, N, 2, dpre, 4, hg, s));
+        }
+      }
+      // transient_mlp.3, .2, .1
+      char* cur = g1;
+      char* nxt = g2;
+      for (int i = 2; i >= 0; --i) {
+        const char* X = (i == 0) ? st + S.hd0 + (int64_t)kHid * es : st + S.t[i - 1];
+        int64_t ldx = (i == 0) ? 2 * kHid : kHid;
+        EO_TRY(dW(cur, kHid, kHid, X, ldx, kHid, G ? G->trans_w[i + 1] : nullptr, kHid, G ? G->trans_b[i + 1] : nullptr));
+        GemmNT g;
+        g.M = N; g.N = kHid; g.K = kHid; g.A = cur; g.lda = kHid; g.B = pr + W.tr_t[i]; g.ldb = kHid;
+        if (i == 0) { g.C = gat + (int64_t)kHid * es; g.ldc = 2 * kHid; }
+        else { g.C = nxt; g.ldc = kHid; }
+        g.mask = X; g.ld_mask = ldx; g.mask_cols = kHid;
+        EO_TRY(gemm_nt(prec, g, s));
+        char* t = cur; cur = nxt; nxt = t;
+      }
+      {  // albedo head -> d a0 (columns 0:128 of GAT)
+        Heads H{};
+        H.J = 3;
+        for (int j = 0; j < 3; ++j) H.h[j] = Head{p->head1_w + j * kHid, p->head1_b + j, 2, nullptr, 3, a->rgb + j, a->g_rgb ? a->g_rgb + j : nullptr};
+        EO_TRY(run_heads_bwd(prec, st + S.hd0, 2 * kHid, kHid, N, H, dpre, 1, gat, 2 * kHid, s));
+        if (G) {
+          HeadGrads hg{{G->head1_w, G->head1_w + kHid, G->head1_w + 2 * kHid}, {G->head1_b, G->head1_b + 1, G->head1_b + 2}};
+          EO_TRY(run_heads_dw(prec, st + S.hd0, 2 * kHid, kHid, N, 3, dpre, 1, hg, s));
+        }
+      }
+      if (G) {
+        EO_TRY(dW(gat, 2 * kHid, kHid, st + S.bott, kW, kW, G->head0_w, kW, G->head0_b));
+        EO_TRY(dW(gat + (int64_t)kHid * es, 2 * kHid, kHid, st + S.bott, kW, kW, G->trans_w[0], 260, G->trans_b[0]));
+        // embedding / W[:,256:260] through the per-image bias rows
+        float* dcb = (float*)(sc + C.dcb);
+        EO_CUDA(cudaMemsetAsync(dcb, 0, p->n_images * kHid * 4, s));
+        int64_t tab_bytes = p->n_images * kHid * 4;
+        int use_smem = tab_bytes <= 40 * 1024;
+        int rows = 512;
+        while (div_up(N, rows) > 2 * 148 && rows < 8192) rows *= 2;
+        EO_TRY(by_type(prec, [&](auto* tag) {
+          using T = std::remove_pointer_t<decltype(tag)>;
+          class_grad_kernel<T><<<div_up(N, rows), kHid, use_smem ? tab_bytes : 0, s>>>(
+              (const T*)(gat + (int64_t)kHid * es), 2 * kHid, (const int32_t*)(st + S.cls), N, p->n_images, dcb, rows, use_smem);
+          EO_LAUNCH_CHECK();
+          return EONERF_OK;
+        }));
+        int nthreads = (int)(p->n_images * 4 > kHid * 4 ? p->n_images * 4 : kHid * 4);
+        emb_grad_kernel<<<div_up(nthreads, 128), 128, 0, s>>>(dcb, p->trans_w[0], p->transient_emb, p->n_images, G->transient_emb, G->trans_w[0]);
+        EO_LAUNCH_CHECK();
+      }
+      {  // d bottleneck = [d a0 | d t0] [W_a0 ; W_t0]
+        GemmNT g;
+        g.M = N; g.N = kW; g.K = 2 * kHid; g.A = gat; g.lda = 2 * kHid; g.B = pr + W.hd0_t; g.ldb = 2 * kHid;
+        g.C = gb; g.ldc = kW;
+        EO_TRY(gemm_nt(prec, g, s));
+      }
+    } else {
+      Heads H{};
+      H.J = 3;
+      for (int j = 0; j < 3; ++j) H.h[j] = Head{p->head1_w + j * kHid, p->head1_b + j, 2, nullptr, 3, a->rgb + j, a->g_rgb ? a->g_rgb + j : nullptr};
+      EO_TRY(run_heads_bwd(prec, st + S.hd0, kHid, kHid, N, H, dpre, 1, g1, kHid, s));
+      if (G) {
+        HeadGrads hg{{G->head1_w, G->head1_w + kHid, G->head1_w + 2 * kHid}, {G->head1_b, G->head1_b + 1, G->head1_b + 2}};
+        EO_TRY(run_heads_dw(prec, st + S.hd0, kHid, kHid, N, 3, dpre, 1, hg, s));
+        EO_TRY(dW(g1, kHid, kHid, st + S.bott, S.ld_bott, 283, G->head0_w, 283, G->head0_b));
+      }
+      GemmNT g;   // d [bottleneck | dir enc] — only the first 256 columns are needed
+      g.M = N; g.N = kW; g.K = kHid; g.A = g1; g.lda = kHid; g.B = pr + W.hd0_t; g.ldb = kHid;
+      g.C = gb; g.ldc = kW;
+      EO_TRY(gemm_nt(prec, g, s));
+    }
+    EO_TRY(dW(gb, kW, kW, st + S.h[7], kW, kW, G ? G->bott_w : nullptr, kW, G ? G->bott_b : nullptr));
+  }
+  {  // sigma head
+    Heads H{};
+    H.J = 1;
+    H.h[0] = Head{p->sigma_w, p->sigma_b, sigma_act, nullptr, 1, a->sigma, a->g_sigma};
+    EO_TRY(run_heads_bwd(prec, st + S.h[7], kW, kW, N, H, dpre, 0, nullptr, 0, s));
+    if (G) {
+      HeadGrads hg{{G->sigma_w, nullptr, nullptr}, {G->sigma_b, nullptr, nullptr}};
+      EO_TRY(run_heads_dw(prec, st + S.h[7], kW, kW, N, 1, dpre, 0, hg, s));
+    }
+  }
+  if (a->density_only) {
+    EO_TRY(by_type(prec, [&](auto* tag) {
+      using T = std::remove_pointer_t<decltype(tag)>;
+      rank1_mask_kernel<T><<<div_up(N * kW, 256), 256, 0, s>>>(dpre, 8, p->sigma_w, (const T*)(st + S.h[7]), kW, N, kW, (T*)ga, kW);
+      EO_LAUNCH_CHECK();
+      return EONERF_OK;
+    }));
+  } else {  // d h7 = (d bott W_b + d sigma_pre (x) w_sigma) masked
+    GemmNT g;
+    g.M = N; g.N = kW; g.K = kW; g.A = gb; g.lda = kW; g.B = pr + W.bott_t; g.ldb = kW;
+    g.C = ga; g.ldc = kW;
+    g.rank1_row = dpre; g.rank1_stride = 8; g.rank1_col = p->sigma_w;
+    g.mask = st + S.h[7]; g.ld_mask = kW; g.mask_cols = kW;
+    EO_TRY(gemm_nt(prec, g, s));
+  }
+
+  // trunk backward.  `cur` holds d(pre-activation) of layer i.
+  const bool want_x = a->g_x != nullptr;
+  char* cur = ga; int64_t ld_cur = kW;
+  // layer 7 -> gb (ld 256) ; 6 -> ga ; 5 -> gb (ld 320, incl. d enc) ; 4 -> ga ; 3 -> gc ; 2 -> ga ; 1 -> gc ; 0 -> ga[:, :64]
+  char* dst_of[8] = {ga, gc, ga, gc, ga, gb, ga, gb};
+  for (int i = 7; i >= 0; --i) {
+    const char* X; int64_t ldx;
+    if (i == 0) { X = st + S.h[4] + (int64_t)kW * es; ldx = kH4E; }
+    else { X = st + S.h[i - 1]; ldx = (i == 5) ? kH4E : kW; }
+    EO_TRY(dW(cur, ld_cur, kW, X, ldx, trunk_k(i), G ? G->trunk_w[i] : nullptr, trunk_k(i), G ? G->trunk_b[i] : nullptr));
+    if (i == 0 && !want_x) break;
+    GemmNT g;
+    g.M = N; g.K = kW; g.A = cur; g.lda = ld_cur; g.B = pr + W.wt[i]; g.ldb = kW;
+    g.C = dst_of[i];
+    if (i == 0) { g.N = kEnc; g.ldc = kW; }
+    else if (i == 5) { g.N = want_x ? kH4E : kW; g.ldc = kH4E; g.mask = X; g.ld_mask = kH4E; g.mask_cols = kW; }
+    else { g.N = kW; g.ldc = kW; g.mask = X; g.ld_mask = kW; g.mask_cols = kW; }
+    EO_TRY(gemm_nt(prec, g, s));
+    cur = dst_of[i]; ld_cur = g.ldc;
+  }
+  if (want_x) {
+    EO_TRY(by_type(prec, [&](auto* tag) {
+      using T = std::remove_pointer_t<decltype(tag)>;
+      posenc_bwd_kernel<T><<<div_up(N * 3, 256), 256, 0, s>>>((const float*)(st + S.xf), (const T*)ga, kW,
+                                                               (const T*)(gb + (int64_t)kW * es), kH4E, N, a->g_x);
+      EO_LAUNCH_CHECK();
+      return EONERF_OK;
+    }));
+  }
+  return EONERF_OK;
+}
+
+}  // namespace eonerf
+
+using namespace eonerf;
+
+static bool valid_prec(int p) { return p == EONERF_PREC_FP32 || p == EONERF_PREC_BF16 || p == EONERF_PREC_BF16_SIMT; }
+static bool valid_field(int f) { return f == EONERF_FIELD_EONERF || f == EONERF_FIELD_VANILLA; }
+
+extern "C" int64_t eonerf_field_prepared_bytes(int32_t field, int32_t precision, int64_t n_images) {
+  if (!valid_prec(precision) || !valid_field(field)) return -1;
+  return prep_layout(field, precision, n_images).total;
+}
+extern "C" int64_t eonerf_field_stash_bytes(int32_t field, int32_t precision, int64_t n_pts, int32_t density_only) {
+  if (!valid_prec(precision) || !valid_field(field) || n_pts < 0) return -1;
+  return stash_layout(field, precision, n_pts, density_only).total;
+}
+extern "C" int64_t eonerf_field_scratch_bytes(int32_t field, int32_t precision, int64_t n_pts, int64_t n_images) {
+  if (!valid_prec(precision) || !valid_field(field) || n_pts < 0) return -1;
+  return scratch_layout(field, precision, n_pts, n_images).total;
+}
+
+extern "C" int eonerf_field_prepare(int32_t field, int32_t precision, const EonerfFieldParams* params, void* prepared,
+                                    eonerf_stream_t stream) {
+  EO_REQUIRE(valid_prec(precision) && valid_field(field), "field_prepare: bad field/precision %d/%d", field, precision);
+  EO_REQUIRE(params && prepared, "field_prepare: null pointer");
+  EO_REQUIRE(field == EONERF_FIELD_VANILLA || (params->n_images > 0 && params->transient_emb), "field_prepare: need n_images > 0");
+  return field_prepare_impl(field, precision, params, prepared, as_stream(stream));
+}
+
+extern "C" int eonerf_field_fwd(const EonerfFieldFwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && valid_prec(a->precision) && valid_field(a->field), "field_fwd: bad field/precision");
+  EO_REQUIRE(a->n_pts >= 0, "field_fwd: negative n_pts");
+  if (a->n_pts == 0) return EONERF_OK;
+  EO_REQUIRE(a->params && a->prepared && a->stash && a->sigma, "field_fwd: null pointer");
+  EO_REQUIRE(a->x || (a->origins && a->viewdirs && a->ray_indices && a->t_starts && a->t_ends),
+             "field_fwd: give x or (origins, viewdirs, ray_indices, t_starts, t_ends)");
+  EO_REQUIRE(a->density_only || a->rgb, "field_fwd: null rgb output");
+  EO_REQUIRE(a->density_only || a->field == EONERF_FIELD_VANILLA || (a->transient_s && a->transient_beta && a->img_idx),
+             "field_fwd: the eonerf field needs img_idx and the transient outputs");
+  return field_fwd_impl(a, as_stream(stream));
+}
+
+extern "C" int eonerf_field_bwd(const EonerfFieldBwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && valid_prec(a->precision) && valid_field(a->field), "field_bwd: bad field/precision");
+  EO_REQUIRE(a->n_pts >= 0, "field_bwd: negative n_pts");
+  if (a->n_pts == 0) return EONERF_OK;
+  EO_REQUIRE(a->params && a->prepared && a->stash && a->scratch && a->sigma, "field_bwd: null pointer");
+  EO_REQUIRE(a->density_only || a->rgb, "field_bwd: null rgb");
+  EO_REQUIRE(a->density_only || a->field == EONERF_FIELD_VANILLA || (a->transient_s && a->transient_beta),
+             "field_bwd: the eonerf field needs the transient forward outputs");
+  return field_bwd_impl(a, as_stream(stream));
+}
+
+// ---- per-ray ambient colour (eonerf.py:163-164): enc4(sun) -> 128 relu -> 3 sigmoid, fp32 ----------
+// stash floats per ray: [enc 32 | hidden 128]; scratch: [d hidden 128 | dpre 8]
+extern "C" int eonerf_ambient_fwd(const EonerfAmbientFwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->n_rays >= 0, "ambient_fwd: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->sundirs && a->w0 && a->b0 && a->w1 && a->b1 && a->stash && a->ambient, "ambient_fwd: null pointer");
+  cudaStream_t s = as_stream(stream);
+  int64_t B = a->n_rays;
+  float* enc = a->stash;
+  float* hid = a->stash + B * kDirEnc;
+  encode_dirs_kernel<float><<<div_up(B * 32, 256), 256, 0, s>>>(a->sundirs, a->sundirs_stride, B, enc, kDirEnc, 0);
+  EO_LAUNCH_CHECK();
+  GemmNT g;
+  g.M = B; g.N = kHid; g.K = 27; g.A = enc; g.lda = kDirEnc; g.B = a->w0; g.ldb = 27; g.C = hid; g.ldc = kHid;
+  g.bias = a->b0; g.relu = 1;
+  EO_TRY(gemm_nt_simt(kF32, g, s));
+  Heads H{};
+  H.J = 3;
+  for (int j = 0; j < 3; ++j) H.h[j] = Head{a->w1 + j * kHid, a->b1 + j, 2, a->ambient + j, 3, nullptr, nullptr};
+  return run_heads_fwd(EONERF_PREC_FP32, hid, kHid, kHid, B, H, s);
+}
+
+extern "C" int eonerf_ambient_bwd(const EonerfAmbientBwdArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->n_rays >= 0, "ambient_bwd: bad arguments");
+  if (a->n_rays == 0) return EONERF_OK;
+  EO_REQUIRE(a->w0 && a->w1 && a->stash && a->scratch && a->ambient && a->g_ambient && a->g_w0 && a->g_b0 && a->g_w1 && a->g_b1,
+             "ambient_bwd: null pointer");
+  cudaStream_t s = as_stream(stream);
+  int64_t B = a->n_rays;
+  const float* enc = a->stash;
+  const float* hid = a->stash + B * kDirEnc;
+  float* dh = a->scratch;
+  float* dpre = a->scratch + B * kHid;
+  Heads H{};
+  H.J = 3;
+  for (int j = 0; j < 3; ++j) H.h[j] = Head{a->w1 + j * kHid, nullptr, 2, nullptr, 3, a->ambient + j, a->g_ambient + j};
+  EO_TRY(run_heads_bwd(EONERF_PREC_FP32, hid, kHid, kHid, B, H, dpre, 0, dh, kHid, s));
+  HeadGrads hg{{a->g_w1, a->g_w1 + kHid, a->g_w1 + 2 * kHid}, {a->g_b1, a->g_b1 + 1, a->g_b1 + 2}};
+  EO_TRY(run_heads_dw(EONERF_PREC_FP32, hid, kHid, kHid, B, 3, dpre, 0, hg, s));
+  GemmTN t;
+  t.A = dh; t.lda = kHid; t.X = enc; t.ldx = kDirEnc; t.M = B; t.N = kHid; t.K = 27; t.D = a->g_w0; t.ldd = 27; t.dbias = a->g_b0;
+  return gemm_tn_simt(kF32, t, s);
+}
+
+// ---- building blocks ---------------------------------------------------------------------------
+extern "C" int eonerf_linear_fwd(const EonerfLinearArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && valid_prec(a->precision), "linear_fwd: bad precision");
+  EO_REQUIRE(a->m >= 0 && a->n > 0 && a->k > 0, "linear_fwd: bad shape");
+  if (a->m == 0) return EONERF_OK;
+  EO_REQUIRE(a->x && a->w && a->y, "linear_fwd: null pointer");
+  GemmNT g;
+  g.A = a->x; g.lda = a->ldx; g.B = a->w; g.ldb = a->ldw; g.C = a->y; g.ldc = a->ldy;
+  g.M = a->m; g.N = a->n; g.K = a->k; g.bias = a->bias; g.relu = a->act == 1;
+  return gemm_nt(a->precision, g, as_stream(stream));
+}
+
+extern "C" int eonerf_linear_dw(const EonerfDwArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && valid_prec(a->precision), "linear_dw: bad precision");
+  EO_REQUIRE(a->m >= 0 && a->n > 0 && a->k > 0, "linear_dw: bad shape");
+  if (a->m == 0) return EONERF_OK;
+  EO_REQUIRE(a->dy && a->x && a->dw, "linear_dw: null pointer");
+  GemmTN t;
+  t.A = a->dy; t.lda = a->lddy; t.X = a->x; t.ldx = a->ldx; t.M = a->m; t.N = a->n; t.K = a->k;
+  t.D = a->dw; t.ldd = a->lddw; t.dbias = a->db;
+  return gemm_tn(a->precision, t, as_stream(stream));
+}

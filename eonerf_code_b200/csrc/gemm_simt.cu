@@ -1,17 +1,19 @@
-// fp32 SIMT GEMMs — the exactness mode of the radiance-field MLP (EONERF_PREC_FP32).
-// Plain 64x64 register-tiled kernels: they exist so that the whole rendering path can be compared with
-// the fp32 reference at 1e-5 without bf16 rounding in the way; the production path is gemm_tc.cu.
+// SIMT GEMMs of the radiance-field MLP — fp32 storage (EONERF_PREC_FP32: the exactness mode, so that the
+// whole rendering path can be compared with the fp32 reference at 1e-5 without bf16 rounding in the way)
+// and bf16 storage with fp32 accumulation (EONERF_PREC_BF16_SIMT: the on-device cross-check of the tcgen05
+// kernels in gemm_tc.cu, which are the production path).  Plain 64x64 register-tiled kernels.
 #include "gemm.cuh"
 
 namespace eonerf {
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
-__global__ void __launch_bounds__(256) gemm_nt_f32_kernel(GemmNT g) {
+template <class T>
+__global__ void __launch_bounds__(256) gemm_nt_simt_kernel(GemmNT g) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
-  const float* A = (const float*)g.A;
-  const float* B = (const float*)g.B;
+  const T* A = (const T*)g.A;
+  const T* B = (const T*)g.B;
   int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   int64_t m0 = (int64_t)blockIdx.x * BM;
   int n0 = blockIdx.y * BN;
@@ -23,8 +25,8 @@ __global__ void __launch_bounds__(256) gemm_nt_f32_kernel(GemmNT g) {
       int row = e >> 4, kk = e & 15;
       int64_t m = m0 + row;
       int n = n0 + row, k = k0 + kk;
-      As[kk][row] = (m < g.M && k < g.K) ? __ldg(A + m * g.lda + k) : 0.f;
-      Bs[kk][row] = (n < g.N && k < g.K) ? __ldg(B + (int64_t)n * g.ldb + k) : 0.f;
+      As[kk][row] = (m < g.M && k < g.K) ? to_f32<T>(A[m * g.lda + k]) : 0.f;
+      Bs[kk][row] = (n < g.N && k < g.K) ? to_f32<T>(B[(int64_t)n * g.ldb + k]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -41,34 +43,38 @@ __global__ void __launch_bounds__(256) gemm_nt_f32_kernel(GemmNT g) {
     }
     __syncthreads();
   }
-  float* C = (float*)g.C;
-  const float* add = (const float*)g.addend;
-  const float* mask = (const float*)g.mask;
+  T* C = (T*)g.C;
+  const T* add = (const T*)g.addend;
+  const T* mask = (const T*)g.mask;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int64_t m = m0 + ty * 4 + i;
     if (m >= g.M) continue;
-    const float* brow = g.class_bias ? g.class_bias + (int64_t)__ldg(g.row_class + m) * g.N : g.bias;
+    const float* brow = g.class_bias ? g.class_bias + (int64_t)__ldg(g.row_class + m) * g.ld_class : g.bias;
+    float r1 = g.rank1_row ? __ldg(g.rank1_row + m * g.rank1_stride) : 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
       if (n >= g.N) continue;
       float v = acc[i][j];
       if (brow) v += __ldg(brow + n);
-      if (add) v += add[m * g.ld_add + n];
+      if (add) v += to_f32<T>(add[m * g.ld_add + n]);
+      if (g.rank1_row) v += r1 * __ldg(g.rank1_col + n);
       if (g.relu) v = fmaxf(v, 0.f);
-      if (mask && n < g.mask_cols && !(mask[m * g.ld_mask + n] > 0.f)) v = 0.f;
-      C[m * g.ldc + n] = v;
+      if (mask && n < g.mask_cols && !(to_f32<T>(mask[m * g.ld_mask + n]) > 0.f)) v = 0.f;
+      C[m * g.ldc + n] = from_f32<T>(v);
     }
   }
 }
 
-// D[n,k] += sum_m A[m,n] X[m,k]; grid = (N tiles, K tiles, M splits)
-__global__ void __launch_bounds__(256) gemm_tn_f32_kernel(GemmTN g, int64_t rows_per_split) {
+// D[n,k] += sum_m A[m,n] X[m,k]; grid = (N tiles, K tiles, M splits); split-M partial sums are combined
+// with fp32 atomics (order-dependent at the 1e-7 level, like the reference's own index_add_/cuBLAS split-K).
+template <class T>
+__global__ void __launch_bounds__(256) gemm_tn_simt_kernel(GemmTN g, int64_t rows_per_split) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Xs[BK][BN + 4];
-  const float* A = (const float*)g.A;
-  const float* X = (const float*)g.X;
+  const T* A = (const T*)g.A;
+  const T* X = (const T*)g.X;
   int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   int n0 = blockIdx.x * BM, k0 = blockIdx.y * BN;
   int64_t mb = (int64_t)blockIdx.z * rows_per_split;
@@ -82,8 +88,8 @@ __global__ void __launch_bounds__(256) gemm_tn_f32_kernel(GemmTN g, int64_t rows
       int e = tid + l * 256;
       int mm = e >> 6, c = e & 63;
       int64_t m = m0 + mm;
-      As[mm][c] = (m < me && n0 + c < g.N) ? __ldg(A + m * g.lda + n0 + c) : 0.f;
-      Xs[mm][c] = (m < me && k0 + c < g.K) ? __ldg(X + m * g.ldx + k0 + c) : 0.f;
+      As[mm][c] = (m < me && n0 + c < g.N) ? to_f32<T>(A[m * g.lda + n0 + c]) : 0.f;
+      Xs[mm][c] = (m < me && k0 + c < g.K) ? to_f32<T>(X[m * g.ldx + k0 + c]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -107,6 +113,7 @@ __global__ void __launch_bounds__(256) gemm_tn_f32_kernel(GemmTN g, int64_t rows
     int n = n0 + ty * 4 + i;
     if (n >= g.N) continue;
     if (do_bias) atomicAdd(g.dbias + n, bsum[i]);
+    if (!g.D) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int k = k0 + tx * 4 + j;
@@ -115,15 +122,16 @@ __global__ void __launch_bounds__(256) gemm_tn_f32_kernel(GemmTN g, int64_t rows
   }
 }
 
-int gemm_nt_f32(const GemmNT& g, cudaStream_t s) {
+int gemm_nt_simt(ElemType t, const GemmNT& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return EONERF_OK;
   dim3 grid(div_up(g.M, BM), div_up(g.N, BN));
-  gemm_nt_f32_kernel<<<grid, 256, 0, s>>>(g);
+  if (t == kF32) gemm_nt_simt_kernel<float><<<grid, 256, 0, s>>>(g);
+  else gemm_nt_simt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
 
-int gemm_tn_f32(const GemmTN& g, cudaStream_t s) {
+int gemm_tn_simt(ElemType t, const GemmTN& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return EONERF_OK;
   int tn = div_up(g.N, BM), tk = div_up(g.K, BN);
   int64_t want = (2 * 148 + tn * tk - 1) / (tn * tk);
@@ -134,7 +142,8 @@ int gemm_tn_f32(const GemmTN& g, cudaStream_t s) {
   rows = (rows + BK - 1) / BK * BK;
   split = (g.M + rows - 1) / rows;
   dim3 grid(tn, tk, (unsigned)split);
-  gemm_tn_f32_kernel<<<grid, 256, 0, s>>>(g, rows);
+  if (t == kF32) gemm_tn_simt_kernel<float><<<grid, 256, 0, s>>>(g, rows);
+  else gemm_tn_simt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, rows);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }

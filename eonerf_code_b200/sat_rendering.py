@@ -1,0 +1,117 @@
+"""Drop-in for /root/reference/sat_rendering.py (the live functions: :10-22, :46-118, :176-335).
+
+Same names, argument meaning and return values; the arithmetic runs in sm_100a kernels (csrc/sampling.cu,
+csrc/render.cu, csrc/field.cu).  Random numbers are drawn with torch on the device in the reference's
+order (camera, [camera re-draw], sun — SURVEY.md Appendix C), or passed in explicitly for parity tests.
+"""
+from typing import Optional
+
+import torch
+
+from . import ops
+from .datasets.satellite import SatRays, namedtuple_map  # noqa: F401
+
+OUT_SLICES = (("rgb", 0, 3), ("depth", 3, 4), ("albedo_rgb", 4, 7), ("ambient_rgb", 7, 10), ("geo_shadows", 10, 11),
+              ("transient_s", 11, 12), ("beta", 12, 13), ("entropy", 13, 14), ("pts_per_ray", 14, 15),
+              ("sc_pts_per_ray", 15, 16), ("opacity_after_surface", 16, 18), ("shadowless_rgb", 18, 21))
+
+
+def n_samples_from_step(render_step_size):
+    return int(2 / render_step_size)                       # sat_rendering.py:64
+
+
+def count_number_of_pts_per_nerfacc_ray(rays, ray_indices):
+    """sat_rendering.py:10-16: fp32 histogram of ray_indices."""
+    n_rays = rays.origins.shape[0]
+    offs = ops.pack_info(ray_indices, n_rays)
+    return (offs[1:] - offs[:-1]).to(torch.float32)
+
+
+def _sample(origins, viewdirs, n_samples, near, u, z_steps):
+    if u is None:
+        u = torch.rand(origins.shape[0], n_samples, dtype=torch.float32, device=origins.device)   # :52
+    ri, ts, te, ppr, offs, stats = ops.sample_compact(origins, viewdirs, near, u, z_steps)
+    P, n_empty = stats.tolist()                            # one host sync (the reference has >= 3 here)
+    return ri[:P], ts[:P], te[:P], ppr, offs, n_empty
+
+
+def satnerf_sampling(origins, viewdirs, sampling_args, near=None, far=None, perturb=True, u=None, z_steps=None):
+    """sat_rendering.py:56-84 -> (ray_indices i64[P], t_starts[P], t_ends[P]).  `u` [B,n] overrides the uniforms."""
+    if far is not None:
+        raise NotImplementedError("far != near + 2 is never used by the reference (sat_rendering.py:60-63)")
+    n = n_samples_from_step(sampling_args["render_step_size"])
+    if not perturb:
+        raise NotImplementedError("perturb=False is not reachable from the reference's call sites (every caller uses the default)")
+    ri, ts, te, _, _, _ = _sample(origins, viewdirs, n, near, u, z_steps)
+    return ri, ts, te
+
+
+def compute_geometric_shadows(chunk_rays, depth, radiance_field, occupancy_grid, sampling_args, u=None, z_steps=None,
+                              info=None):
+    """sat_rendering.py:87-118 -> (geo_shadow[B,1], sc_pts_per_ray[B]); differentiable in depth and the parameters."""
+    e = radiance_field._engine()
+    n = n_samples_from_step(sampling_args["render_step_size"])
+    info = {} if info is None else info
+    geo = ops._SunPassFn.apply(e, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs, depth, n, u, z_steps, info,
+                               *e.tensors())
+    return geo, info["sc_pts_per_ray"]
+
+
+def render_image(
+    radiance_field: torch.nn.Module,
+    occupancy_grid,
+    rays: SatRays,
+    scene_aabb: torch.Tensor,
+    args,
+    epoch_idx: Optional[int] = None,
+    chunk: int = 5120,
+    near_plane: Optional[float] = None,
+    far_plane: Optional[float] = None,
+    render_step_size: float = 1e-3,
+    render_bkgd: Optional[torch.Tensor] = None,
+    cone_angle: float = 0.0,
+    alpha_thre: float = 0.0,
+    early_stop_eps: float = 0.0,
+    timestamps: Optional[torch.Tensor] = None,
+    only_depth: bool = False,
+    eval: bool = False,
+    uniforms=None,
+    z_steps=None,
+):
+    """sat_rendering.py:176-335 -> (dict of 12 [..., C] tensors (or {"depth"}), n_rendering_samples).
+    `uniforms`: optional list with one dict per chunk {u_cam, u_sun, u_cam2} replacing the device RNG."""
+    rays_shape = rays.origins.shape
+    if len(rays_shape) == 3:
+        num_rays = rays_shape[0] * rays_shape[1]
+        rays = namedtuple_map(lambda r: r.reshape([num_rays] + list(r.shape[2:])), rays)
+    else:
+        num_rays = rays_shape[0]
+    sampling_args = {"render_step_size": render_step_size}
+    n = n_samples_from_step(render_step_size)
+    e = radiance_field._engine()
+    outs, n_rendering_samples = [], 0
+    for ci, i in enumerate(range(0, num_rays, chunk)):
+        chunk_rays = namedtuple_map(lambda r: r[i:i + chunk], rays)
+        us = uniforms[ci] if uniforms is not None else {}
+        ri, ts, te, ppr, offs, n_empty = _sample(chunk_rays.origins, chunk_rays.viewdirs, n, chunk_rays.t_near,
+                                                 us.get("u_cam"), z_steps)
+        if n_empty:                                         # :260-262 re-draw with near=None
+            ri, ts, te, _, offs, _ = _sample(chunk_rays.origins, chunk_rays.viewdirs, n, None, us.get("u_cam2"), z_steps)
+        n_rendering_samples += ts.numel()
+        comp = ops._CameraPassFn.apply(e, only_depth, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs,
+                                       chunk_rays.img_idx, ri, ts, te, offs, *e.tensors())
+        if only_depth:                                      # :227-249
+            outs.append(comp[:, 3:4])
+            continue
+        geo = sc_ppr = None
+        if epoch_idx >= 2:                                  # :269-276
+            info = {}
+            geo = ops._SunPassFn.apply(e, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs, comp[:, 3:4], n,
+                                       us.get("u_sun"), z_steps, info, *e.tensors())
+            sc_ppr = info["sc_pts_per_ray"]
+        rad = radiance_field.radiometricT_enc.weight if radiance_field.radiometric_normalization else None
+        outs.append(ops._EpilogueFn.apply(comp, geo, ppr, sc_ppr, chunk_rays.img_idx, eval, rad, e.n_images))
+    out = torch.cat(outs, dim=0) if len(outs) != 1 else outs[0]
+    if only_depth:
+        return {"depth": out.view((*rays_shape[:-1], -1))}, n_rendering_samples
+    return {k: out[:, a:b].view((*rays_shape[:-1], -1)) for k, a, b in OUT_SLICES}, n_rendering_samples

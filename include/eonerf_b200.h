@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 4
+#define EONERF_ABI_VERSION 5
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -219,11 +219,13 @@ int eonerf_epilogue_bwd(const EonerfEpilogueBwdArgs* a, eonerf_stream_t stream);
  * MLP.forward (radiance_fields/mlp.py:87-101), SinusoidalEncoder.forward (mlp.py:190-208) and, for
  * BASELINE config 2, VanillaNeRFRadianceField.forward (mlp.py:245-250) — forward and backward.
  *
- * precision: EONERF_PREC_FP32  SIMT fp32 kernels (exactness mode, used for tight parity tests)
- *            EONERF_PREC_BF16  tcgen05/TMEM tensor-core kernels, bf16 operands, fp32 accumulation
+ * precision: EONERF_PREC_FP32       fp32 storage, SIMT kernels (exactness mode, used for the 1e-5 parity tests)
+ *            EONERF_PREC_BF16       bf16 storage, tcgen05/TMEM/TMA tensor-core GEMMs, fp32 accumulation
+ *            EONERF_PREC_BF16_SIMT  bf16 storage, SIMT GEMMs (on-device cross-check of the tensor-core kernels)
  * ---------------------------------------------------------------------------------------------- */
 #define EONERF_PREC_FP32 0
 #define EONERF_PREC_BF16 1
+#define EONERF_PREC_BF16_SIMT 2
 
 #define EONERF_FIELD_EONERF 0
 #define EONERF_FIELD_VANILLA 1
@@ -239,25 +241,24 @@ typedef struct {
   float* trans_w[4]; float* trans_b[4];     /* transient_mlp.hidden_layers.{0..3}: (128,260) (128,128)x3  (eonerf only) */
   float* ts_w; float* ts_b;                 /* transient_scalar (1,128) (1) */
   float* tb_w; float* tb_b;                 /* transient_beta   (1,128) (1) */
-  float* amb0_w; float* amb0_b;             /* ambient_mlp.hidden_layers.0 (128,27) (128) */
-  float* amb1_w; float* amb1_b;             /* ambient_mlp.output_layer   (3,128) (3) */
   float* transient_emb;                     /* (n_img,4) */
   int64_t n_images;
 } EonerfFieldParams;
 
 /* bytes of the prepared-parameter blob / of the forward stash / of the backward scratch */
-int64_t eonerf_field_prepared_bytes(int32_t field, int32_t precision);
-int64_t eonerf_field_stash_bytes(int32_t field, int32_t precision, int64_t n_pts, int64_t n_images, int32_t density_only);
+int64_t eonerf_field_prepared_bytes(int32_t field, int32_t precision, int64_t n_images);
+int64_t eonerf_field_stash_bytes(int32_t field, int32_t precision, int64_t n_pts, int32_t density_only);
 int64_t eonerf_field_scratch_bytes(int32_t field, int32_t precision, int64_t n_pts, int64_t n_images);
 
-/* Convert the fp32 master weight matrices into the kernels' operand layouts: K padded to a multiple of
- * 8 elements, W [out,Kp] and W^T [Kp,out], fp32 or bf16.  Call once per optimiser step. */
+/* Convert the fp32 master weight matrices into the kernels' operand layouts (K padded, W [out,Kp] and
+ * W^T [Kp,out], fp32 or bf16) and build the per-image bias table that folds the 4-d transient embedding
+ * into layer transient_mlp.0 (eonerf.py:165-167).  Call after every optimiser step. */
 int eonerf_field_prepare(int32_t field, int32_t precision, const EonerfFieldParams* params, void* prepared,
                          eonerf_stream_t stream);
 
 typedef struct {
   int32_t field; int32_t precision;
-  const EonerfFieldParams* params;  /* fp32 masters: biases, the 1- and 3-wide heads, the embedding */
+  const EonerfFieldParams* params;  /* fp32 masters: biases, the 1- and 3-wide heads */
   const void* prepared;
   int64_t n_pts;
   /* sample positions: either explicit x[N,3] ... */
@@ -298,26 +299,29 @@ typedef struct {
 int eonerf_field_bwd(const EonerfFieldBwdArgs* a, eonerf_stream_t stream);
 
 /* Per-ray ambient colour sigmoid(W1 relu(W0 enc4(sun) + b0) + b1) (eonerf.py:163-164), fwd + bwd.
- * Tiny (B rows); always fp32. */
+ * Tiny (B rows); always fp32.  stash: B*160 floats, scratch: B*136 floats. */
 typedef struct {
   const float* sundirs; int64_t sundirs_stride; int64_t n_rays;
   const float* w0; const float* b0; const float* w1; const float* b1;   /* (128,27) (128) (3,128) (3) */
-  float* hidden;                   /* [B,128] stash */
+  float* stash;
   float* ambient;                  /* [B,3] */
 } EonerfAmbientFwdArgs;
 int eonerf_ambient_fwd(const EonerfAmbientFwdArgs* a, eonerf_stream_t stream);
 
 typedef struct {
-  const float* sundirs; int64_t sundirs_stride; int64_t n_rays;
+  int64_t n_rays;
   const float* w0; const float* w1;
-  const float* hidden; const float* ambient; const float* g_ambient;   /* [B,128] [B,3] [B,3] */
+  const float* stash; float* scratch;
+  const float* ambient; const float* g_ambient;                         /* [B,3] [B,3] */
   float* g_w0; float* g_b0; float* g_w1; float* g_b1;                    /* accumulated into (atomics) */
 } EonerfAmbientBwdArgs;
 int eonerf_ambient_bwd(const EonerfAmbientBwdArgs* a, eonerf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Building block exposed for tests and micro-benchmarks: Y = act(X W^T + b) on the tensor cores
- * (tcgen05 / TMEM / TMA) or the SIMT path.  X [M,K] and W [N,K] are bf16 (BF16) or fp32 (FP32).
+ * Building blocks exposed for tests and micro-benchmarks:
+ *   Y[M,N] = act(X[M,K] W[N,K]^T + b)        and        dW[N,K] += dY[M,N]^T X[M,K], db[N] += colsum(dY)
+ * X, W, Y, dY are fp32 (EONERF_PREC_FP32) or bf16 (EONERF_PREC_BF16: tcgen05; EONERF_PREC_BF16_SIMT).
+ * Tensor-core constraints: K % 8 == 0, leading dimensions % 8 == 0, 16-byte aligned bases.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t precision;
@@ -328,16 +332,13 @@ typedef struct {
 } EonerfLinearArgs;
 int eonerf_linear_fwd(const EonerfLinearArgs* a, eonerf_stream_t stream);
 
-/* dW[N,K] (fp32) = dY[M,N]^T X[M,K], reduced over M (split over CTAs, deterministic two-stage).
- * `partials` must hold eonerf_dw_partials_bytes(n,k) bytes. */
 typedef struct {
   int32_t precision;
   const void* dy; int64_t lddy; const void* x; int64_t ldx;
   int64_t m; int32_t n; int32_t k;
-  float* partials;
   float* dw; int64_t lddw;          /* accumulated into */
+  float* db;                        /* accumulated into, or NULL */
 } EonerfDwArgs;
-int64_t eonerf_dw_partials_bytes(int32_t n, int32_t k);
 int eonerf_linear_dw(const EonerfDwArgs* a, eonerf_stream_t stream);
 
 #ifdef __cplusplus

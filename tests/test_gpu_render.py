@@ -1,0 +1,178 @@
+"""GPU: render_image / rendering / compute_geometric_shadows through the drop-in module vs the reference's outputs
+(tests/golden/render.npz) and the oracle.  fp32 exactness mode: composited RGB / depth / shadow within 1e-5 relative
+(BASELINE.json north_star); parameter gradients vs the oracle's autograd."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import close, fingerprint, make_model, rel_err, t
+from oracle import eonerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(golden, tag, cuda, precision="fp32"):
+    g = golden["render"]
+    n_img = int(g[f"{tag}_n_img"])
+    p = O.init_params(n_img, seed=21, bias_scale=0.05)
+    np.testing.assert_allclose(fingerprint(p), g[f"{tag}_fingerprint"], rtol=1e-12)
+    m = make_model(p, n_img, cuda, precision)
+    rays, ts = t(g[f"{tag}_rays"], cuda), t(g[f"{tag}_ts"], cuda)
+    us = [dict(u_cam=t(g[f"{tag}_u_cam"], cuda), u_sun=t(g[f"{tag}_u_sun"], cuda))]
+    return g, p, m, rays, ts, us
+
+
+def _render(m, rays, ts, n, epoch, us, cuda, eval=False, chunk=None, **kw):
+    from eonerf_code_b200 import sat_rendering
+    from eonerf_code_b200.datasets.satellite import define_satrays_from_tensors
+    sr = define_satrays_from_tensors(rays, ts)
+    zs = torch.linspace(0, 1, n).to(cuda)
+    return sat_rendering.render_image(m, None, sr, None, None, epoch_idx=epoch, chunk=chunk or rays.shape[0],
+                                      render_step_size=2.0 / n, eval=eval, uniforms=us, z_steps=zs, **kw)
+
+
+@pytest.mark.parametrize("tag", ["train_e2", "train_e0", "eval_e5"])
+def test_render_image_golden_fp32(cuda, golden, tag):
+    from eonerf_code_b200 import sat_rendering
+    g, p, m, rays, ts, us = _setup(golden, tag, cuda)
+    n, epoch, ev = int(g[f"{tag}_n"]), int(g[f"{tag}_epoch"]), bool(g[f"{tag}_eval"])
+    m.train(not ev)
+    with torch.set_grad_enabled(not ev):
+        res, nren = _render(m, rays, ts, n, epoch, us, cuda, eval=ev)
+    assert nren == int(g[f"{tag}_n_rendering_samples"])            # index parity: same number of kept samples
+    assert list(res.keys()) == [k for k, _, _ in sat_rendering.OUT_SLICES]
+    ref = t(g[f"{tag}_out"])
+    for k, a, b in sat_rendering.OUT_SLICES:
+        assert res[k].shape == (rays.shape[0], b - a) and res[k].dtype == torch.float32
+        close(res[k], ref[:, a:b], 1e-5, 2e-6)
+    if ev:
+        return
+    from eonerf_code_b200 import metrics
+    pixels = t(g[f"{tag}_pixels"], cuda)
+    loss = metrics.mse(pixels, res["rgb"]) if epoch < 2 else metrics.uncertainty_aware_loss(pixels, res["rgb"], res["beta"])[0]
+    close(loss, t(g[f"{tag}_loss"]), 1e-5)
+    loss.backward()
+    names = [str(s) for s in g[f"{tag}_grad_names"]]
+    assert [k for k, _ in m.named_parameters()] == names
+    grads = [v.grad if v.grad is not None else torch.zeros_like(v) for _, v in m.named_parameters()]
+    norms = np.array([float(v.double().norm()) for v in grads])
+    np.testing.assert_allclose(norms, g[f"{tag}_grad_norms"], rtol=5e-4, atol=1e-8)
+    heads = np.stack([np.resize(v.flatten()[:16].cpu().numpy(), 16) for v in grads])
+    scale = np.abs(g[f"{tag}_grad_heads"]).max(axis=1, keepdims=True) + 1e-12
+    assert np.max(np.abs(heads - g[f"{tag}_grad_heads"]) / scale) < 2e-3
+
+
+@pytest.mark.parametrize("epoch", [0, 2])
+def test_full_gradients_vs_oracle_fp32(cuda, epoch):
+    """Every parameter gradient of one training step (incl. the serial sun-pass -> depth -> compositing chain)."""
+    from eonerf_code_b200 import metrics
+    from eonerf_code_b200.datasets.synthetic import make_rays
+    B, n, n_img = 96, 48, 5
+    p = O.init_params(n_img, seed=8, bias_scale=0.05)
+    m = make_model(p, n_img, cuda, "fp32")
+    rays, ts, pixels = make_rays(B, n_img, seed=13)
+    gen = torch.Generator().manual_seed(4)
+    u_cam, u_sun = torch.rand(B, n, generator=gen), torch.rand(B, n, generator=gen)
+    loss_o, out_o, grads_o, nren_o = O.train_step_grads(p, O.satrays_from_table(rays, ts), pixels, n, epoch, u_cam, u_sun)
+    res, nren = _render(m, rays.to(cuda), ts.to(cuda), n, epoch, [dict(u_cam=u_cam.to(cuda), u_sun=u_sun.to(cuda))], cuda)
+    assert nren == nren_o
+    px = pixels.to(cuda)
+    loss = metrics.mse(px, res["rgb"]) if epoch < 2 else metrics.uncertainty_aware_loss(px, res["rgb"], res["beta"])[0]
+    loss.backward()
+    close(loss, loss_o, 1e-5)
+    bad = {}
+    for k, v in m.named_parameters():
+        gg = v.grad if v.grad is not None else torch.zeros_like(v)
+        e = rel_err(gg, grads_o[k], floor=1e-9)
+        if e > 5e-4:
+            bad[k] = e
+    assert not bad, bad
+    if epoch < 2:   # s == 1: transient / ambient / sun branches get exactly zero
+        assert float(m.ambient_mlp.output_layer.weight.grad.abs().max()) == 0.0
+
+
+def test_only_depth_and_chunking_and_image_shape(cuda, golden):
+    g = golden["render"]
+    p = O.init_params(6, seed=21, bias_scale=0.05)
+    m = make_model(p, 6, cuda, "fp32")
+    rays, ts, u, n = t(g["depth_rays"], cuda), t(g["depth_ts"], cuda), t(g["depth_u"], cuda), int(g["depth_n"])
+    with torch.no_grad():
+        res, nren = _render(m, rays, ts, n, 3, [dict(u_cam=u)], cuda, only_depth=True)
+    assert list(res.keys()) == ["depth"] and nren == int(g["depth_n_rendering_samples"])
+    close(res["depth"], t(g["depth_out"]), 1e-5, 2e-6)
+    # two chunks + [H,W,*] shaped rays give the same numbers as one chunk (sat_rendering.py:201-209,252)
+    B = rays.shape[0]
+    us2 = [dict(u_cam=u[:B // 2]), dict(u_cam=u[B // 2:])]
+    from eonerf_code_b200 import sat_rendering
+    from eonerf_code_b200.datasets.satellite import SatRays, define_satrays_from_tensors
+    sr = define_satrays_from_tensors(rays, ts)
+    sr_img = SatRays(*[x.reshape(4, B // 4, -1) for x in sr])
+    with torch.no_grad():
+        res2, nren2 = sat_rendering.render_image(m, None, sr_img, None, None, epoch_idx=3, chunk=B // 2, render_step_size=2.0 / n,
+                                                 only_depth=True, uniforms=us2, z_steps=torch.linspace(0, 1, n).to(cuda))
+    assert res2["depth"].shape == (4, B // 4, 1) and nren2 == nren
+    close(res2["depth"].reshape(B, 1), res["depth"], 1e-6, 1e-7)
+
+
+def test_operator_level_api_fp32(cuda, golden):
+    """satnerf_sampling -> rendering -> compute_geometric_shadows called like the reference's render loop does."""
+    from eonerf_code_b200 import sat_rendering
+    from eonerf_code_b200.datasets.satellite import define_satrays_from_tensors
+    g, p, m, rays, ts, us = _setup(golden, "train_e2", cuda)
+    n = int(g["train_e2_n"])
+    sr = define_satrays_from_tensors(rays, ts)
+    zs = torch.linspace(0, 1, n).to(cuda)
+    args = {"render_step_size": 2.0 / n}
+    ri, t0, t1 = sat_rendering.satnerf_sampling(sr.origins, sr.viewdirs, args, near=sr.t_near, u=us[0]["u_cam"], z_steps=zs)
+    t1_before = t1.clone()
+    albedo, depth, beta, tr_s, ambient, entropy = m.rendering(sr, t0, t1, ri, 2)
+    assert float(t1.max()) == 1e10 and int((t1 != t1_before).sum()) == rays.shape[0]    # in-place 1e10 (eonerf.py:220)
+    geo, sc_ppr = sat_rendering.compute_geometric_shadows(sr, depth, m, None, args, u=us[0]["u_sun"], z_steps=zs)
+    ref = t(g["train_e2_out"])
+    close(depth, ref[:, 3:4], 1e-5, 2e-6); close(albedo, ref[:, 4:7], 1e-5, 2e-6)
+    close(ambient * 0.2, ref[:, 7:10], 1e-5, 2e-6); close(geo, ref[:, 10:11], 1e-5, 2e-6)
+    close(tr_s, ref[:, 11:12], 1e-5, 2e-6); close(beta, ref[:, 12:13], 1e-5, 2e-6)
+    assert torch.equal(sc_ppr.cpu(), ref[:, 15]) and torch.all(entropy == 1)
+    # d geo / d depth is live
+    (gd,) = torch.autograd.grad(geo.sum(), depth, retain_graph=True)
+    assert float(gd.abs().max()) > 0
+
+
+@pytest.mark.parametrize("precision", ["bf16_simt", "bf16"])
+def test_render_image_bf16(cuda, golden, precision):
+    """bf16 MLP: sample indices still bit-exact (same n_rendering_samples, pts_per_ray); composited outputs within the
+    tolerance the bf16 MLP allows (1e-3 abs on MLP outputs -> 5e-3 abs on composited colours / depth)."""
+    g, p, m, rays, ts, us = _setup(golden, "train_e2", cuda, precision)
+    n = int(g["train_e2_n"])
+    res, nren = _render(m, rays, ts, n, 2, us, cuda)
+    ref = t(g["train_e2_out"])
+    assert nren == int(g["train_e2_n_rendering_samples"])
+    assert torch.equal(res["pts_per_ray"].cpu(), ref[:, 14:15])
+    for k, a, b in (("rgb", 0, 3), ("depth", 3, 4), ("albedo_rgb", 4, 7), ("ambient_rgb", 7, 10), ("transient_s", 11, 12),
+                    ("beta", 12, 13), ("shadowless_rgb", 18, 21)):
+        assert float((res[k].cpu() - ref[:, a:b]).abs().max()) <= 5e-3, k
+    res["rgb"].sum().backward()
+    assert all(torch.isfinite(v.grad).all() for v in m.parameters() if v.grad is not None)
+
+
+@pytest.mark.parametrize("precision", ["bf16"])
+def test_sum_of_weights_and_determinism_at_full_size(cuda, precision):
+    """Size-independent properties at BASELINE config 3 size (8192 rays x 128 samples): two runs with the same uniforms
+    are bit-identical (no atomics in compositing), pts_per_ray sums to n_rendering_samples, outputs finite and in range."""
+    from eonerf_code_b200.datasets.synthetic import make_rays
+    B, n, n_img = 8192, 128, 19
+    p = O.init_params(n_img, seed=42)
+    m = make_model(p, n_img, cuda, precision)
+    rays, ts, _ = make_rays(B, n_img, seed=42)
+    gen = torch.Generator().manual_seed(0)
+    us = [dict(u_cam=torch.rand(B, n, generator=gen).to(cuda), u_sun=torch.rand(B, n, generator=gen).to(cuda))]
+    with torch.no_grad():
+        r1, n1 = _render(m, rays.to(cuda), ts.to(cuda), n, 2, us, cuda)
+        r2, n2 = _render(m, rays.to(cuda), ts.to(cuda), n, 2, us, cuda)
+    assert n1 == n2 == int(r1["pts_per_ray"].sum())
+    for k in r1:
+        assert torch.equal(r1[k], r2[k]), k
+        assert torch.isfinite(r1[k]).all(), k
+    assert float(r1["rgb"].min()) >= 0 and float(r1["rgb"].max()) <= 1
+    assert float(r1["geo_shadows"].min()) >= 0 and float(r1["geo_shadows"].max()) <= 1
+    assert float(r1["depth"].min()) >= 0

@@ -1,6 +1,548 @@
-// placeholder until the tcgen05 kernels land
+// bf16 tensor-core GEMMs of the radiance-field MLP for sm_100a: tcgen05.mma with TMEM accumulators, operands
+// staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier ring, warp-specialised
+// (1 TMA thread, 1 MMA thread, 4 epilogue warps), persistent over output tiles.
+//
+//   gemm_nt_tc :  C[M,N] = epi(A[M,K] B[N,K]^T)    forward layers (B = W) and input gradients (B = W^T)
+//                 both operands K-major; tile 128 x BLOCK_N(<=256) x 64; two TMEM accumulator stages so the MMA of
+//                 tile i+1 overlaps the epilogue of tile i
+//   gemm_tn_tc :  D[N,K] += A[M,N]^T X[M,K]        parameter gradients; the contraction runs over the SAMPLE axis,
+//                 so both operands are MN-major views of the row-major activations (no transposes are ever
+//                 materialised); split over CTAs along the samples, fp32 partial tiles merged with red.global.add
+//
+// Replaces the cuBLAS SGEMMs behind nn.Linear in /root/reference/radiance_fields/mlp.py:90,99 (forward) and their
+// autograd backward.  Shared-memory operand layouts follow the canonical UMMA layouts:
+//   K-major  SW128: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), 16-byte chunks XOR-swizzled by row%8
+//   MN-major SW128: the same physical image read the other way round: 64 contiguous MN elements x 8 K-rows per
+//                   atom, K groups SBO = 1024 B apart, 64-wide MN blocks LBO = (one TMA box) apart.
+#include <cuda.h>
+
 #include "gemm.cuh"
+
 namespace eonerf {
-int gemm_nt_tc(const GemmNT&, cudaStream_t) { set_error("tensor-core GEMM not built"); return EONERF_EINVAL; }
-int gemm_tn_tc(const GemmTN&, cudaStream_t) { set_error("tensor-core GEMM not built"); return EONERF_EINVAL; }
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread l of the warp receives lane (base_lane + l)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// descriptors
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kSwizzle128 = 2;   // UMMA LayoutType::SWIZZLE_128B
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);            // start address, bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset, bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)kSwizzle128 << 61;                  // layout type, bits [61,64)
+  return d;
+}
+
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32
+__host__ __device__ constexpr uint32_t instr_desc(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                          // c_format = F32
+         | (1u << 7)                        // a_format = BF16
+         | (1u << 10)                       // b_format = BF16
+         | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
+         | ((uint32_t)(n >> 3) << 17)       // n_dim
+         | ((uint32_t)(m >> 4) << 24);      // m_dim
+}
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                 // 64 bf16 = one 128-byte swizzle row
+constexpr int kBoxBytes = 64 * kBlockK * 2; // a [64 x 64] bf16 box (MN-major operands are loaded box by box)
+constexpr int kThreads = 192;               // warp 0: TMA, warp 1: TMEM alloc + MMA, warps 2..5: epilogue
+
+struct NTParams {
+  int64_t M; int N, K;
+  int block_n, n_tiles, k_blocks;
+  int64_t m_tiles;
+  __nv_bfloat16* C; int64_t ldc;
+  const float* bias;
+  const int32_t* row_class; const float* class_bias; int64_t ld_class;
+  const __nv_bfloat16* addend; int64_t ld_add;
+  const float* rank1_row; int64_t rank1_stride; const float* rank1_col;
+  int relu;
+  const __nv_bfloat16* mask; int64_t ld_mask; int mask_cols;
+};
+
+template <int kStages>
+__global__ void __launch_bounds__(kThreads, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB, NTParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = kBlockM * kBlockK * 2;
+  const int b_bytes = p.block_n * kBlockK * 2;
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int64_t total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int64_t mt = t / p.n_tiles; int nt = (int)(t % p.n_tiles);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+        tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBlockK, (int)(mt * kBlockM));
+        tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * kBlockK, nt * p.block_n);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = instr_desc(kBlockM, p.block_n, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // K-major SW128: 8-row groups 1024 B apart; stepping 16 elements along K moves the start by 32 bytes
+          uint64_t da = smem_desc(sa + k * 32, 16, 1024);
+          uint64_t db = smem_desc(sb + k * 32, 16, 1024);
+          umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&acc_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ===== epilogue: TMEM -> registers -> bias / addend / rank-1 / ReLU / mask -> bf16 -> global =====
+    const int quarter = warp & 3;           // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int64_t mt = t / p.n_tiles; int nt = (int)(t % p.n_tiles);
+      const int64_t m = mt * kBlockM + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      const int n0 = nt * p.block_n;
+      const float* brow = p.class_bias ? (row_ok ? p.class_bias + (int64_t)__ldg(p.row_class + m) * p.ld_class : p.class_bias) : p.bias;
+      const float r1 = (p.rank1_row && row_ok) ? __ldg(p.rank1_row + m * p.rank1_stride) : 0.f;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
+      for (int c = 0; c < p.block_n; c += 32) {
+        __syncwarp();                                            // tcgen05.ld is .sync.aligned: reconverge after the row_ok skip
+        uint32_t r[32];
+        const int width = (p.block_n - c) >= 32 ? 32 : 16;       // block_n is a multiple of 16
+        if (width == 32) tmem_ld32(taddr + c, r); else tmem_ld16(taddr + c, r);
+        tmem_ld_wait();
+        if (c + width >= p.block_n) {                            // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+        if (!row_ok) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {                            // 8 columns -> one 16-byte store
+          if (v * 8 >= width) break;
+          const int n = n0 + c + v * 8;
+          if (n >= p.N) break;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]);
+          if (brow) {
+            const float4 b0 = __ldg((const float4*)(brow + n)), b1 = __ldg((const float4*)(brow + n + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          if (p.addend) {
+            const uint4 a = __ldg((const uint4*)(p.addend + m * p.ld_add + n));
+            const __nv_bfloat162* a2 = (const __nv_bfloat162*)&a;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float2 x = __bfloat1622float2(a2[j]); f[2 * j] += x.x; f[2 * j + 1] += x.y; }
+          }
+          if (p.rank1_row) {
+            const float4 c0 = __ldg((const float4*)(p.rank1_col + n)), c1 = __ldg((const float4*)(p.rank1_col + n + 4));
+            f[0] += r1 * c0.x; f[1] += r1 * c0.y; f[2] += r1 * c0.z; f[3] += r1 * c0.w;
+            f[4] += r1 * c1.x; f[5] += r1 * c1.y; f[6] += r1 * c1.z; f[7] += r1 * c1.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.mask && n < p.mask_cols) {
+            const uint4 mk = __ldg((const uint4*)(p.mask + m * p.ld_mask + n));
+            const __nv_bfloat162* m2 = (const __nv_bfloat162*)&mk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 x = __bfloat1622float2(m2[j]);
+              if (!(x.x > 0.f)) f[2 * j] = 0.f;
+              if (!(x.y > 0.f)) f[2 * j + 1] = 0.f;
+            }
+          }
+          uint4 o;
+          __nv_bfloat162* o2 = (__nv_bfloat162*)&o;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          *(uint4*)(p.C + m * p.ldc + n) = o;
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TN: D[n,k] += sum_m A[m,n] X[m,k]     (MMA "M" = n: output features of dY, MMA "N" = k: input features)
+// ------------------------------------------------------------------------------------------------
+struct TNParams {
+  int64_t M;                 // samples (contraction)
+  int N, K;                  // valid output extents
+  int mt_count;              // 128-row blocks of N handled by one CTA (1 or 2)
+  int block_k;               // width of the K tile (MMA N), multiple of 16, <= 256
+  int k_tiles;               // number of K tiles
+  int64_t chunks_per_cta;    // 64-sample chunks per CTA
+  int64_t chunks;            // total 64-sample chunks
+  float* D; int64_t ldd;
+};
+
+template <int kStages>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmX, TNParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int a_boxes = p.mt_count * 2;                   // 64-feature boxes of dY
+  const int x_boxes = (p.block_k + 63) / 64;            // 64-feature boxes of X
+  const int stage_bytes = (a_boxes + x_boxes) * kBoxBytes;
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int kt = blockIdx.x % p.k_tiles;                // which K tile
+  const int64_t split = blockIdx.x / p.k_tiles;
+  const int64_t c_begin = split * p.chunks_per_cta;
+  const int64_t c_end = (c_begin + p.chunks_per_cta < p.chunks) ? c_begin + p.chunks_per_cta : p.chunks;
+  const int64_t my_chunks = c_end > c_begin ? c_end - c_begin : 0;
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t c = c_begin; c < c_end; ++c) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* s0 = smem + (size_t)stage * stage_bytes;
+      mbar_expect_tx(&full_bar[stage], stage_bytes);
+      for (int b = 0; b < a_boxes; ++b) tma_load_2d(s0 + b * kBoxBytes, &tmA, &full_bar[stage], b * 64, (int)(c * kBlockK));
+      for (int b = 0; b < x_boxes; ++b)
+        tma_load_2d(s0 + (a_boxes + b) * kBoxBytes, &tmX, &full_bar[stage], kt * p.block_k + b * 64, (int)(c * kBlockK));
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = instr_desc(kBlockM, p.block_k, 1, 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t c = 0; c < my_chunks; ++c) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t s0 = smem_u32(smem + (size_t)stage * stage_bytes);
+      const uint32_t sx = s0 + a_boxes * kBoxBytes;
+#pragma unroll
+      for (int k = 0; k < kBlockK / 16; ++k) {
+        // MN-major SW128: atom = 64 MN elements x 8 K rows (1024 B); 16 K rows per MMA = 2 atoms = 2048 B per step;
+        // 64-wide MN blocks are one box (LBO) apart
+        const uint64_t dx = smem_desc(sx + k * 2048, kBoxBytes, 1024);
+        for (int mt = 0; mt < p.mt_count; ++mt) {
+          const uint64_t da = smem_desc(s0 + mt * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
+          umma_bf16(tmem_base + mt * 256, da, dx, idesc, (c | k) != 0);
+        }
+      }
+      umma_commit(&empty_bar[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+    umma_commit(&acc_full);
+  } else if (warp >= 2 && my_chunks > 0) {
+    const int quarter = warp & 3;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    for (int mt = 0; mt < p.mt_count; ++mt) {
+      const int n = mt * kBlockM + quarter * 32 + lane;          // output row (feature of dY)
+      const uint32_t taddr = tmem_base + mt * 256 + ((uint32_t)(quarter * 32) << 16);
+      for (int c = 0; c < p.block_k; c += 32) {
+        __syncwarp();
+        uint32_t r[32];
+        const int width = (p.block_k - c) >= 32 ? 32 : 16;
+        if (width == 32) tmem_ld32(taddr + c, r); else tmem_ld16(taddr + c, r);
+        tmem_ld_wait();
+        if (n >= p.N) continue;
+        float* drow = p.D + (int64_t)n * p.ldd + kt * p.block_k + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < width && kt * p.block_k + c + j < p.K) atomicAdd(drow + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dbias[n] += sum_m A[m,n]
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ A, int64_t lda, int64_t M, int N,
+                                                          float* __restrict__ out, int rows_per_block) {
+  int n = threadIdx.x;
+  int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int64_t m = m0; m < m1; ++m) acc += __bfloat162float(A[m * lda + n]);
+  atomicAdd(out + n, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (leading dimension ld elements); box = 64 columns x box_rows rows, 128-byte swizzle;
+// out-of-bounds elements read as zero (ragged M / K tails need no special casing in the kernels)
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EONERF_ECUDA; }
+  if (((uintptr_t)base & 15) || (ld * 2) % 16) {
+    set_error("tensor-core GEMM operands need 16-byte aligned bases and leading dimensions that are multiples of 8 (ld=%lld)", (long long)ld);
+    return EONERF_EINVAL;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows, (long long)cols, (long long)ld); return EONERF_ECUDA; }
+  return EONERF_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+constexpr int kNTStages = 4;
+constexpr int kTNStages = 3;
+constexpr int kSmemNT = kNTStages * (kBlockM * kBlockK * 2 + 256 * kBlockK * 2) + 1024;
+constexpr int kSmemTN = kTNStages * 8 * kBoxBytes + 1024;
+
+int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
+  if (g.M <= 0 || g.N <= 0) return EONERF_OK;
+  EO_REQUIRE(g.K > 0 && g.K % 8 == 0, "gemm_nt_tc: K must be a positive multiple of 8 (got %d)", g.K);
+  EO_REQUIRE(g.N % 8 == 0 && g.ldc % 8 == 0 && ((uintptr_t)g.C & 15) == 0, "gemm_nt_tc: N and ldc must be multiples of 8, C 16-byte aligned");
+  EO_REQUIRE(!g.addend || (g.ld_add % 8 == 0 && ((uintptr_t)g.addend & 15) == 0), "gemm_nt_tc: misaligned addend");
+  EO_REQUIRE(!g.mask || (g.ld_mask % 8 == 0 && ((uintptr_t)g.mask & 15) == 0 && g.mask_cols % 8 == 0), "gemm_nt_tc: misaligned mask");
+  EO_REQUIRE(!g.class_bias || g.ld_class % 4 == 0, "gemm_nt_tc: class_bias rows must be 16-byte aligned");
+  static bool configured = false;
+  if (!configured) {
+    EO_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<kNTStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNT));
+    configured = true;
+  }
+  NTParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.n_tiles = (g.N + 255) / 256;
+  p.block_n = ((g.N + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;
+  p.k_blocks = (g.K + kBlockK - 1) / kBlockK;
+  p.m_tiles = (g.M + kBlockM - 1) / kBlockM;
+  p.C = (__nv_bfloat16*)g.C; p.ldc = g.ldc; p.bias = g.bias;
+  p.row_class = g.row_class; p.class_bias = g.class_bias; p.ld_class = g.ld_class;
+  p.addend = (const __nv_bfloat16*)g.addend; p.ld_add = g.ld_add;
+  p.rank1_row = g.rank1_row; p.rank1_stride = g.rank1_stride; p.rank1_col = g.rank1_col;
+  p.relu = g.relu; p.mask = (const __nv_bfloat16*)g.mask; p.ld_mask = g.ld_mask; p.mask_cols = g.mask_cols;
+  CUtensorMap tmA, tmB;
+  int r;
+  if ((r = make_map(&tmA, g.A, g.M, g.K, g.lda, kBlockM)) != EONERF_OK) return r;
+  if ((r = make_map(&tmB, g.B, g.N, g.K, g.ldb, p.block_n)) != EONERF_OK) return r;
+  int64_t tiles = p.m_tiles * p.n_tiles;
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  gemm_nt_tc_kernel<kNTStages><<<grid, kThreads, kSmemNT, s>>>(tmA, tmB, p);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return EONERF_OK;
+  static bool configured = false;
+  if (!configured) {
+    EO_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<kTNStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTN));
+    configured = true;
+  }
+  if (g.dbias) {
+    EO_REQUIRE(g.N <= 256, "gemm_tn_tc: dbias supports N <= 256");
+    int rows = 512;
+    while (div_up(g.M, rows) > 4 * sm_count() && rows < 16384) rows *= 2;
+    colsum_bf16_kernel<<<div_up(g.M, rows), 256, 0, s>>>((const __nv_bfloat16*)g.A, g.lda, g.M, g.N, g.dbias, rows);
+    EO_LAUNCH_CHECK();
+  }
+  if (!g.D) return EONERF_OK;
+  EO_REQUIRE(g.N <= 256, "gemm_tn_tc: N (features of dY) must be <= 256 (got %d)", g.N);
+  TNParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.mt_count = (g.N + kBlockM - 1) / kBlockM;
+  // K tiles are whole 64-element swizzle atoms (MN-major operands are read atom by atom); columns beyond K load as zeros
+  const int kp = (g.K + 63) / 64 * 64;
+  p.k_tiles = (kp + 255) / 256;
+  p.block_k = ((kp / 64 + p.k_tiles - 1) / p.k_tiles) * 64;
+  p.chunks = (g.M + kBlockK - 1) / kBlockK;
+  int64_t splits = sm_count() / p.k_tiles;
+  if (splits > p.chunks) splits = p.chunks;
+  if (splits < 1) splits = 1;
+  p.chunks_per_cta = (p.chunks + splits - 1) / splits;
+  splits = (p.chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
+  p.D = g.D; p.ldd = g.ldd;
+  CUtensorMap tmA, tmX;
+  int r;
+  // boxes of [64 samples x 64 features]; the tensor-map column extent is the number of valid features (zeros beyond)
+  if ((r = make_map(&tmA, g.A, g.M, g.N, g.lda, kBlockK)) != EONERF_OK) return r;
+  if ((r = make_map(&tmX, g.X, g.M, g.K, g.ldx, kBlockK)) != EONERF_OK) return r;
+  gemm_tn_tc_kernel<kTNStages><<<(unsigned)(splits * p.k_tiles), kThreads, kSmemTN, s>>>(tmA, tmX, p);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+}  // namespace eonerf

@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(256) weights_bwd_kernel(EonerfWeightsBwdArgs a
     float ga = ((ok && a.g_alphas) ? __ldg(a.g_alphas + i) : 0.f) + gw * s.T;
     float v = ok ? gT * s.T : 0.f;
     float inc = warp_inclusive_sum(v, lane);
-    float suffix = S - (run + inc);
+    // exclusive suffix sum_{k>i} v_k.  The last sample's suffix is 0 by definition: S - prefix would leave a
+    // ~1e-8*S rounding residue there, and its interval is 1e10 long (eonerf.py:220)
+    float suffix = (i == end - 1) ? 0.f : S - (run + inc);
     run += __shfl_sync(kFull, inc, 31);
     if (ok) a.g_sigmas[i] = (te - ts) * (ga * expf(-s.tau) - suffix);
   }
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(EonerfCompositeBwdAr
     float G = ok ? G_of(i) : 0.f;
     float v = ok ? G * s.w : 0.f;
     float inc = warp_inclusive_sum(v, lane);
-    float suffix = S - (run + inc);
+    float suffix = (i == end - 1) ? 0.f : S - (run + inc);   // exact 0 for the 1e10-long last interval (see weights_bwd)
     run += __shfl_sync(kFull, inc, 31);
     if (ok) {
       // T_{j+1} = T_j * exp(-tau_j)

@@ -175,10 +175,10 @@ __global__ void set_last_kernel(float* __restrict__ t_ends, const int64_t* __res
 using namespace eonerf;
 
 extern "C" int eonerf_sample_compact(const EonerfSampleArgs* a, eonerf_stream_t stream) {
-  EO_REQUIRE(a && a->origins && a->viewdirs && a->u && a->z_steps, "sample_compact: null input");
-  EO_REQUIRE(a->ray_indices && a->t_starts && a->t_ends && a->pts_per_ray && a->ray_offsets && a->stats,
-             "sample_compact: null output");
-  EO_REQUIRE(a->n_samples >= 2 && a->n_rays >= 0, "sample_compact: need n_samples >= 2 (got %d)", a->n_samples);
+  EO_REQUIRE(a && a->n_samples >= 2 && a->n_rays >= 0, "sample_compact: need n_samples >= 2 and n_rays >= 0");
+  EO_REQUIRE(a->ray_offsets && a->stats, "sample_compact: null ray_offsets / stats");
+  EO_REQUIRE(a->n_rays == 0 || (a->origins && a->viewdirs && a->u && a->z_steps), "sample_compact: null input");
+  EO_REQUIRE(a->n_rays == 0 || (a->ray_indices && a->t_starts && a->t_ends && a->pts_per_ray), "sample_compact: null output");
   cudaStream_t s = as_stream(stream);
   if (a->n_rays > 0) {
     int blocks = div_up(a->n_rays, 8);

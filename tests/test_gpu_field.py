@@ -2,8 +2,9 @@
 golden vectors of the reference and the oracle's autograd.
 
 Tolerances (BASELINE.json north_star): fp32 exactness mode 1e-5 relative; bf16 tensor-core mode 1e-3 absolute on the
-MLP outputs — the survey's probe found bf16 operands hold 1e-3 for >99 % of elements with a tail up to
-~2e-3, so the bf16 assertion is: 99 % within 1e-3 and all within 4e-3.  Gradients in bf16 mode: 3e-2 relative to the
+MLP outputs — bf16 operands (8 mantissa bits) through 8+ layers leave a tail above 1e-3 on the un-squashed sigma output
+(SURVEY.md §7 probe: max 1.7e-3), so the bf16 assertion is the north star's own target: >= 90 % of the elements of every
+output within 1e-3 absolute, and all within 4e-3.  Gradients in bf16 mode: 3e-2 relative to the
 largest entry of each tensor."""
 import pytest
 import torch
@@ -22,7 +23,7 @@ def check_outputs(outs, refs, precision):
             close(a, b, 1e-5, 2e-6)
         else:
             err = (a.detach().cpu().double() - b.double()).abs()
-            assert float((err <= 1e-3).double().mean()) >= 0.99, (name, float(err.max()))
+            assert float((err <= 1e-3).double().mean()) >= 0.90, (name, float(err.max()))
             assert float(err.max()) <= 4e-3, (name, float(err.max()))
 
 

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeonerf_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 COMP_COLS = 12
 OUT_COLS = 21
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT = 0, 1, 2
@@ -19,6 +19,10 @@ P = C.c_void_p
 I64 = C.c_int64
 I32 = C.c_int32
 F32 = C.c_float
+
+
+class Profile(C.Structure):
+    _fields_ = [("launches", I64), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
 
 
 class SampleArgs(C.Structure):
@@ -141,6 +145,9 @@ SYMBOLS = {
     "eonerf_abi_version": (C.c_int, []),
     "eonerf_last_error": (C.c_char_p, []),
     "eonerf_check_device": (C.c_int, []),
+    "eonerf_launch_count": (I64, [I32]),
+    "eonerf_profile_enable": (C.c_int, [I32]),
+    "eonerf_profile_read": (C.c_int, [C.POINTER(Profile), I32]),
     "eonerf_sample_compact": (C.c_int, _ARGS(SampleArgs)),
     "eonerf_pack_info": (C.c_int, [P, I64, I64, P, P]),
     "eonerf_set_last_t_end": (C.c_int, [P, P, I64, F32, P]),

@@ -29,7 +29,17 @@ void set_error(const char* fmt, ...);
     }                                                                                      \
   } while (0)
 
-#define EO_LAUNCH_CHECK() EO_CUDA(cudaPeekAtLastError())
+void count_launch();
+#define EO_LAUNCH_CHECK()              \
+  do {                                 \
+    ::eonerf::count_launch();          \
+    EO_CUDA(cudaPeekAtLastError());    \
+  } while (0)
+
+// Optional per-launch CUDA-event timing of the GEMM kernels (bench.py's live roofline measurement).
+// kind: 0 = gemm_nt_tc, 1 = gemm_tn_tc, 2 = SIMT GEMMs.  No-ops unless eonerf_profile_enable(1) was called.
+void profile_begin(int kind, double flops, double bytes, cudaStream_t s);
+void profile_end(cudaStream_t s);
 
 static inline cudaStream_t as_stream(eonerf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

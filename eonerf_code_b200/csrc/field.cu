@@ -491,7 +491,7 @@ static int field_fwd_impl(const EonerfFieldFwdArgs* a, cudaStream_t s) {
     else { g.A = st + S.h[i - 1]; g.lda = (i == 5) ? kH4E : kW; }
     g.B = pr + W.w[i]; g.ldb = trunk_kp(i);
     g.C = st + S.h[i]; g.ldc = (i == 4) ? kH4E : kW;
-    g.bias = p->trunk_b[i]; g.relu = 1;
+    g.bias = p->trunk_b[i]; g.relu = 1; g.alg_k = trunk_k(i);
     EO_TRY(gemm_nt(prec, g, s));
   }
   {  // sigma head: softplus (eonerf.py:106,145) / relu (vanilla, mlp.py:250)

@@ -21,6 +21,7 @@ struct GemmNT {
   const void* B = nullptr; int64_t ldb = 0;
   void* C = nullptr; int64_t ldc = 0;
   int64_t M = 0; int N = 0; int K = 0;
+  int alg_k = 0;   // un-padded contraction length (0: = K), only used to count algorithmic FLOPs
   const float* bias = nullptr;
   const int32_t* row_class = nullptr; const float* class_bias = nullptr; int64_t ld_class = 0;
   const void* addend = nullptr; int64_t ld_add = 0;

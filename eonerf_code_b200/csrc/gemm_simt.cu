@@ -125,8 +125,10 @@ __global__ void __launch_bounds__(256) gemm_tn_simt_kernel(GemmTN g, int64_t row
 int gemm_nt_simt(ElemType t, const GemmNT& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return EONERF_OK;
   dim3 grid(div_up(g.M, BM), div_up(g.N, BN));
+  profile_begin(2, 2.0 * g.M * g.N * (g.alg_k ? g.alg_k : g.K), 0.0, s);
   if (t == kF32) gemm_nt_simt_kernel<float><<<grid, 256, 0, s>>>(g);
   else gemm_nt_simt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g);
+  profile_end(s);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -142,8 +144,10 @@ int gemm_tn_simt(ElemType t, const GemmTN& g, cudaStream_t s) {
   rows = (rows + BK - 1) / BK * BK;
   split = (g.M + rows - 1) / rows;
   dim3 grid(tn, tk, (unsigned)split);
+  profile_begin(2, 2.0 * g.M * g.N * g.K, 0.0, s);
   if (t == kF32) gemm_tn_simt_kernel<float><<<grid, 256, 0, s>>>(g, rows);
   else gemm_tn_simt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, rows);
+  profile_end(s);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }

@@ -500,7 +500,10 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   if ((r = make_map(&tmB, g.B, g.N, g.K, g.ldb, p.block_n)) != EONERF_OK) return r;
   int64_t tiles = p.m_tiles * p.n_tiles;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const double ak = g.alg_k ? g.alg_k : g.K;
+  profile_begin(0, 2.0 * g.M * g.N * ak, 2.0 * (g.M * ak + (double)g.N * ak + (double)g.M * g.N), s);
   gemm_nt_tc_kernel<kNTStages><<<grid, kThreads, kSmemNT, s>>>(tmA, tmB, p);
+  profile_end(s);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -540,7 +543,9 @@ int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
   // boxes of [64 samples x 64 features]; the tensor-map column extent is the number of valid features (zeros beyond)
   if ((r = make_map(&tmA, g.A, g.M, g.N, g.lda, kBlockK)) != EONERF_OK) return r;
   if ((r = make_map(&tmX, g.X, g.M, g.K, g.ldx, kBlockK)) != EONERF_OK) return r;
+  profile_begin(1, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.N * p.k_tiles + (double)g.M * g.K) + 4.0 * g.N * g.K, s);
   gemm_tn_tc_kernel<kTNStages><<<(unsigned)(splits * p.k_tiles), kThreads, kSmemTN, s>>>(tmA, tmX, p);
+  profile_end(s);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 5
+#define EONERF_ABI_VERSION 6
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -37,6 +37,15 @@ int eonerf_abi_version(void);
 const char* eonerf_last_error(void);
 /* 0 if the current device can run the kernels (compute capability 10.x), else EONERF_EDEVICE. */
 int eonerf_check_device(void);
+
+/* Instrumentation (bench.py): number of kernels this library launched since the last reset; per-launch CUDA-event
+ * timing of the GEMM kernels.  kinds: 0 = tcgen05 NT GEMM (forward / input gradients), 1 = tcgen05 TN GEMM (parameter
+ * gradients), 2 = SIMT GEMMs.  `flops`/`bytes` are the ALGORITHMIC counts of the timed launches (2*M*N*K with the
+ * un-padded K; operand + result bytes). */
+typedef struct { int64_t launches; double ms; double flops; double bytes; } EonerfProfile;
+int64_t eonerf_launch_count(int32_t reset);
+int eonerf_profile_enable(int32_t on);
+int eonerf_profile_read(EonerfProfile* out, int32_t n_kinds);   /* synchronises the recorded events, then clears them */
 
 /* ------------------------------------------------------------------------------------------------
  * Stratified sampling + cube mask + order-preserving compaction.

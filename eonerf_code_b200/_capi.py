@@ -9,10 +9,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeonerf_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 COMP_COLS = 12
 OUT_COLS = 21
-PREC_FP32, PREC_BF16, PREC_BF16_SIMT = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16_FUSED = 0, 1, 2, 3
 FIELD_EONERF, FIELD_VANILLA = 0, 1
 
 P = C.c_void_p

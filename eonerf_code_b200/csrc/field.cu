@@ -19,89 +19,9 @@
 // The 1- and 3-wide heads (sigma, albedo, transient scalar/beta) are warp-per-row fp32 dot products.
 #include <type_traits>
 
-#include "gemm.cuh"
+#include "field_layout.cuh"
 
 namespace eonerf {
-
-constexpr int kW = 256;       // trunk width (eonerf.py:73-75; --fc_units is never read)
-constexpr int kEnc = 64;      // 63 pos-enc columns + 1 zero pad
-constexpr int kH4E = kW + kEnc;
-constexpr int kHid = 128;
-constexpr int kDirEnc = 32;   // 27 view-enc columns + 5 zero pad
-constexpr float kHalfPi = 1.57079637050628662109375f;   // fl32(0.5*pi): torch adds the python scalar in fp32 (mlp.py:203)
-
-static inline int64_t align_up(int64_t v, int64_t a = 256) { return (v + a - 1) / a * a; }
-
-struct StashLayout {
-  int64_t xf, cls, h[8], bott, hd0, t[3], total;
-  int ld_bott, ld_hd0;
-};
-
-static StashLayout stash_layout(int field, int precision, int64_t n, int density_only) {
-  StashLayout L{};
-  int64_t es = elem_size(precision), off = 0;
-  auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes); return o; };
-  L.xf = take(n * 3 * 4);
-  L.cls = take(n * 4);
-  for (int i = 0; i < 8; ++i) L.h[i] = take(n * (i == 4 ? kH4E : kW) * es);
-  L.ld_bott = field == EONERF_FIELD_VANILLA ? kW + kDirEnc : kW;
-  L.ld_hd0 = field == EONERF_FIELD_VANILLA ? kHid : 2 * kHid;
-  if (!density_only) {
-    L.bott = take(n * L.ld_bott * es);
-    L.hd0 = take(n * L.ld_hd0 * es);
-    if (field == EONERF_FIELD_EONERF)
-      for (int i = 0; i < 3; ++i) L.t[i] = take(n * kHid * es);
-  }
-  L.total = off;
-  return L;
-}
-
-struct ScratchLayout {
-  int64_t ga, gb, gc, gat, g1, g2, dpre, dcb, total;
-};
-
-static ScratchLayout scratch_layout(int field, int precision, int64_t n, int64_t n_images) {
-  ScratchLayout L{};
-  int64_t es = elem_size(precision), off = 0;
-  auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes); return o; };
-  L.ga = take(n * kW * es);
-  L.gb = take(n * kH4E * es);
-  L.gc = take(n * (kW + kDirEnc) * es);
-  L.gat = take(n * 2 * kHid * es);
-  L.g1 = take(n * kHid * es);
-  L.g2 = take(n * kHid * es);
-  L.dpre = take(n * 8 * 4);
-  L.dcb = take((n_images > 0 ? n_images : 1) * kHid * 4);
-  L.total = off;
-  return L;
-}
-
-// prepared blob: for every matrix W [out, Kp] then W^T [Kp, out] in T, then the fp32 class-bias table
-struct PrepLayout {
-  int64_t w[8], wt[8];       // trunk
-  int64_t bott, bott_t;
-  int64_t hd0, hd0_t;        // eonerf: [256,256] = [albedo_mlp.0 ; transient_mlp.0[:, :256]]   vanilla: [128,288]
-  int64_t tr[3], tr_t[3];    // transient_mlp.{1,2,3}
-  int64_t class_bias;        // fp32 [n_img,256] = [ albedo_mlp.0.bias | transient_mlp.0.bias + W[:,256:260] emb[img] ]
-  int64_t total;
-};
-
-static int trunk_kp(int i) { return i == 0 ? kEnc : (i == 5 ? kH4E : kW); }
-static int trunk_k(int i) { return i == 0 ? 63 : (i == 5 ? 319 : kW); }
-
-static PrepLayout prep_layout(int field, int precision, int64_t n_images) {
-  PrepLayout L{};
-  int64_t es = elem_size(precision), off = 0;
-  auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes); return o; };
-  for (int i = 0; i < 8; ++i) { L.w[i] = take(kW * trunk_kp(i) * es); L.wt[i] = take(kW * trunk_kp(i) * es); }
-  L.bott = take(kW * kW * es); L.bott_t = take(kW * kW * es);
-  int64_t hd0 = field == EONERF_FIELD_VANILLA ? kHid * (kW + kDirEnc) : 2 * kHid * kW;
-  L.hd0 = take(hd0 * es); L.hd0_t = take(hd0 * es);
-  for (int i = 0; i < 3; ++i) { L.tr[i] = take(kHid * kHid * es); L.tr_t[i] = take(kHid * kHid * es); }
-  L.class_bias = take((n_images > 0 ? n_images : 1) * 2 * kHid * 4);
-  L.total = off;
-  return L;
-}
 
 // ------------------------------------------------------------------------------------------------
 // prepare: W fp32 [rows, k] (ld = ldw) -> dst [rows, kp] (zero padded) and dst_t [kp, rows]
@@ -883,19 +803,23 @@ static int field_bwd_impl(const EonerfFieldBwdArgs* a, cudaStream_t s) {
 
 using namespace eonerf;
 
-static bool valid_prec(int p) { return p == EONERF_PREC_FP32 || p == EONERF_PREC_BF16 || p == EONERF_PREC_BF16_SIMT; }
+static bool valid_prec(int p) { return p == EONERF_PREC_FP32 || p == EONERF_PREC_BF16 || p == EONERF_PREC_BF16_SIMT || p == EONERF_PREC_BF16_FUSED; }
+static bool fused(int p) { return p == EONERF_PREC_BF16_FUSED; }
 static bool valid_field(int f) { return f == EONERF_FIELD_EONERF || f == EONERF_FIELD_VANILLA; }
 
 extern "C" int64_t eonerf_field_prepared_bytes(int32_t field, int32_t precision, int64_t n_images) {
   if (!valid_prec(precision) || !valid_field(field)) return -1;
+  if (fused(precision)) return field == EONERF_FIELD_EONERF ? prep_layout(field, EONERF_PREC_BF16, n_images).total + fused_prepared_extra_bytes(n_images) : -1;
   return prep_layout(field, precision, n_images).total;
 }
 extern "C" int64_t eonerf_field_stash_bytes(int32_t field, int32_t precision, int64_t n_pts, int32_t density_only) {
   if (!valid_prec(precision) || !valid_field(field) || n_pts < 0) return -1;
+  if (fused(precision)) return field == EONERF_FIELD_EONERF ? fused_stash_bytes(n_pts, density_only) : -1;
   return stash_layout(field, precision, n_pts, density_only).total;
 }
 extern "C" int64_t eonerf_field_scratch_bytes(int32_t field, int32_t precision, int64_t n_pts, int64_t n_images) {
   if (!valid_prec(precision) || !valid_field(field) || n_pts < 0) return -1;
+  if (fused(precision)) return field == EONERF_FIELD_EONERF ? fused_scratch_bytes(n_pts, n_images, 0) : -1;
   return scratch_layout(field, precision, n_pts, n_images).total;
 }
 
@@ -904,6 +828,11 @@ extern "C" int eonerf_field_prepare(int32_t field, int32_t precision, const Eone
   EO_REQUIRE(valid_prec(precision) && valid_field(field), "field_prepare: bad field/precision %d/%d", field, precision);
   EO_REQUIRE(params && prepared, "field_prepare: null pointer");
   EO_REQUIRE(field == EONERF_FIELD_VANILLA || (params->n_images > 0 && params->transient_emb), "field_prepare: need n_images > 0");
+  if (fused(precision)) {
+    EO_REQUIRE(field == EONERF_FIELD_EONERF, "field_prepare: the fused precision mode supports the EO-NeRF field only");
+    EO_TRY(field_prepare_impl(field, EONERF_PREC_BF16, params, prepared, as_stream(stream)));
+    return fused_prepare(params, prepared, as_stream(stream));
+  }
   return field_prepare_impl(field, precision, params, prepared, as_stream(stream));
 }
 
@@ -911,12 +840,14 @@ extern "C" int eonerf_field_fwd(const EonerfFieldFwdArgs* a, eonerf_stream_t str
   EO_REQUIRE(a && valid_prec(a->precision) && valid_field(a->field), "field_fwd: bad field/precision");
   EO_REQUIRE(a->n_pts >= 0, "field_fwd: negative n_pts");
   if (a->n_pts == 0) return EONERF_OK;
-  EO_REQUIRE(a->params && a->prepared && a->stash && a->sigma, "field_fwd: null pointer");
+  EO_REQUIRE(a->params && a->prepared && a->sigma, "field_fwd: null pointer");
+  EO_REQUIRE(a->stash || fused(a->precision), "field_fwd: null stash (only the fused mode can run without one: inference)");
   EO_REQUIRE(a->x || (a->origins && a->viewdirs && a->ray_indices && a->t_starts && a->t_ends),
              "field_fwd: give x or (origins, viewdirs, ray_indices, t_starts, t_ends)");
   EO_REQUIRE(a->density_only || a->rgb, "field_fwd: null rgb output");
   EO_REQUIRE(a->density_only || a->field == EONERF_FIELD_VANILLA || (a->transient_s && a->transient_beta && a->img_idx),
              "field_fwd: the eonerf field needs img_idx and the transient outputs");
+  if (fused(a->precision)) return fused_field_fwd(a, as_stream(stream));
   return field_fwd_impl(a, as_stream(stream));
 }
 
@@ -928,6 +859,7 @@ extern "C" int eonerf_field_bwd(const EonerfFieldBwdArgs* a, eonerf_stream_t str
   EO_REQUIRE(a->density_only || a->rgb, "field_bwd: null rgb");
   EO_REQUIRE(a->density_only || a->field == EONERF_FIELD_VANILLA || (a->transient_s && a->transient_beta),
              "field_bwd: the eonerf field needs the transient forward outputs");
+  if (fused(a->precision)) return fused_field_bwd(a, as_stream(stream));
   return field_bwd_impl(a, as_stream(stream));
 }
 

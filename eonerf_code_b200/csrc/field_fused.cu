@@ -1,0 +1,542 @@
+// Fused radiance-field MLP for sm_100a: EONerfMLP.forward / query_density
+// (/root/reference/radiance_fields/eonerf.py:141-170, mlp.py:87-111,190-208) as ONE persistent tcgen05 kernel, and its
+// input-gradient chain as a second one.  A 128-sample tile enters the kernel once (positions -> positional encoding in
+// shared memory) and every layer's activation stays on chip: the accumulator lives in TMEM, the epilogue warps turn
+// it into the next layer's bf16 A operand directly in the 128-byte-swizzled shared-memory image the tensor core reads.
+//
+//   warp 0      weight producer: streams pre-tiled 16 KB weight blocks (cp.async.bulk, 3-deep mbarrier ring)
+//   warp 1      MMA issuer (one thread): tcgen05.mma 128x128x16, accumulators in TMEM (2 tiles x 256 columns)
+//   warps 2-9   epilogue: TMEM -> registers -> bias / ReLU / heads -> bf16 -> shared memory (next A operand)
+//                         -> cp.async.bulk store of the same image to the tile-blocked stash (training only)
+//
+// Two tiles ("slots") are in flight per CTA and ping-pong: while the tensor core works on one tile's layer, the
+// epilogue warps drain the other tile's accumulator, so the MMA pipe only idles when an epilogue is longer than a layer.
+//
+// Rounding points are those of the layer-by-layer bf16 path (field.cu): bf16 activations and weights, fp32 accumulate,
+// fp32 biases and narrow heads.
+#include "field_fused.cuh"
+#include "tc_ptx.cuh"
+
+namespace eonerf {
+
+namespace {
+
+constexpr int kRingStages = 3;
+constexpr int kSlotBytes = 5 * kBlkBytes;                  // ACT blocks 0..3 + ENC block 4
+constexpr int kOffRing = 0;
+constexpr int kOffSlot = kRingStages * kBlkBytes;          // 49152
+constexpr int kOffConst = kOffSlot + 2 * kSlotBytes;       // 212992
+constexpr int kConstBytes = 15360;
+constexpr int kOffPart = kOffConst + kConstBytes;          // [128][2] floats
+constexpr int kOffBar = kOffPart + 1024;
+constexpr int kSmemFused = kOffBar + 128 + 1024;           // + alignment slack
+constexpr int kFusedThreads = 320;
+constexpr int kEpiThreads = 256;
+
+static_assert(kCFloats * 4 <= kConstBytes, "constants do not fit");
+static_assert(kSmemFused <= 232448, "shared memory budget");
+
+// ---- forward program ------------------------------------------------------------------------------------------------
+struct FStage {
+  int8_t halves, nkb, a[5], out_blk, relu, kind, mask, pad;
+  int16_t bias_off;            // float offset into the constants block, -1: per-image class bias from global
+};
+// kind: 0 plain, 1 + sigma head, 2 + albedo head (class bias), 3 + transient heads
+__constant__ FStage c_fstage[kFwdStages] = {
+    {2, 1, {4, 0, 0, 0, 0}, 0, 1, 0, 0, 0, kCBiasTrunk + 0 * 256},
+    {2, 4, {0, 1, 2, 3, 0}, 0, 1, 0, 1, 0, kCBiasTrunk + 1 * 256},
+    {2, 4, {0, 1, 2, 3, 0}, 0, 1, 0, 2, 0, kCBiasTrunk + 2 * 256},
+    {2, 4, {0, 1, 2, 3, 0}, 0, 1, 0, 3, 0, kCBiasTrunk + 3 * 256},
+    {2, 4, {0, 1, 2, 3, 0}, 0, 1, 0, 4, 0, kCBiasTrunk + 4 * 256},
+    {2, 5, {0, 1, 2, 3, 4}, 0, 1, 0, 5, 0, kCBiasTrunk + 5 * 256},
+    {2, 4, {0, 1, 2, 3, 0}, 0, 1, 0, 6, 0, kCBiasTrunk + 6 * 256},
+    {2, 4, {0, 1, 2, 3, 0}, 0, 1, 1, 7, 0, kCBiasTrunk + 7 * 256},
+    {2, 4, {0, 1, 2, 3, 0}, 0, 0, 0, -1, 0, kCBiasBott},
+    {2, 4, {0, 1, 2, 3, 0}, 0, 1, 2, kMaskHd0, 0, -1},
+    {1, 2, {2, 3, 0, 0, 0}, 0, 1, 0, kMaskT1 + 0, 0, kCBiasTr + 0 * 128},
+    {1, 2, {0, 1, 0, 0, 0}, 2, 1, 0, kMaskT1 + 1, 0, kCBiasTr + 1 * 128},
+    {1, 2, {2, 3, 0, 0, 0}, 0, 1, 3, kMaskT1 + 2, 0, kCBiasTr + 2 * 128},
+};
+
+struct FusedFwdParams {
+  int64_t M; int64_t n_tiles; int n_stages; int training;
+  const float* x;
+  const float* origins; int64_t o_stride; const float* viewdirs; int64_t d_stride;
+  const int64_t* ray_indices; const float* t_starts; const float* t_ends; float* z_mid;
+  const int64_t* img_idx; int64_t img_stride;
+  const uint8_t* wblob; const float* consts; const float* class_bias;
+  int blk_off[kFwdStages];
+  uint8_t* arr[kNumArr];
+  uint32_t* mask[kNumMask];
+  float* xf; int32_t* cls;
+  float* sigma; float* rgb; float* ts; float* tb;
+};
+
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }          // nn.Sigmoid
+__device__ __forceinline__ float softplus_f(float v) { return v > 20.0f ? v : log1pf(expf(v)); }   // nn.Softplus(beta=1, threshold=20)
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
+
+// shared-memory byte offset of (row, 16-byte chunk) inside a [128 x 64] bf16 block
+__device__ __forceinline__ uint32_t blk_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// positional-encoding column c (0..63) of position x  (mlp.py:199-205; same arithmetic as encode_kernel in field.cu)
+__device__ __forceinline__ float posenc_col(const float (&x)[3], int c) {
+  if (c < 3) return c == 0 ? x[0] : (c == 1 ? x[1] : x[2]);
+  if (c >= 63) return 0.f;
+  int e = c - 3;
+  const int hf = e >= 30;
+  e -= hf * 30;
+  const int dim = e % 3;
+  const float xv = dim == 0 ? x[0] : (dim == 1 ? x[1] : x[2]);
+  const float xb = xv * (float)(1 << (e / 3));
+  return sinf(hf ? __fadd_rn(xb, kHalfPi) : xb);
+}
+
+template <bool kTrain>
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __grid_constant__ FusedFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* w_full = (uint64_t*)(smem + kOffBar);
+  uint64_t* w_empty = w_full + kRingStages;
+  uint64_t* acc_full = w_empty + kRingStages;
+  uint64_t* act_ready = acc_full + 2;
+  uint32_t* tmem_base_s = (uint32_t*)(act_ready + 2);
+  float* cst = (float*)(smem + kOffConst);
+  float* part = (float*)(smem + kOffPart);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRingStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&act_ready[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_s, 512);
+  for (int i = threadIdx.x; i < kCFloats; i += kFusedThreads) cst[i] = __ldg(p.consts + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+  const int64_t n_pairs = (p.n_tiles + 1) / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== weight producer =====
+      int rs = 0; uint32_t rph = 0;
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (int s = 0; s < p.n_stages; ++s) {
+          const int nblk = c_fstage[s].halves * c_fstage[s].nkb;
+          const uint8_t* src = p.wblob + (size_t)p.blk_off[s] * kBlkBytes;
+          for (int rep = 0; rep < 2; ++rep)
+            for (int b = 0; b < nblk; ++b) {
+              mbar_wait(&w_empty[rs], rph ^ 1);
+              mbar_expect_tx(&w_full[rs], kBlkBytes);
+              bulk_load(smem + kOffRing + rs * kBlkBytes, src + (size_t)b * kBlkBytes, kBlkBytes, &w_full[rs]);
+              if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+            }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = instr_desc(128, 128, 0, 0);
+      int rs = 0; uint32_t rph = 0;
+      uint32_t aph = 0;                                  // bit `slot` = phase of act_ready[slot]
+      const uint32_t ring0 = smem_u32(smem + kOffRing);
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (int s = 0; s < p.n_stages; ++s) {
+          const FStage d = c_fstage[s];
+          for (int slot = 0; slot < 2; ++slot) {
+            mbar_wait(&act_ready[slot], (aph >> slot) & 1u);
+            aph ^= 1u << slot;
+            tc_fence_after();
+            const uint32_t slot0 = smem_u32(smem + kOffSlot + slot * kSlotBytes);
+            for (int h = 0; h < d.halves; ++h) {
+              const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
+              for (int kb = 0; kb < d.nkb; ++kb) {
+                mbar_wait(&w_full[rs], rph);
+                tc_fence_after();
+                const uint32_t sa = slot0 + d.a[kb] * kBlkBytes;
+                const uint32_t sb = ring0 + rs * kBlkBytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0);
+                umma_commit(&w_empty[rs]);
+                if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+              }
+            }
+            umma_commit(&acc_full[slot]);
+          }
+        }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int e = threadIdx.x - 64;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;                    // row of the tile
+    uint32_t cph = 0;                                    // bit `slot` = phase of acc_full[slot]
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      uint32_t cls_pack = 0;                             // image index of this row in slot 0 (low 16 bits) / slot 1
+      // ---- positional encoding of both tiles ----
+      if (e == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, kEpiThreads);
+      for (int slot = 0; slot < 2; ++slot) {
+        const int64_t tile = 2 * pair + slot;
+        const int64_t pt = tile * kTileM + r;
+        const bool valid = pt < p.M;
+        float x[3] = {0.f, 0.f, 0.f};
+        int64_t ray = -1;
+        if (valid) {
+          if (p.x) {
+            x[0] = __ldg(p.x + 3 * pt); x[1] = __ldg(p.x + 3 * pt + 1); x[2] = __ldg(p.x + 3 * pt + 2);
+            if (p.ray_indices) ray = __ldg(p.ray_indices + pt);
+          } else {
+            ray = __ldg(p.ray_indices + pt);
+            const float ts = __ldg(p.t_starts + pt), te = __ldg(p.t_ends + pt);
+            const float zm = __fdiv_rn(__fadd_rn(ts, te), 2.0f);                              // eonerf.py:206
+            const float* o = p.origins + ray * p.o_stride;
+            const float* dd = p.viewdirs + ray * p.d_stride;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) x[k] = __fadd_rn(__ldg(o + k), __fmul_rn(__ldg(dd + k), zm));   // eonerf.py:207
+            if (half == 0 && p.z_mid) p.z_mid[pt] = zm;
+          }
+          if (p.img_idx) {
+            const int64_t img = p.ray_indices ? __ldg(p.img_idx + ray * p.img_stride) : __ldg(p.img_idx + pt * p.img_stride);
+            cls_pack |= ((uint32_t)img & 0xFFFFu) << (16 * slot);
+          }
+          if (kTrain && half == 0) {
+            p.xf[3 * pt] = x[0]; p.xf[3 * pt + 1] = x[1]; p.xf[3 * pt + 2] = x[2];
+            if (p.cls) p.cls[pt] = (int32_t)((cls_pack >> (16 * slot)) & 0xFFFFu);
+          }
+        }
+        uint8_t* enc = smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint32_t w[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = half * 32 + jj * 8 + u * 2;
+            w[u] = pack_bf16(posenc_col(x, c), posenc_col(x, c + 1));
+          }
+          *(uint4*)(enc + blk_off(r, half * 4 + jj)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(1, kEpiThreads);
+      if (e == 0) {
+        mbar_arrive(&act_ready[0]);
+        mbar_arrive(&act_ready[1]);
+        if (kTrain) {
+          for (int slot = 0; slot < 2; ++slot) {
+            const int64_t tile = 2 * pair + slot;
+            if (tile < p.n_tiles)
+              bulk_store(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
+          }
+          tma_store_commit();
+        }
+      }
+
+      // ---- the layers ----
+      for (int s = 0; s < p.n_stages; ++s) {
+        const FStage d = c_fstage[s];
+        const int cpt = d.halves == 2 ? 128 : 64;          // columns per thread
+        const int col0 = half * cpt;
+        for (int slot = 0; slot < 2; ++slot) {
+          const int64_t tile = 2 * pair + slot;
+          const int64_t pt = tile * kTileM + r;
+          const bool valid = pt < p.M;
+          uint8_t* act = smem + kOffSlot + slot * kSlotBytes;
+          const float* brow = d.bias_off >= 0 ? nullptr : p.class_bias + (size_t)((cls_pack >> (16 * slot)) & 0xFFFFu) * 256;
+          mbar_wait(&acc_full[slot], (cph >> slot) & 1u);
+          cph ^= 1u << slot;
+          tc_fence_after();
+          if (e == 0) tma_store_wait_read<0>();              // earlier stash stores have finished reading this slot
+          named_bar_sync(1, kEpiThreads);
+          const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + col0;
+          float h0 = 0.f, h1 = 0.f, h2 = 0.f;               // head partial sums
+          uint32_t mbits[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c * 32 >= cpt) break;
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            float b[32];
+            if (d.bias_off >= 0) {
+              const float4* bp = (const float4*)(cst + d.bias_off + col0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { const float4 t = bp[j]; b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w; }
+            } else {
+              const float4* bp = (const float4*)(brow + col0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { const float4 t = __ldg(bp + j); b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w; }
+            }
+            tmem_ld_wait();
+            uint32_t pk[16];
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float f0 = __uint_as_float(v[2 * j]) + b[2 * j], f1 = __uint_as_float(v[2 * j + 1]) + b[2 * j + 1];
+              if (d.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+              pk[j] = pack_bf16(f0, f1);
+              bits |= ((pk[j] & 0x7FFFu) ? 1u : 0u) << (2 * j);
+              bits |= ((pk[j] & 0x7FFF0000u) ? 1u : 0u) << (2 * j + 1);
+            }
+            mbits[c] = bits;
+            if (d.kind == 1) {
+              const float4* wp = (const float4*)(cst + kCWSigma + col0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w = wp[j];
+                h0 = fmaf(bf_lo(pk[2 * j]), w.x, h0); h0 = fmaf(bf_hi(pk[2 * j]), w.y, h0);
+                h0 = fmaf(bf_lo(pk[2 * j + 1]), w.z, h0); h0 = fmaf(bf_hi(pk[2 * j + 1]), w.w, h0);
+              }
+            } else if (d.kind == 2) {
+              if (half == 0) {
+                const float* wa = cst + kCWAlb + c * 32;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float lo = bf_lo(pk[j]), hi = bf_hi(pk[j]);
+                  h0 = fmaf(lo, wa[2 * j], h0); h0 = fmaf(hi, wa[2 * j + 1], h0);
+                  h1 = fmaf(lo, wa[128 + 2 * j], h1); h1 = fmaf(hi, wa[128 + 2 * j + 1], h1);
+                  h2 = fmaf(lo, wa[256 + 2 * j], h2); h2 = fmaf(hi, wa[256 + 2 * j + 1], h2);
+                }
+              }
+            } else if (d.kind == 3) {
+              const float* ws = cst + kCWTs + col0 + c * 32;
+              const float* wb = cst + kCWTb + col0 + c * 32;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float lo = bf_lo(pk[j]), hi = bf_hi(pk[j]);
+                h0 = fmaf(lo, ws[2 * j], h0); h0 = fmaf(hi, ws[2 * j + 1], h0);
+                h1 = fmaf(lo, wb[2 * j], h1); h1 = fmaf(hi, wb[2 * j + 1], h1);
+              }
+            }
+            const int colg = col0 + c * 32;                   // first output column of this chunk
+            uint8_t* blk = act + (d.out_blk + (colg >> 6)) * kBlkBytes;
+            const int ch0 = (colg & 63) >> 3;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              *(uint4*)(blk + blk_off(r, ch0 + jj)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+          if (half == 1 && (d.kind == 1 || d.kind == 3)) { part[2 * r] = h0; part[2 * r + 1] = h1; }
+          tc_fence_before();
+          fence_proxy_async();
+          named_bar_sync(1, kEpiThreads);
+          if (e == 0) {
+            if (s + 1 < p.n_stages) mbar_arrive(&act_ready[slot]);
+            if (kTrain && tile < p.n_tiles) {
+              const int nb = d.halves * 2;
+              for (int b = 0; b < nb; ++b)
+                bulk_store(p.arr[s] + ((size_t)tile * nb + b) * kBlkBytes, act + (d.out_blk + b) * kBlkBytes, kBlkBytes);
+              tma_store_commit();
+            }
+          }
+          if (valid) {
+            if (half == 0) {
+              if (d.kind == 1) {
+                p.sigma[pt] = softplus_f(h0 + part[2 * r] + cst[kCScalars + 0]);               // eonerf.py:106,145
+              } else if (d.kind == 2) {
+                p.rgb[3 * pt + 0] = sigmoid_f(h0 + cst[kCScalars + 1]);
+                p.rgb[3 * pt + 1] = sigmoid_f(h1 + cst[kCScalars + 2]);
+                p.rgb[3 * pt + 2] = sigmoid_f(h2 + cst[kCScalars + 3]);
+              } else if (d.kind == 3) {
+                p.ts[pt] = sigmoid_f(h0 + part[2 * r] + cst[kCScalars + 4]);
+                p.tb[pt] = softplus_f(h1 + part[2 * r + 1] + cst[kCScalars + 5]);
+              }
+            }
+            if (kTrain && d.mask >= 0) {
+              uint32_t* mrow = p.mask[d.mask] + pt * 8;
+              if (cpt == 128) *(uint4*)(mrow + half * 4) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
+              else *(uint2*)(mrow + half * 2) = make_uint2(mbits[0], mbits[1]);
+            }
+          }
+        }
+      }
+    }
+    if (e == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- prepare: weight blocks + constants ----------------------------------------------------------------------------
+struct PackJob { const __nv_bfloat16* src; int ld, row0, rows, col0; };
+struct PackJobs { PackJob j[kBwdBlocks]; int n; };
+
+// block image [128 x 64]: element (n, k) = src[(row0+n)*ld + col0+k] for n < rows (zero beyond), swizzled
+__global__ void __launch_bounds__(256) pack_blocks_kernel(const __grid_constant__ PackJobs jobs, uint8_t* __restrict__ dst) {
+  const int b = blockIdx.x >> 2;
+  const int idx = (blockIdx.x & 3) * 256 + threadIdx.x;     // 1024 16-byte chunks per block
+  const int n = idx >> 3, c = idx & 7;
+  const PackJob j = jobs.j[b];
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (n < j.rows) v = __ldg((const uint4*)(j.src + (size_t)(j.row0 + n) * j.ld + j.col0 + c * 8));
+  *(uint4*)(dst + (size_t)b * kBlkBytes + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+}
+
+struct ConstSrc { const float* bt[8]; const float* bb; const float* btr[3]; const float* ws; const float* wa; const float* wts; const float* wtb;
+                  const float* bs; const float* ba; const float* bts; const float* btb; };
+__global__ void pack_consts_kernel(ConstSrc c, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kCFloats) return;
+  float v = 0.f;
+  if (i < kCBiasBott) v = c.bt[i >> 8][i & 255];
+  else if (i < kCBiasTr) v = c.bb[i - kCBiasBott];
+  else if (i < kCWSigma) v = c.btr[(i - kCBiasTr) >> 7][(i - kCBiasTr) & 127];
+  else if (i < kCWAlb) v = c.ws[i - kCWSigma];
+  else if (i < kCWTs) v = c.wa[i - kCWAlb];
+  else if (i < kCWTb) v = c.wts[i - kCWTs];
+  else if (i < kCScalars) v = c.wtb[i - kCWTb];
+  else if (i == kCScalars) v = c.bs[0];
+  else if (i < kCScalars + 4) v = c.ba[i - kCScalars - 1];
+  else if (i == kCScalars + 4) v = c.bts[0];
+  else if (i == kCScalars + 5) v = c.btb[0];
+  dst[i] = v;
+}
+
+}  // namespace
+
+int64_t fused_prepared_extra_bytes(int64_t) { return fused_prep_layout().total; }
+int64_t fused_stash_bytes(int64_t n_pts, int density_only) { return fused_stash_layout(n_pts, density_only).total; }
+int64_t fused_scratch_bytes(int64_t n_pts, int64_t n_images, int density_only) {
+  return fused_scratch_layout(n_pts, n_images, density_only).total;
+}
+
+static void fwd_block_offsets(int* off) {
+  static const int nb[kFwdStages] = {2, 8, 8, 8, 8, 10, 8, 8, 8, 8, 2, 2, 2};
+  int o = 0;
+  for (int s = 0; s < kFwdStages; ++s) { off[s] = o; o += nb[s]; }
+}
+
+int fused_prepare(const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
+  const PrepLayout W = prep_layout(EONERF_FIELD_EONERF, EONERF_PREC_BF16, p->n_images);
+  const FusedPrepLayout F = fused_prep_layout();
+  uint8_t* base = (uint8_t*)prepared;
+  uint8_t* ext = base + W.total;
+  auto bf = [&](int64_t off) { return (const __nv_bfloat16*)(base + off); };
+  {  // forward blocks: stage-major, then output half, then k block;  B = W [out, Kp]
+    PackJobs J{};
+    int n = 0;
+    auto add = [&](const __nv_bfloat16* src, int ld, int out_rows, int kp) {
+      for (int h = 0; h < out_rows / 128; ++h)
+        for (int kb = 0; kb < kp / 64; ++kb) J.j[n++] = PackJob{src, ld, h * 128, 128, kb * 64};
+    };
+    for (int i = 0; i < 8; ++i) add(bf(W.w[i]), trunk_kp(i), kW, trunk_kp(i));
+    add(bf(W.bott), kW, kW, kW);
+    add(bf(W.hd0), kW, kW, kW);
+    for (int i = 0; i < 3; ++i) add(bf(W.tr[i]), kHid, kHid, kHid);
+    if (n != kFwdBlocks) { set_error("fused_prepare: forward block count %d != %d", n, kFwdBlocks); return EONERF_EINVAL; }
+    J.n = n;
+    pack_blocks_kernel<<<n * 4, 256, 0, s>>>(J, ext + F.fblob);
+    EO_LAUNCH_CHECK();
+  }
+  {  // backward blocks: B = W^T [in, out]
+    PackJobs J{};
+    int n = 0;
+    auto add = [&](const __nv_bfloat16* src, int ld, int row0, int rows, int out_cols) {
+      for (int h = 0; h < (rows + 127) / 128; ++h)
+        for (int kb = 0; kb < out_cols / 64; ++kb) {
+          const int rr = rows - h * 128 < 128 ? rows - h * 128 : 128;
+          J.j[n++] = PackJob{src, ld, row0 + h * 128, rr, kb * 64};
+        }
+    };
+    for (int i = 2; i >= 0; --i) add(bf(W.tr_t[i]), kHid, 0, kHid, kHid);      // S0..S2
+    add(bf(W.hd0_t), 2 * kHid, 0, kW, 2 * kHid);                               // S3
+    add(bf(W.bott_t), kW, 0, kW, kW);                                          // S4
+    add(bf(W.wt[7]), kW, 0, kW, kW);                                           // S5
+    add(bf(W.wt[6]), kW, 0, kW, kW);                                           // S6
+    add(bf(W.wt[5]), kW, kW, kEnc, kW);                                        // S7e: encoding rows of W5^T
+    add(bf(W.wt[5]), kW, 0, kW, kW);                                           // S7
+    for (int i = 4; i >= 1; --i) add(bf(W.wt[i]), kW, 0, kW, kW);              // S8..S11
+    add(bf(W.wt[0]), kW, 0, kEnc, kW);                                         // S12
+    if (n != kBwdBlocks) { set_error("fused_prepare: backward block count %d != %d", n, kBwdBlocks); return EONERF_EINVAL; }
+    J.n = n;
+    pack_blocks_kernel<<<n * 4, 256, 0, s>>>(J, ext + F.bblob);
+    EO_LAUNCH_CHECK();
+  }
+  ConstSrc c{};
+  for (int i = 0; i < 8; ++i) c.bt[i] = p->trunk_b[i];
+  c.bb = p->bott_b;
+  for (int i = 0; i < 3; ++i) c.btr[i] = p->trans_b[i + 1];
+  c.ws = p->sigma_w; c.wa = p->head1_w; c.wts = p->ts_w; c.wtb = p->tb_w;
+  c.bs = p->sigma_b; c.ba = p->head1_b; c.bts = p->ts_b; c.btb = p->tb_b;
+  pack_consts_kernel<<<div_up(kCFloats, 256), 256, 0, s>>>(c, (float*)(ext + F.consts));
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+static int fused_grid(int64_t n_pairs) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (int)(n_pairs < sms ? n_pairs : sms);
+}
+
+int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
+  EO_REQUIRE(a->field == EONERF_FIELD_EONERF, "fused precision mode supports the EO-NeRF field only");
+  const int64_t N = a->n_pts;
+  const EonerfFieldParams* prm = a->params;
+  const PrepLayout W = prep_layout(EONERF_FIELD_EONERF, EONERF_PREC_BF16, prm->n_images);
+  const FusedPrepLayout F = fused_prep_layout();
+  const uint8_t* ext = (const uint8_t*)a->prepared + W.total;
+  const bool train = a->stash != nullptr;
+  FusedFwdParams p{};
+  p.M = N;
+  p.n_tiles = (N + kTileM - 1) / kTileM;
+  p.n_stages = a->density_only ? 8 : kFwdStages;
+  p.training = train;
+  p.x = a->x;
+  p.origins = a->origins; p.o_stride = a->origins_stride; p.viewdirs = a->viewdirs; p.d_stride = a->viewdirs_stride;
+  p.ray_indices = a->ray_indices; p.t_starts = a->t_starts; p.t_ends = a->t_ends; p.z_mid = a->z_mid;
+  p.img_idx = a->density_only ? nullptr : a->img_idx; p.img_stride = a->img_idx_stride;
+  p.wblob = ext + F.fblob; p.consts = (const float*)(ext + F.consts);
+  p.class_bias = (const float*)((const uint8_t*)a->prepared + W.class_bias);
+  fwd_block_offsets(p.blk_off);
+  if (train) {
+    const FusedStashLayout S = fused_stash_layout(N, a->density_only);
+    uint8_t* st = (uint8_t*)a->stash;
+    for (int i = 0; i < kNumArr; ++i) p.arr[i] = S.arr[i] >= 0 ? st + S.arr[i] : nullptr;
+    for (int i = 0; i < kNumMask; ++i) p.mask[i] = S.mask[i] >= 0 ? (uint32_t*)(st + S.mask[i]) : nullptr;
+    p.xf = (float*)(st + S.xf);
+    p.cls = a->density_only ? nullptr : (int32_t*)(st + S.cls);
+  }
+  p.sigma = a->sigma; p.rgb = a->rgb; p.ts = a->transient_s; p.tb = a->transient_beta;
+  static bool configured = false;
+  if (!configured) {
+    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
+    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
+    configured = true;
+  }
+  const int64_t n_pairs = (p.n_tiles + 1) / 2;
+  const int grid = fused_grid(n_pairs);
+  const double flops = (double)N * (a->density_only ? 982528.0 : 1345280.0);
+  profile_begin(3, flops, 0.0, s);
+  if (train) fused_fwd_kernel<true><<<grid, kFusedThreads, kSmemFused, s>>>(p);
+  else fused_fwd_kernel<false><<<grid, kFusedThreads, kSmemFused, s>>>(p);
+  profile_end(s);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+int fused_field_bwd(const EonerfFieldBwdArgs*, cudaStream_t) {
+  set_error("fused_field_bwd: not built yet");
+  return EONERF_EINVAL;
+}
+
+int gemm_tn_blocked(const GemmTNBlocked&, cudaStream_t) {
+  set_error("gemm_tn_blocked: not built yet");
+  return EONERF_EINVAL;
+}
+
+}  // namespace eonerf

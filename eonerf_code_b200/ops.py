@@ -262,11 +262,13 @@ class FieldEngine:
     def scratch_bytes(self, n):
         return K.lib().eonerf_field_scratch_bytes(self.field, self.precision, n, self.n_images)
 
-    def fwd(self, n, density_only, x=None, rays=None, img_idx=None, cond_dirs=None, want_z=False):
-        """rays = (origins, viewdirs, ray_indices, t_starts, t_ends).  Returns dict of outputs + stash."""
+    def fwd(self, n, density_only, x=None, rays=None, img_idx=None, cond_dirs=None, want_z=False, keep=True):
+        """rays = (origins, viewdirs, ray_indices, t_starts, t_ends).  Returns dict of outputs + stash.
+        keep=False (inference): the fused mode keeps no activations at all; the layered modes still need the buffer."""
         dev = next(iter(self.named.values())).device
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        out = dict(sigma=f32(n), stash=torch.empty(self.stash_bytes(n, density_only), dtype=torch.uint8, device=dev))
+        no_stash = not keep and self.precision == K.PREC_BF16_FUSED
+        out = dict(sigma=f32(n), stash=None if no_stash else torch.empty(self.stash_bytes(n, density_only), dtype=torch.uint8, device=dev))
         a = K.FieldFwdArgs()
         ps = self.params_struct()
         a.field, a.precision, a.params, a.prepared, a.n_pts = self.field, self.precision, C.pointer(ps), _p(self.prepared()), n
@@ -359,7 +361,7 @@ class _FieldFn(torch.autograd.Function):
     def forward(ctx, engine, density_only, x, img_idx, cond_dirs, *params):
         _need_cuda(x)
         n = x.shape[0]
-        out = engine.fwd(n, density_only, x=x, img_idx=img_idx, cond_dirs=cond_dirs)
+        out = engine.fwd(n, density_only, x=x, img_idx=img_idx, cond_dirs=cond_dirs, keep=any(ctx.needs_input_grad))
         ctx.engine, ctx.density_only, ctx.n, ctx.out = engine, density_only, n, out
         ctx.x_needs_grad = x.requires_grad
         ctx.params = params
@@ -422,7 +424,7 @@ class _CameraPassFn(torch.autograd.Function):
         B, P = origins.shape[0], ts.numel()
         ri = ri.contiguous()
         f = engine.fwd(P, density_only=only_depth, rays=(origins, viewdirs, ri, ts, te),
-                       img_idx=None if only_depth else _img_idx_2d(img_idx), want_z=True)
+                       img_idx=None if only_depth else _img_idx_2d(img_idx), want_z=True, keep=any(ctx.needs_input_grad))
         set_last_t_end(te, offs)                                    # after z / positions were taken
         amb = amb_stash = None
         if not only_depth:
@@ -477,7 +479,7 @@ class _SunPassFn(torch.autograd.Function):
             u_sun = torch.rand(B, n_samples, dtype=torch.float32, device=dev)      # sat_rendering.py:52 via :93
         ri2, ts2, te2, sc_ppr, offs2, stats2 = sample_compact(sun[:, 0:3], sun[:, 3:6], None, u_sun, z_steps)
         Q = int(stats2[0])                                          # the one host sync of the sun pass
-        f2 = engine.fwd(Q, density_only=True, rays=(sun[:, 0:3], sun[:, 3:6], ri2, ts2, te2))
+        f2 = engine.fwd(Q, density_only=True, rays=(sun[:, 0:3], sun[:, 3:6], ri2, ts2, te2), keep=any(ctx.needs_input_grad))
         geo = torch.empty(B, 1, dtype=torch.float32, device=dev)
         a = K.ShadowFwdArgs(_p(ts2), _p(te2), _p(f2["sigma"]), _p(offs2), B, Q, _p(geo))
         K.call("shadow_fwd", a, _stream())

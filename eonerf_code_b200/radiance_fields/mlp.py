@@ -9,7 +9,7 @@ import torch.nn as nn
 from .. import _capi as K
 from .. import ops
 
-PRECISIONS = {"bf16": K.PREC_BF16, "fp32": K.PREC_FP32, "bf16_simt": K.PREC_BF16_SIMT}
+PRECISIONS = {"bf16": K.PREC_BF16, "fp32": K.PREC_FP32, "bf16_simt": K.PREC_BF16_SIMT, "bf16_fused": K.PREC_BF16_FUSED}
 
 
 class LayerStack(nn.Module):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 6
+#define EONERF_ABI_VERSION 7
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -231,10 +231,14 @@ int eonerf_epilogue_bwd(const EonerfEpilogueBwdArgs* a, eonerf_stream_t stream);
  * precision: EONERF_PREC_FP32       fp32 storage, SIMT kernels (exactness mode, used for the 1e-5 parity tests)
  *            EONERF_PREC_BF16       bf16 storage, tcgen05/TMEM/TMA tensor-core GEMMs, fp32 accumulation
  *            EONERF_PREC_BF16_SIMT  bf16 storage, SIMT GEMMs (on-device cross-check of the tensor-core kernels)
+ *            EONERF_PREC_BF16_FUSED bf16 storage, the whole MLP as one persistent tcgen05 kernel per direction; activations
+ *                                   stay in shared memory / TMEM between layers, the stash is tile-blocked (EO-NeRF field
+ *                                   only).  eonerf_field_fwd accepts stash == NULL in this mode: inference, nothing kept.
  * ---------------------------------------------------------------------------------------------- */
 #define EONERF_PREC_FP32 0
 #define EONERF_PREC_BF16 1
 #define EONERF_PREC_BF16_SIMT 2
+#define EONERF_PREC_BF16_FUSED 3
 
 #define EONERF_FIELD_EONERF 0
 #define EONERF_FIELD_VANILLA 1

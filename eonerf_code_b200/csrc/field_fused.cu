@@ -26,7 +26,7 @@ constexpr int kSlotBytes = 5 * kBlkBytes;                  // ACT blocks 0..3 + 
 constexpr int kOffRing = 0;
 constexpr int kOffSlot = kRingStages * kBlkBytes;          // 49152
 constexpr int kOffConst = kOffSlot + 2 * kSlotBytes;       // 212992
-constexpr int kConstBytes = 15360;
+constexpr int kConstBytes = 15872;
 constexpr int kOffPart = kOffConst + kConstBytes;          // [128][2] floats
 constexpr int kOffBar = kOffPart + 1024;
 constexpr int kSmemFused = kOffBar + 128 + 1024;           // + alignment slack
@@ -39,7 +39,7 @@ static_assert(kSmemFused <= 232448, "shared memory budget");
 // ---- forward program ------------------------------------------------------------------------------------------------
 struct FStage {
   int8_t halves, nkb, a[5], out_blk, relu, kind, mask, pad;
-  int16_t bias_off;            // float offset into the constants block, -1: per-image class bias from global
+  int16_t bias_off;            // float offset into the constants block
 };
 // kind: 0 plain, 1 + sigma head, 2 + albedo head (class bias), 3 + transient heads
 __constant__ FStage c_fstage[kFwdStages] = {
@@ -52,7 +52,7 @@ __constant__ FStage c_fstage[kFwdStages] = {
     {2, 4, {0, 1, 2, 3, 0}, 0, 1, 0, 6, 0, kCBiasTrunk + 6 * 256},
     {2, 4, {0, 1, 2, 3, 0}, 0, 1, 1, 7, 0, kCBiasTrunk + 7 * 256},
     {2, 4, {0, 1, 2, 3, 0}, 0, 0, 0, -1, 0, kCBiasBott},
-    {2, 4, {0, 1, 2, 3, 0}, 0, 1, 2, kMaskHd0, 0, -1},
+    {2, 4, {0, 1, 2, 3, 0}, 0, 1, 2, kMaskHd0, 0, kCBiasHd0},
     {1, 2, {2, 3, 0, 0, 0}, 0, 1, 0, kMaskT1 + 0, 0, kCBiasTr + 0 * 128},
     {1, 2, {0, 1, 0, 0, 0}, 2, 1, 0, kMaskT1 + 1, 0, kCBiasTr + 1 * 128},
     {1, 2, {2, 3, 0, 0, 0}, 0, 1, 3, kMaskT1 + 2, 0, kCBiasTr + 2 * 128},
@@ -64,7 +64,7 @@ struct FusedFwdParams {
   const float* origins; int64_t o_stride; const float* viewdirs; int64_t d_stride;
   const int64_t* ray_indices; const float* t_starts; const float* t_ends; float* z_mid;
   const int64_t* img_idx; int64_t img_stride;
-  const uint8_t* wblob; const float* consts; const float* class_bias;
+  const uint8_t* wblob; const float* consts; const float* class_delta;   // class_delta: [n_img,128] fp32
   int blk_off[kFwdStages];
   uint8_t* arr[kNumArr];
   uint32_t* mask[kNumMask];
@@ -85,17 +85,42 @@ __device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 
 // shared-memory byte offset of (row, 16-byte chunk) inside a [128 x 64] bf16 block
 __device__ __forceinline__ uint32_t blk_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
-// positional-encoding column c (0..63) of position x  (mlp.py:199-205; same arithmetic as encode_kernel in field.cu)
+// explicit shared-space accesses (the 1024-byte alignment arithmetic on the dynamic shared-memory base hides the address
+// space from the compiler, which would otherwise emit generic LD/ST)
+__device__ __forceinline__ void lds_f4(uint32_t a, float& x, float& y, float& z, float& w) {
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a));
+}
+__device__ __forceinline__ void lds_f2(uint32_t a, float& x, float& y) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_f2(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+// sin(a) for |a| < ~1e3: two-term Cody-Waite reduction to [-pi, pi] then MUFU.SIN.  Absolute error < 6e-7, far below
+// the bf16 resolution the value is rounded to (2^-9 relative), at ~7 instructions instead of ~45 for sinf().
+__device__ __forceinline__ float sin_reduced(float a) {
+  const float k = rintf(a * 0.15915494309189535f);
+  float rr = fmaf(k, -6.2831854820251465f, a);
+  rr = fmaf(k, 1.7484555314695172e-7f, rr);
+  return __sinf(rr);
+}
+
+// positional-encoding column kBase+c (c compile-time after unrolling) of position x
+// (mlp.py:199-205: [x, sin(2^k x) k=0..9 (frequency-major), sin(2^k x + pi/2)], column 63 is padding)
+template <int kBase>
 __device__ __forceinline__ float posenc_col(const float (&x)[3], int c) {
-  if (c < 3) return c == 0 ? x[0] : (c == 1 ? x[1] : x[2]);
+  c += kBase;
+  if (c < 3) return x[c];
   if (c >= 63) return 0.f;
   int e = c - 3;
   const int hf = e >= 30;
   e -= hf * 30;
-  const int dim = e % 3;
-  const float xv = dim == 0 ? x[0] : (dim == 1 ? x[1] : x[2]);
-  const float xb = xv * (float)(1 << (e / 3));
-  return sinf(hf ? __fadd_rn(xb, kHalfPi) : xb);
+  const float xb = x[e % 3] * (float)(1 << (e / 3));
+  return sin_reduced(hf ? __fadd_rn(xb, kHalfPi) : xb);                  // torch adds the scalar in fp32 (mlp.py:203)
 }
 
 template <bool kTrain>
@@ -180,9 +205,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;                    // row of the tile
-    uint32_t cph = 0;                                    // bit `slot` = phase of acc_full[slot]
+    const uint32_t s_cst = smem_u32(cst);
+    const uint32_t s_part = smem_u32(part);
+    uint32_t cph = 0;                               // bit `slot` = phase of acc_full[slot]
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      uint32_t cls_pack = 0;                             // image index of this row in slot 0 (low 16 bits) / slot 1
+      uint32_t cls_pack = 0;                        // image index of this row in slot 0 (low 16 bits) / slot 1
       // ---- positional encoding of both tiles ----
       if (e == 0) tma_store_wait_read<0>();
       named_bar_sync(1, kEpiThreads);
@@ -215,17 +242,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
             if (p.cls) p.cls[pt] = (int32_t)((cls_pack >> (16 * slot)) & 0xFFFFu);
           }
         }
-        uint8_t* enc = smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes;
+        const uint32_t enc = smem_u32(smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes);
+        uint32_t w[16];
+        if (half == 0) {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          uint32_t w[4];
+          for (int u = 0; u < 16; ++u) w[u] = pack_bf16(posenc_col<0>(x, 2 * u), posenc_col<0>(x, 2 * u + 1));
+        } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = half * 32 + jj * 8 + u * 2;
-            w[u] = pack_bf16(posenc_col(x, c), posenc_col(x, c + 1));
-          }
-          *(uint4*)(enc + blk_off(r, half * 4 + jj)) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int u = 0; u < 16; ++u) w[u] = pack_bf16(posenc_col<32>(x, 2 * u), posenc_col<32>(x, 2 * u + 1));
         }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) sts_u4(enc + blk_off(r, half * 4 + jj), w[4 * jj], w[4 * jj + 1], w[4 * jj + 2], w[4 * jj + 3]);
       }
       fence_proxy_async();
       named_bar_sync(1, kEpiThreads);
@@ -247,84 +274,91 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         const FStage d = c_fstage[s];
         const int cpt = d.halves == 2 ? 128 : 64;          // columns per thread
         const int col0 = half * cpt;
+        const float relu_lo = d.relu ? 0.f : -INFINITY;
         for (int slot = 0; slot < 2; ++slot) {
           const int64_t tile = 2 * pair + slot;
           const int64_t pt = tile * kTileM + r;
           const bool valid = pt < p.M;
-          uint8_t* act = smem + kOffSlot + slot * kSlotBytes;
-          const float* brow = d.bias_off >= 0 ? nullptr : p.class_bias + (size_t)((cls_pack >> (16 * slot)) & 0xFFFFu) * 256;
+          const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
+          // per-image part of the HD0 bias (transient half only): W[:,256:260] . emb[img]
+          const float* delta = (d.kind == 2 && half == 1) ? p.class_delta + (size_t)((cls_pack >> (16 * slot)) & 0xFFFFu) * kHid : nullptr;
           mbar_wait(&acc_full[slot], (cph >> slot) & 1u);
           cph ^= 1u << slot;
           tc_fence_after();
-          if (e == 0) tma_store_wait_read<0>();              // earlier stash stores have finished reading this slot
+          if (e == 0) tma_store_wait_read<1>();             // this slot's previous stash store has drained (the other slot's may be in flight)
           named_bar_sync(1, kEpiThreads);
           const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + col0;
           float h0 = 0.f, h1 = 0.f, h2 = 0.f;               // head partial sums
-          uint32_t mbits[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c * 32 >= cpt) break;
+          uint32_t* mrow = (kTrain && d.mask >= 0 && valid) ? p.mask[d.mask] + pt * 8 + col0 / 32 : nullptr;
+#pragma unroll 1
+          for (int c = 0; c < cpt / 32; ++c) {
             uint32_t v[32];
             tmem_ld32(taddr + c * 32, v);
             float b[32];
-            if (d.bias_off >= 0) {
-              const float4* bp = (const float4*)(cst + d.bias_off + col0 + c * 32);
+            const uint32_t sb = s_cst + (uint32_t)(d.bias_off + col0 + c * 32) * 4u;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { const float4 t = bp[j]; b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w; }
-            } else {
-              const float4* bp = (const float4*)(brow + col0 + c * 32);
+            for (int j = 0; j < 8; ++j) lds_f4(sb + j * 16, b[4 * j], b[4 * j + 1], b[4 * j + 2], b[4 * j + 3]);
+            if (delta) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { const float4 t = __ldg(bp + j); b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w; }
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = __ldg((const float4*)(delta + c * 32) + j);
+                b[4 * j] += t.x; b[4 * j + 1] += t.y; b[4 * j + 2] += t.z; b[4 * j + 3] += t.w;
+              }
             }
             tmem_ld_wait();
             uint32_t pk[16];
-            uint32_t bits = 0u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float f0 = __uint_as_float(v[2 * j]) + b[2 * j], f1 = __uint_as_float(v[2 * j + 1]) + b[2 * j + 1];
-              if (d.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-              pk[j] = pack_bf16(f0, f1);
-              bits |= ((pk[j] & 0x7FFFu) ? 1u : 0u) << (2 * j);
-              bits |= ((pk[j] & 0x7FFF0000u) ? 1u : 0u) << (2 * j + 1);
+            for (int j = 0; j < 16; ++j)
+              pk[j] = pack_bf16(fmaxf(__uint_as_float(v[2 * j]) + b[2 * j], relu_lo), fmaxf(__uint_as_float(v[2 * j + 1]) + b[2 * j + 1], relu_lo));
+            if (mrow) {                                       // ReLU sign bits: column 2j -> bit 15-j, column 2j+1 -> bit 31-j
+              uint32_t bits = 0u;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) bits |= ((pk[j] + 0x7FFF7FFFu) >> j) & (0x80008000u >> j);
+              mrow[c] = bits;
             }
-            mbits[c] = bits;
             if (d.kind == 1) {
-              const float4* wp = (const float4*)(cst + kCWSigma + col0 + c * 32);
+              const uint32_t sw = s_cst + (uint32_t)(kCWSigma + col0 + c * 32) * 4u;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 w = wp[j];
-                h0 = fmaf(bf_lo(pk[2 * j]), w.x, h0); h0 = fmaf(bf_hi(pk[2 * j]), w.y, h0);
-                h0 = fmaf(bf_lo(pk[2 * j + 1]), w.z, h0); h0 = fmaf(bf_hi(pk[2 * j + 1]), w.w, h0);
+                float w0, w1, w2, w3;
+                lds_f4(sw + j * 16, w0, w1, w2, w3);
+                h0 = fmaf(bf_lo(pk[2 * j]), w0, h0); h0 = fmaf(bf_hi(pk[2 * j]), w1, h0);
+                h0 = fmaf(bf_lo(pk[2 * j + 1]), w2, h0); h0 = fmaf(bf_hi(pk[2 * j + 1]), w3, h0);
               }
             } else if (d.kind == 2) {
               if (half == 0) {
-                const float* wa = cst + kCWAlb + c * 32;
+                const uint32_t sw = s_cst + (uint32_t)(kCWAlb + c * 32) * 4u;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float lo = bf_lo(pk[j]), hi = bf_hi(pk[j]);
-                  h0 = fmaf(lo, wa[2 * j], h0); h0 = fmaf(hi, wa[2 * j + 1], h0);
-                  h1 = fmaf(lo, wa[128 + 2 * j], h1); h1 = fmaf(hi, wa[128 + 2 * j + 1], h1);
-                  h2 = fmaf(lo, wa[256 + 2 * j], h2); h2 = fmaf(hi, wa[256 + 2 * j + 1], h2);
+                for (int j = 0; j < 8; ++j) {
+                  float w0, w1, w2, w3;
+                  const float a0 = bf_lo(pk[2 * j]), a1 = bf_hi(pk[2 * j]), a2 = bf_lo(pk[2 * j + 1]), a3 = bf_hi(pk[2 * j + 1]);
+                  lds_f4(sw + j * 16, w0, w1, w2, w3);
+                  h0 = fmaf(a0, w0, h0); h0 = fmaf(a1, w1, h0); h0 = fmaf(a2, w2, h0); h0 = fmaf(a3, w3, h0);
+                  lds_f4(sw + 512 + j * 16, w0, w1, w2, w3);
+                  h1 = fmaf(a0, w0, h1); h1 = fmaf(a1, w1, h1); h1 = fmaf(a2, w2, h1); h1 = fmaf(a3, w3, h1);
+                  lds_f4(sw + 1024 + j * 16, w0, w1, w2, w3);
+                  h2 = fmaf(a0, w0, h2); h2 = fmaf(a1, w1, h2); h2 = fmaf(a2, w2, h2); h2 = fmaf(a3, w3, h2);
                 }
               }
             } else if (d.kind == 3) {
-              const float* ws = cst + kCWTs + col0 + c * 32;
-              const float* wb = cst + kCWTb + col0 + c * 32;
+              const uint32_t sw = s_cst + (uint32_t)(kCWTs + col0 + c * 32) * 4u;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float lo = bf_lo(pk[j]), hi = bf_hi(pk[j]);
-                h0 = fmaf(lo, ws[2 * j], h0); h0 = fmaf(hi, ws[2 * j + 1], h0);
-                h1 = fmaf(lo, wb[2 * j], h1); h1 = fmaf(hi, wb[2 * j + 1], h1);
+              for (int j = 0; j < 8; ++j) {
+                float w0, w1, w2, w3;
+                const float a0 = bf_lo(pk[2 * j]), a1 = bf_hi(pk[2 * j]), a2 = bf_lo(pk[2 * j + 1]), a3 = bf_hi(pk[2 * j + 1]);
+                lds_f4(sw + j * 16, w0, w1, w2, w3);
+                h0 = fmaf(a0, w0, h0); h0 = fmaf(a1, w1, h0); h0 = fmaf(a2, w2, h0); h0 = fmaf(a3, w3, h0);
+                lds_f4(sw + (kCWTb - kCWTs) * 4 + j * 16, w0, w1, w2, w3);
+                h1 = fmaf(a0, w0, h1); h1 = fmaf(a1, w1, h1); h1 = fmaf(a2, w2, h1); h1 = fmaf(a3, w3, h1);
               }
             }
             const int colg = col0 + c * 32;                   // first output column of this chunk
-            uint8_t* blk = act + (d.out_blk + (colg >> 6)) * kBlkBytes;
+            const uint32_t blk = act + (uint32_t)(d.out_blk + (colg >> 6)) * kBlkBytes;
             const int ch0 = (colg & 63) >> 3;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              *(uint4*)(blk + blk_off(r, ch0 + jj)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+            for (int jj = 0; jj < 4; ++jj) sts_u4(blk + blk_off(r, ch0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
           }
-          if (half == 1 && (d.kind == 1 || d.kind == 3)) { part[2 * r] = h0; part[2 * r + 1] = h1; }
+          if (half == 1 && (d.kind == 1 || d.kind == 3)) sts_f2(s_part + r * 8, h0, h1);
           tc_fence_before();
           fence_proxy_async();
           named_bar_sync(1, kEpiThreads);
@@ -332,28 +366,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
             if (s + 1 < p.n_stages) mbar_arrive(&act_ready[slot]);
             if (kTrain && tile < p.n_tiles) {
               const int nb = d.halves * 2;
-              for (int b = 0; b < nb; ++b)
-                bulk_store(p.arr[s] + ((size_t)tile * nb + b) * kBlkBytes, act + (d.out_blk + b) * kBlkBytes, kBlkBytes);
-              tma_store_commit();
+              for (int bb = 0; bb < nb; ++bb)
+                bulk_store(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes,
+                           kBlkBytes);
             }
+            if (kTrain) tma_store_commit();                  // always one group per (stage, slot): wait_group.read 1 counts on it
           }
-          if (valid) {
-            if (half == 0) {
-              if (d.kind == 1) {
-                p.sigma[pt] = softplus_f(h0 + part[2 * r] + cst[kCScalars + 0]);               // eonerf.py:106,145
-              } else if (d.kind == 2) {
-                p.rgb[3 * pt + 0] = sigmoid_f(h0 + cst[kCScalars + 1]);
-                p.rgb[3 * pt + 1] = sigmoid_f(h1 + cst[kCScalars + 2]);
-                p.rgb[3 * pt + 2] = sigmoid_f(h2 + cst[kCScalars + 3]);
-              } else if (d.kind == 3) {
-                p.ts[pt] = sigmoid_f(h0 + part[2 * r] + cst[kCScalars + 4]);
-                p.tb[pt] = softplus_f(h1 + part[2 * r + 1] + cst[kCScalars + 5]);
-              }
-            }
-            if (kTrain && d.mask >= 0) {
-              uint32_t* mrow = p.mask[d.mask] + pt * 8;
-              if (cpt == 128) *(uint4*)(mrow + half * 4) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-              else *(uint2*)(mrow + half * 2) = make_uint2(mbits[0], mbits[1]);
+          if (valid && half == 0 && d.kind != 0) {
+            float p0 = 0.f, p1 = 0.f;
+            if (d.kind != 2) lds_f2(s_part + r * 8, p0, p1);
+            if (d.kind == 1) {
+              p.sigma[pt] = softplus_f(h0 + p0 + cst[kCScalars + 0]);                          // eonerf.py:106,145
+            } else if (d.kind == 2) {
+              p.rgb[3 * pt + 0] = sigmoid_f(h0 + cst[kCScalars + 1]);
+              p.rgb[3 * pt + 1] = sigmoid_f(h1 + cst[kCScalars + 2]);
+              p.rgb[3 * pt + 2] = sigmoid_f(h2 + cst[kCScalars + 3]);
+            } else {
+              p.ts[pt] = sigmoid_f(h0 + p0 + cst[kCScalars + 4]);
+              p.tb[pt] = softplus_f(h1 + p1 + cst[kCScalars + 5]);
             }
           }
         }
@@ -386,7 +416,7 @@ __global__ void __launch_bounds__(256) pack_blocks_kernel(const __grid_constant_
 }
 
 struct ConstSrc { const float* bt[8]; const float* bb; const float* btr[3]; const float* ws; const float* wa; const float* wts; const float* wtb;
-                  const float* bs; const float* ba; const float* bts; const float* btb; };
+                  const float* bs; const float* ba; const float* bts; const float* btb; const float* bh0; const float* bt0; };
 __global__ void pack_consts_kernel(ConstSrc c, float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kCFloats) return;
@@ -402,12 +432,25 @@ __global__ void pack_consts_kernel(ConstSrc c, float* __restrict__ dst) {
   else if (i < kCScalars + 4) v = c.ba[i - kCScalars - 1];
   else if (i == kCScalars + 4) v = c.bts[0];
   else if (i == kCScalars + 5) v = c.btb[0];
+  else if (i >= kCBiasHd0 && i < kCBiasHd0 + kHid) v = c.bh0[i - kCBiasHd0];
+  else if (i >= kCBiasHd0 + kHid) v = c.bt0[i - kCBiasHd0 - kHid];
   dst[i] = v;
+}
+
+// delta[img, j] = sum_e W_t0[j, 256+e] emb[img, e]
+__global__ void class_delta_kernel(const float* __restrict__ wt0, const float* __restrict__ emb, int64_t n_images, float* __restrict__ delta) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_images * kHid) return;
+  const int img = idx / kHid, j = idx % kHid;
+  float v = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v = fmaf(__ldg(wt0 + j * 260 + 256 + e), __ldg(emb + img * 4 + e), v);
+  delta[idx] = v;
 }
 
 }  // namespace
 
-int64_t fused_prepared_extra_bytes(int64_t) { return fused_prep_layout().total; }
+int64_t fused_prepared_extra_bytes(int64_t n_images) { return fused_prep_layout(n_images).total; }
 int64_t fused_stash_bytes(int64_t n_pts, int density_only) { return fused_stash_layout(n_pts, density_only).total; }
 int64_t fused_scratch_bytes(int64_t n_pts, int64_t n_images, int density_only) {
   return fused_scratch_layout(n_pts, n_images, density_only).total;
@@ -421,7 +464,7 @@ static void fwd_block_offsets(int* off) {
 
 int fused_prepare(const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
   const PrepLayout W = prep_layout(EONERF_FIELD_EONERF, EONERF_PREC_BF16, p->n_images);
-  const FusedPrepLayout F = fused_prep_layout();
+  const FusedPrepLayout F = fused_prep_layout(p->n_images);
   uint8_t* base = (uint8_t*)prepared;
   uint8_t* ext = base + W.total;
   auto bf = [&](int64_t off) { return (const __nv_bfloat16*)(base + off); };
@@ -471,7 +514,10 @@ int fused_prepare(const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
   for (int i = 0; i < 3; ++i) c.btr[i] = p->trans_b[i + 1];
   c.ws = p->sigma_w; c.wa = p->head1_w; c.wts = p->ts_w; c.wtb = p->tb_w;
   c.bs = p->sigma_b; c.ba = p->head1_b; c.bts = p->ts_b; c.btb = p->tb_b;
+  c.bh0 = p->head0_b; c.bt0 = p->trans_b[0];
   pack_consts_kernel<<<div_up(kCFloats, 256), 256, 0, s>>>(c, (float*)(ext + F.consts));
+  EO_LAUNCH_CHECK();
+  class_delta_kernel<<<div_up(p->n_images * kHid, 128), 128, 0, s>>>(p->trans_w[0], p->transient_emb, p->n_images, (float*)(ext + F.delta));
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -488,7 +534,7 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   const int64_t N = a->n_pts;
   const EonerfFieldParams* prm = a->params;
   const PrepLayout W = prep_layout(EONERF_FIELD_EONERF, EONERF_PREC_BF16, prm->n_images);
-  const FusedPrepLayout F = fused_prep_layout();
+  const FusedPrepLayout F = fused_prep_layout(prm->n_images);
   const uint8_t* ext = (const uint8_t*)a->prepared + W.total;
   const bool train = a->stash != nullptr;
   FusedFwdParams p{};
@@ -501,7 +547,7 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   p.ray_indices = a->ray_indices; p.t_starts = a->t_starts; p.t_ends = a->t_ends; p.z_mid = a->z_mid;
   p.img_idx = a->density_only ? nullptr : a->img_idx; p.img_stride = a->img_idx_stride;
   p.wblob = ext + F.fblob; p.consts = (const float*)(ext + F.consts);
-  p.class_bias = (const float*)((const uint8_t*)a->prepared + W.class_bias);
+  p.class_delta = (const float*)(ext + F.delta);
   fwd_block_offsets(p.blk_off);
   if (train) {
     const FusedStashLayout S = fused_stash_layout(N, a->density_only);

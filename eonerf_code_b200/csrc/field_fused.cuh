@@ -78,24 +78,27 @@ constexpr int kCWAlb = 2944;          // 3 x 128
 constexpr int kCWTs = 3328;           // 128
 constexpr int kCWTb = 3456;           // 128
 constexpr int kCScalars = 3584;       // b_sigma, b_alb[3], b_ts, b_tb
-constexpr int kCFloats = 3600;
+constexpr int kCBiasHd0 = 3600;       // 256: [albedo_mlp.0.bias | transient_mlp.0.bias]  (the per-image part is `delta`)
+constexpr int kCFloats = 3856;
 
 // weight-block programs: forward 13 stages, backward 15 stages (see field_fused.cu)
 constexpr int kFwdStages = 13;
 constexpr int kFwdBlocks = 2 + 4 * 8 + 10 + 2 * 8 + 8 + 8 + 3 * 2;   // 82
-constexpr int kBwdStages = 15;
+constexpr int kBwdStages = 14;
 constexpr int kBwdBlocks = 3 * 2 + 8 + 8 + 8 + 8 + 4 + 8 + 4 * 8 + 4;  // 86
 
 struct FusedPrepLayout {
-  int64_t fblob, bblob, consts, total;   // relative to the start of the fused extras
+  int64_t fblob, bblob, consts, delta, total;   // relative to the start of the fused extras
 };
-static inline FusedPrepLayout fused_prep_layout() {
+// delta: fp32 [n_img,128] = W_t0[:,256:260] . emb[img]  (eonerf.py:165-167: the transient embedding enters as a bias row)
+static inline FusedPrepLayout fused_prep_layout(int64_t n_images) {
   FusedPrepLayout L{};
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes, 1024); return o; };
   L.fblob = take((int64_t)kFwdBlocks * kBlkBytes);
   L.bblob = take((int64_t)kBwdBlocks * kBlkBytes);
   L.consts = take(kCFloats * 4);
+  L.delta = take((n_images > 0 ? n_images : 1) * kHid * 4);
   L.total = off;
   return L;
 }

@@ -101,7 +101,10 @@ def test_fused_stash_is_the_blocked_image_of_the_layered_stash(cuda):
         off += al(n * ld * 2)
     enc_f = unblock(st, L["arr"][13][0], L["n_tiles"], 1)[:n].float()
     enc_l = layered(lay_h[4][0], 320, 320)[:, 256:320].float()
-    assert torch.equal(enc_f, enc_l)                     # same arithmetic: bit-identical encoding
+    # the fused kernel evaluates the sines with a Cody-Waite reduction + MUFU.SIN (abs error < 6e-7) instead of sinf():
+    # after rounding to bf16 a value may land on the neighbouring bf16 number, rarely
+    d = (enc_f - enc_l).abs()
+    assert float(d.max()) <= 2 ** -8 and float((d > 0).float().mean()) < 2e-3
     h0_f = unblock(st, L["arr"][0][0], L["n_tiles"], 4)[:n].float()
     h0_l = layered(lay_h[0][0], 256, 256).float()
     d = (h0_f - h0_l).abs()
@@ -112,7 +115,9 @@ def test_fused_stash_is_the_blocked_image_of_the_layered_stash(cuda):
     # ReLU sign bits agree with the stashed activations they were taken from
     for stage, arr in ((0, h0_f), (7, h7_f)):
         m = st[L["mask"][stage]:L["mask"][stage] + n * 32].view(torch.int32).view(n, 8)
-        bits = ((m[:, :, None] >> torch.arange(32, device=cuda)[None, None, :]) & 1).reshape(n, 256).bool()
+        j = torch.arange(16, device=cuda)
+        pos = torch.stack([15 - j, 31 - j], 1).reshape(32)            # column 2j -> bit 15-j, column 2j+1 -> bit 31-j
+        bits = ((m[:, :, None] >> pos[None, None, :]) & 1).reshape(n, 256).bool()
         assert torch.equal(bits, arr > 0)
 
 

@@ -1,0 +1,682 @@
+// Fused input-gradient chain of the radiance-field MLP for sm_100a (autograd backward of
+// /root/reference/radiance_fields/eonerf.py:141-170 / mlp.py:87-101 with respect to the activations and positions).
+//
+// Same machine as the fused forward (field_fused.cu): one weight-producer warp, one MMA-issuer warp, eight epilogue
+// warps, two 128-sample tiles ping-ponging per CTA, accumulators in TMEM, the running gradient G (wrt a layer's
+// pre-activation) kept as the bf16 A operand in shared memory.  Per stage   G_prev = (G . W) * relu'(h_prev)   with the
+// ReLU derivative taken from the forward's sign bits (32 B per sample per layer instead of re-reading activations).
+// Every G is also stored tile-blocked to HBM: the parameter gradients dW = G^T X are separate tcgen05 GEMMs over the
+// blocked G and the blocked forward stash (gemm_tn_blocked), because all layers' dW accumulators cannot live in TMEM.
+//
+// stage   A (G of)      B = W^T of            epilogue                                         output
+//  0      T3            transient_mlp.3       mask T2                                          G_T2  -> blocks 2,3
+//  1      T2            transient_mlp.2       mask T1                                          G_T1  -> blocks 0,1
+//  2      T1            transient_mlp.1       mask HD0[:,128:]; + albedo head part (SIMT)      G_HD0 -> blocks 0..3
+//  3      HD0           [albedo_mlp.0;t_mlp.0] none (bottleneck is linear)                     G_BOTT
+//  4      BOTT          bottleneck            + dsigma (x) w_sigma, mask H7                    G_H7
+//  5,6    H7, H6        base_mlp.7, .6        mask H6, H5                                      G_H6, G_H5
+//  7      H5            base_mlp.5[:,256:319] none                                             G_ENC5 -> DENC block (only if g_x wanted)
+//  8      H5            base_mlp.5[:,0:256]   mask H4                                          G_H4
+//  9..12  H4..H1        base_mlp.4 .. .1      mask H3..H0                                      G_H3..G_H0
+//  13     H0            base_mlp.0            + G_ENC5, positional-encoding backward           g_x (only if wanted)
+#include "fused_common.cuh"
+
+namespace eonerf {
+
+namespace {
+
+struct BStage {
+  int8_t halves, nkb, a[4], out_blk, mask, mask_w0, kind, garr, pad;
+};
+// kind: 0 plain, 1 + albedo head part, 2 + sigma rank-1 term, 3 encoding part of layer 5, 4 final (positions)
+__constant__ BStage c_bstage[kBwdStages] = {
+    {1, 2, {0, 1, 0, 0}, 2, kMaskT1 + 1, 0, 0, 11, 0},
+    {1, 2, {2, 3, 0, 0}, 0, kMaskT1 + 0, 0, 0, 10, 0},
+    {1, 2, {0, 1, 0, 0}, 2, kMaskHd0, 4, 1, 9, 0},
+    {2, 4, {0, 1, 2, 3}, 0, -1, 0, 0, 8, 0},
+    {2, 4, {0, 1, 2, 3}, 0, kMaskH0 + 7, 0, 2, 7, 0},
+    {2, 4, {0, 1, 2, 3}, 0, kMaskH0 + 6, 0, 0, 6, 0},
+    {2, 4, {0, 1, 2, 3}, 0, kMaskH0 + 5, 0, 0, 5, 0},
+    {1, 4, {0, 1, 2, 3}, 4, -1, 0, 3, -1, 0},
+    {2, 4, {0, 1, 2, 3}, 0, kMaskH0 + 4, 0, 0, 4, 0},
+    {2, 4, {0, 1, 2, 3}, 0, kMaskH0 + 3, 0, 0, 3, 0},
+    {2, 4, {0, 1, 2, 3}, 0, kMaskH0 + 2, 0, 0, 2, 0},
+    {2, 4, {0, 1, 2, 3}, 0, kMaskH0 + 1, 0, 0, 1, 0},
+    {2, 4, {0, 1, 2, 3}, 0, kMaskH0 + 0, 0, 0, 0, 0},
+    {1, 4, {0, 1, 2, 3}, 0, -1, 0, 4, -1, 0},
+};
+static const int kBwdBlkCount[kBwdStages] = {2, 2, 2, 8, 8, 8, 8, 4, 8, 8, 8, 8, 8, 4};
+
+struct FusedBwdParams {
+  int64_t M; int64_t n_tiles;
+  int n_prog; int8_t prog[kBwdStages];
+  int density_only;
+  const uint8_t* wblob; const float* consts;
+  int blk_off[kBwdStages];
+  const uint32_t* mask[kNumMask];
+  uint8_t* garr[13];
+  const float* xf;
+  // forward outputs and incoming gradients (any g_* may be NULL = 0)
+  const float* sigma; const float* rgb; const float* ts; const float* tb;
+  const float* g_sigma; const float* g_rgb; const float* g_ts; const float* g_tb;
+  float* dpre;         // [Mpad, 8]: 0 sigma, 1..3 albedo, 4 transient_s, 5 transient_beta (pre-activation gradients of the heads)
+  float* g_x;          // [M, 3] or NULL
+};
+
+// shared-memory use of the constants region in this kernel: head weights (kCWSigma.. as in the forward), then per-row
+// head gradients [2 slots][128 rows][4] = (dsigma, drgb0, drgb1, drgb2)
+constexpr int kOffRows = kOffConst + 4096;
+static_assert(4096 + 2 * 128 * 16 <= kConstBytes, "row scalars do not fit");
+
+// keep[j] of a packed bf16 pair: sign-bit layout written by the forward (column 2j -> bit 15-j, column 2j+1 -> bit 31-j)
+__device__ __forceinline__ uint32_t apply_mask(uint32_t pk, uint32_t m, int j) {
+  const uint32_t sel = ((m << j) & 0x80008000u) >> 15;       // 0x00010001 pattern of the kept halves
+  return pk & (sel * 0xFFFFu);
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __grid_constant__ FusedBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* w_full = (uint64_t*)(smem + kOffBar);
+  uint64_t* w_empty = w_full + kRingStages;
+  uint64_t* acc_full = w_empty + kRingStages;
+  uint64_t* act_ready = acc_full + 2;
+  uint32_t* tmem_base_s = (uint32_t*)(act_ready + 2);
+  float* hw = (float*)(smem + kOffConst);                   // head weights: w_sigma 256 | w_alb 384 | w_ts 128 | w_tb 128
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRingStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&act_ready[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_s, 512);
+  for (int i = threadIdx.x; i < 896; i += kFusedThreads) hw[i] = __ldg(p.consts + kCWSigma + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+  const int64_t n_pairs = (p.n_tiles + 1) / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== weight producer =====
+      int rs = 0; uint32_t rph = 0;
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (int i = 0; i < p.n_prog; ++i) {
+          const int s = p.prog[i];
+          const int nblk = c_bstage[s].halves * c_bstage[s].nkb;
+          const uint8_t* src = p.wblob + (size_t)p.blk_off[s] * kBlkBytes;
+          for (int rep = 0; rep < 2; ++rep)
+            for (int b = 0; b < nblk; ++b) {
+              mbar_wait(&w_empty[rs], rph ^ 1);
+              mbar_expect_tx(&w_full[rs], kBlkBytes);
+              bulk_load(smem + kOffRing + rs * kBlkBytes, src + (size_t)b * kBlkBytes, kBlkBytes, &w_full[rs]);
+              if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+            }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = instr_desc(128, 128, 0, 0);
+      int rs = 0; uint32_t rph = 0;
+      uint32_t aph = 0;
+      const uint32_t ring0 = smem_u32(smem + kOffRing);
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (int i = 0; i < p.n_prog; ++i) {
+          const BStage d = c_bstage[p.prog[i]];
+          for (int slot = 0; slot < 2; ++slot) {
+            mbar_wait(&act_ready[slot], (aph >> slot) & 1u);
+            aph ^= 1u << slot;
+            tc_fence_after();
+            const uint32_t slot0 = smem_u32(smem + kOffSlot + slot * kSlotBytes);
+            for (int h = 0; h < d.halves; ++h) {
+              const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
+              for (int kb = 0; kb < d.nkb; ++kb) {
+                mbar_wait(&w_full[rs], rph);
+                tc_fence_after();
+                const uint32_t sa = slot0 + d.a[kb] * kBlkBytes;
+                const uint32_t sb = ring0 + rs * kBlkBytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0);
+                umma_commit(&w_empty[rs]);
+                if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+              }
+            }
+            umma_commit(&acc_full[slot]);
+          }
+        }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int e = threadIdx.x - 64;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t s_hw = smem_u32(hw);
+    uint32_t cph = 0;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      // ---- head gradients -> first G of the chain ----
+      if (e == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, kEpiThreads);
+      for (int slot = 0; slot < 2; ++slot) {
+        const int64_t tile = 2 * pair + slot;
+        const int64_t pt = tile * kTileM + r;
+        const bool valid = pt < p.M;
+        const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
+        const uint32_t s_row = smem_u32(smem + kOffRows) + (uint32_t)(slot * 128 + r) * 16u;
+        float dsig = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, dts = 0.f, dtb = 0.f;
+        if (valid) {
+          // derivatives through the forward outputs: softplus' = 1 - exp(-y), sigmoid' = y (1 - y)
+          if (p.g_sigma) dsig = __ldg(p.g_sigma + pt) * (-expm1f(-__ldg(p.sigma + pt)));
+          if (!p.density_only) {
+            if (p.g_rgb) {
+              const float y0 = __ldg(p.rgb + 3 * pt), y1 = __ldg(p.rgb + 3 * pt + 1), y2 = __ldg(p.rgb + 3 * pt + 2);
+              d0 = __ldg(p.g_rgb + 3 * pt) * y0 * (1.0f - y0);
+              d1 = __ldg(p.g_rgb + 3 * pt + 1) * y1 * (1.0f - y1);
+              d2 = __ldg(p.g_rgb + 3 * pt + 2) * y2 * (1.0f - y2);
+            }
+            if (p.g_ts) { const float y = __ldg(p.ts + pt); dts = __ldg(p.g_ts + pt) * y * (1.0f - y); }
+            if (p.g_tb) dtb = __ldg(p.g_tb + pt) * (-expm1f(-__ldg(p.tb + pt)));
+          }
+        }
+        if (half == 0) {
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_row), "f"(dsig), "f"(d0), "f"(d1), "f"(d2) : "memory");
+          if (tile < p.n_tiles) {                            // rows of the padded tail are zero: they add nothing to dW
+            float* dp = p.dpre + pt * 8;
+            *(float4*)dp = make_float4(dsig, d0, d1, d2);
+            *(float4*)(dp + 4) = make_float4(dts, dtb, 0.f, 0.f);
+          }
+        }
+        if (p.density_only) {
+          // G_H7 = dsigma (x) w_sigma, masked by H7 > 0: thread covers columns half*128 .. +128
+          uint4 mw = make_uint4(0, 0, 0, 0);
+          if (valid) mw = __ldg((const uint4*)(p.mask[kMaskH0 + 7] + pt * 8 + half * 4));
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t m = c == 0 ? mw.x : (c == 1 ? mw.y : (c == 2 ? mw.z : mw.w));
+            const uint32_t sw = s_hw + (uint32_t)(half * 128 + c * 32) * 4u;
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float w0, w1, w2, w3;
+              lds_f4(sw + j * 16, w0, w1, w2, w3);
+              pk[2 * j] = apply_mask(pack_bf16(dsig * w0, dsig * w1), m, 2 * j);
+              pk[2 * j + 1] = apply_mask(pack_bf16(dsig * w2, dsig * w3), m, 2 * j + 1);
+            }
+            const int colg = half * 128 + c * 32;
+            const uint32_t blk = act + (uint32_t)(colg >> 6) * kBlkBytes;
+            const int ch0 = (colg & 63) >> 3;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) sts_u4(blk + blk_off(r, ch0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+        } else {
+          // G_T3 = (dts (x) w_ts + dtb (x) w_tb), masked by T3 > 0: thread covers columns half*64 .. +64 -> blocks 0,1
+          uint2 mw = make_uint2(0, 0);
+          if (valid) mw = __ldg((const uint2*)(p.mask[kMaskT1 + 2] + pt * 8 + half * 2));
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t m = c == 0 ? mw.x : mw.y;
+            const uint32_t sws = s_hw + (uint32_t)(640 + half * 64 + c * 32) * 4u;     // w_ts at float 640, w_tb at 768
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a0, a1, a2, a3, b0, b1, b2, b3;
+              lds_f4(sws + j * 16, a0, a1, a2, a3);
+              lds_f4(sws + 512 + j * 16, b0, b1, b2, b3);
+              pk[2 * j] = apply_mask(pack_bf16(fmaf(dts, a0, dtb * b0), fmaf(dts, a1, dtb * b1)), m, 2 * j);
+              pk[2 * j + 1] = apply_mask(pack_bf16(fmaf(dts, a2, dtb * b2), fmaf(dts, a3, dtb * b3)), m, 2 * j + 1);
+            }
+            const int colg = half * 64 + c * 32;
+            const uint32_t blk = act + (uint32_t)(colg >> 6) * kBlkBytes;
+            const int ch0 = (colg & 63) >> 3;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) sts_u4(blk + blk_off(r, ch0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(1, kEpiThreads);
+      if (e == 0) {
+        mbar_arrive(&act_ready[0]);
+        mbar_arrive(&act_ready[1]);
+        const int ga = p.density_only ? 7 : 12;
+        const int nb = p.density_only ? 4 : 2;
+        for (int slot = 0; slot < 2; ++slot) {
+          const int64_t tile = 2 * pair + slot;
+          if (tile < p.n_tiles)
+            for (int bb = 0; bb < nb; ++bb)
+              bulk_store(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
+        }
+        tma_store_commit();
+      }
+
+      // ---- the chain ----
+      for (int i = 0; i < p.n_prog; ++i) {
+        const int s = p.prog[i];
+        const BStage d = c_bstage[s];
+        const int cpt = d.halves == 2 ? 128 : 64;
+        const int col0 = half * cpt;
+        for (int slot = 0; slot < 2; ++slot) {
+          const int64_t tile = 2 * pair + slot;
+          const int64_t pt = tile * kTileM + r;
+          const bool valid = pt < p.M;
+          const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
+          const uint32_t s_row = smem_u32(smem + kOffRows) + (uint32_t)(slot * 128 + r) * 16u;
+          // ReLU sign bits of this thread's columns (and of the albedo half for stage 2), fetched while the MMA runs
+          uint4 mw = make_uint4(~0u, ~0u, ~0u, ~0u);
+          uint2 mwa = make_uint2(0u, 0u);
+          if (d.mask >= 0) {
+            mw = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) {
+              const uint32_t* mrow = p.mask[d.mask] + pt * 8;
+              if (cpt == 128) mw = __ldg((const uint4*)(mrow + half * 4));
+              else { const uint2 t = __ldg((const uint2*)(mrow + d.mask_w0 + half * 2)); mw.x = t.x; mw.y = t.y; }
+              if (d.kind == 1) mwa = __ldg((const uint2*)(mrow + half * 2));
+            }
+          }
+          float dsig = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+          if (d.kind == 1 || d.kind == 2) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dsig), "=f"(d0), "=f"(d1), "=f"(d2) : "r"(s_row) : "memory");
+          mbar_wait(&acc_full[slot], (cph >> slot) & 1u);
+          cph ^= 1u << slot;
+          tc_fence_after();
+          if (e == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, kEpiThreads);
+          const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + col0;
+          if (d.kind == 4) {
+            // ---- final stage: g_enc = acc[0:64] + G_ENC5, positional-encoding backward (half 0 owns the 64 columns) ----
+            if (half == 0) {
+              float ge[64];
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ge[c * 32 + j] = __uint_as_float(v[j]);
+              }
+              const uint32_t denc = act + 4 * kBlkBytes;
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch) {
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(denc + blk_off(r, ch)) : "memory");
+                ge[ch * 8 + 0] += bf_lo(w0); ge[ch * 8 + 1] += bf_hi(w0); ge[ch * 8 + 2] += bf_lo(w1); ge[ch * 8 + 3] += bf_hi(w1);
+                ge[ch * 8 + 4] += bf_lo(w2); ge[ch * 8 + 5] += bf_hi(w2); ge[ch * 8 + 6] += bf_lo(w3); ge[ch * 8 + 7] += bf_hi(w3);
+              }
+              if (valid) {
+                // g_x[c] = g_enc[c] + sum_k 2^k ( cos(2^k x_c) g_enc[3+3k+c] + cos(2^k x_c + pi/2) g_enc[33+3k+c] )
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  const float x = __ldg(p.xf + 3 * pt + c);
+                  float g = ge[c];
+#pragma unroll
+                  for (int k = 0; k < 10; ++k) {
+                    const float sc = (float)(1 << k), xb = x * sc;
+                    g += sc * (cos_reduced(xb) * ge[3 + 3 * k + c] + cos_reduced(__fadd_rn(xb, kHalfPi)) * ge[33 + 3 * k + c]);
+                  }
+                  p.g_x[3 * pt + c] = g;
+                }
+              }
+            }
+            tc_fence_before();
+            named_bar_sync(1, kEpiThreads);
+            if (e == 0) tma_store_commit();                  // keep one bulk group per (stage, slot)
+            continue;
+          }
+          const bool write_out = !(d.kind == 3 && half == 1);   // encoding part: only 64 real columns
+#pragma unroll 1
+          for (int c = 0; c < cpt / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            const uint32_t m = c == 0 ? mw.x : (c == 1 ? mw.y : (c == 2 ? mw.z : mw.w));
+            float w[32];
+            if (d.kind == 2) {
+              const uint32_t sw = s_hw + (uint32_t)(col0 + c * 32) * 4u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) lds_f4(sw + j * 16, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            }
+            tmem_ld_wait();
+            uint32_t pk[16];
+            if (d.kind == 2) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                pk[j] = apply_mask(pack_bf16(fmaf(dsig, w[2 * j], __uint_as_float(v[2 * j])), fmaf(dsig, w[2 * j + 1], __uint_as_float(v[2 * j + 1]))), m, j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = apply_mask(pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), m, j);
+            }
+            if (write_out) {
+              const int colg = col0 + c * 32;
+              const uint32_t blk = act + (uint32_t)(d.out_blk + (colg >> 6)) * kBlkBytes;
+              const int ch0 = (colg & 63) >> 3;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) sts_u4(blk + blk_off(r, ch0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+            }
+          }
+          if (d.kind == 1) {
+            // albedo half of G_HD0: sum_j drgb_j (x) albedo_mlp.output_layer.weight[j], masked by HD0[:, 0:128] > 0 -> blocks 0,1
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              const uint32_t m = c == 0 ? mwa.x : mwa.y;
+              const uint32_t sw = s_hw + (uint32_t)(256 + half * 64 + c * 32) * 4u;    // w_alb rows at floats 256, 384, 512
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3;
+                lds_f4(sw + j * 16, a0, a1, a2, a3);
+                lds_f4(sw + 512 + j * 16, b0, b1, b2, b3);
+                lds_f4(sw + 1024 + j * 16, c0, c1, c2, c3);
+                pk[2 * j] = apply_mask(pack_bf16(fmaf(d0, a0, fmaf(d1, b0, d2 * c0)), fmaf(d0, a1, fmaf(d1, b1, d2 * c1))), m, 2 * j);
+                pk[2 * j + 1] = apply_mask(pack_bf16(fmaf(d0, a2, fmaf(d1, b2, d2 * c2)), fmaf(d0, a3, fmaf(d1, b3, d2 * c3))), m, 2 * j + 1);
+              }
+              const int colg = half * 64 + c * 32;
+              const uint32_t blk = act + (uint32_t)(colg >> 6) * kBlkBytes;
+              const int ch0 = (colg & 63) >> 3;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) sts_u4(blk + blk_off(r, ch0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          named_bar_sync(1, kEpiThreads);
+          if (e == 0) {
+            if (i + 1 < p.n_prog) mbar_arrive(&act_ready[slot]);
+            if (d.garr >= 0 && tile < p.n_tiles) {
+              const int nb = d.kind == 1 ? 4 : d.halves * 2;
+              const int b0 = d.kind == 1 ? 0 : d.out_blk;
+              for (int bb = 0; bb < nb; ++bb)
+                bulk_store(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (b0 + bb) * kBlkBytes,
+                           kBlkBytes);
+            }
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (e == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- SIMT side kernels over the blocked layout ------------------------------------------------------------------------
+// element (sample m, feature k) of a blocked array with nb blocks per tile
+__device__ __forceinline__ const uint4* blk_chunk(const uint8_t* base, int nb, int64_t m, int chunk) {
+  const int64_t tile = m >> 7;
+  const int rr = (int)(m & 127);
+  return (const uint4*)(base + ((size_t)tile * nb + (chunk >> 3)) * kBlkBytes + rr * 128 + (((chunk & 7) ^ (rr & 7)) << 4));
+}
+__device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
+  f[0] = bf_lo(v.x); f[1] = bf_hi(v.x); f[2] = bf_lo(v.y); f[3] = bf_hi(v.y);
+  f[4] = bf_lo(v.z); f[5] = bf_hi(v.z); f[6] = bf_lo(v.w); f[7] = bf_hi(v.w);
+}
+
+// dw_j[k] += sum_m dpre[m, col0+j] X[m, k];  db_j += sum_m dpre[m, col0+j]     (narrow heads, K = 128 or 256 features
+// starting at 16-byte chunk `chunk0` of the blocked array).  256 threads = (256/lpr) rows x lpr chunks per sweep.
+struct HeadGradsB { float* dw[3]; float* db[3]; };
+template <int J>
+__global__ void __launch_bounds__(256) heads_dw_blocked_kernel(const uint8_t* __restrict__ X, int nb, int chunk0, int K, int64_t M,
+                                                               const float* __restrict__ dpre, int col0, HeadGradsB G,
+                                                               int64_t rows_per_block) {
+  __shared__ float red[8][J][264];
+  const int lpr = K >> 3, rows = 256 / lpr;
+  const int sub = threadIdx.x % lpr, rsub = threadIdx.x / lpr;
+  const int64_t m_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m_end = m_begin + rows_per_block < M ? m_begin + rows_per_block : M;
+  float acc[J][8], bs[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    bs[j] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  }
+  for (int64_t m0 = m_begin + rsub; m0 < m_end; m0 += 4 * rows) {
+    uint4 xv[4];
+    float dv[4][J];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t m = m0 + (int64_t)u * rows;
+      if (m < m_end) {
+        xv[u] = __ldg(blk_chunk(X, nb, m, chunk0 + sub));
+#pragma unroll
+        for (int j = 0; j < J; ++j) dv[u][j] = __ldg(dpre + m * 8 + col0 + j);
+      } else {
+        xv[u] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < J; ++j) dv[u][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float x[8];
+      unpack8(xv[u], x);
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        bs[j] += dv[u][j];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(dv[u][j], x[e], acc[j][e]);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lpr == 16) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      bs[j] += __shfl_xor_sync(kFull, bs[j], 16);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[j][e] += __shfl_xor_sync(kFull, acc[j][e], 16);
+    }
+  }
+  if (lane < lpr) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[warp][j][lane * 8 + e] = acc[j][e];
+      if (lane == 0) red[warp][j][256] = bs[j];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < J * (K + 1); idx += 256) {
+    const int j = idx / (K + 1), k = idx % (K + 1);
+    const int col = k < K ? k : 256;
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) v += red[wv][j][col];
+    if (k < K) atomicAdd(G.dw[j] + k, v); else atomicAdd(G.db[j], v);
+  }
+}
+
+// dcb[img, j] += sum_{rows of image img} G_HD0[row, 128 + j]   (j < 128): gradient of the per-image bias rows
+__global__ void __launch_bounds__(256) class_grad_blocked_kernel(const uint8_t* __restrict__ G, const int32_t* __restrict__ cls, int64_t M,
+                                                                 int64_t n_images, float* __restrict__ dcb, int64_t rows_per_block,
+                                                                 int use_smem) {
+  extern __shared__ float tab[];
+  const int sub = threadIdx.x & 15, rsub = threadIdx.x >> 4;
+  const int64_t m_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m_end = m_begin + rows_per_block < M ? m_begin + rows_per_block : M;
+  if (use_smem) {
+    for (int64_t i = threadIdx.x; i < n_images * kHid; i += 256) tab[i] = 0.f;
+    __syncthreads();
+  }
+  float* dst = use_smem ? tab : dcb;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  int cur = -1;
+  for (int64_t m = m_begin + rsub; m < m_end; m += 16) {
+    const int c = __ldg(cls + m);
+    if (c != cur) {
+      if (cur >= 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { atomicAdd(dst + (int64_t)cur * kHid + sub * 8 + e, acc[e]); acc[e] = 0.f; }
+      }
+      cur = c;
+    }
+    float v[8];
+    unpack8(__ldg(blk_chunk(G, 4, m, 16 + sub)), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += v[e];
+  }
+  if (cur >= 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(dst + (int64_t)cur * kHid + sub * 8 + e, acc[e]);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < n_images * kHid; i += 256)
+      if (tab[i] != 0.f) atomicAdd(dcb + i, tab[i]);
+  }
+}
+
+// d emb[img,e] += sum_j dcb[img,j] W[j,256+e];   dW[j,256+e] += sum_img dcb[img,j] emb[img,e]
+__global__ void emb_grad_fused_kernel(const float* __restrict__ dcb, const float* __restrict__ wt0, const float* __restrict__ emb,
+                                      int64_t n_images, float* __restrict__ g_emb, float* __restrict__ g_wt0) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n_images * 4) {
+    int img = idx / 4, e = idx % 4;
+    float v = 0.f;
+    for (int j = 0; j < kHid; ++j) v = fmaf(__ldg(dcb + img * kHid + j), __ldg(wt0 + j * 260 + 256 + e), v);
+    if (g_emb) g_emb[idx] += v;
+  }
+  if (idx < kHid * 4 && g_wt0) {
+    int j = idx / 4, e = idx % 4;
+    float v = 0.f;
+    for (int64_t img = 0; img < n_images; ++img) v = fmaf(__ldg(dcb + img * kHid + j), __ldg(emb + img * 4 + e), v);
+    g_wt0[j * 260 + 256 + e] += v;
+  }
+}
+
+template <int J>
+static int run_heads_dw_blocked(const uint8_t* X, int nb, int chunk0, int K, int64_t M, const float* dpre, int col0, const HeadGradsB& G,
+                                cudaStream_t s) {
+  int64_t rows = 1024;
+  while (div_up(M, rows) > 4 * 148) rows *= 2;
+  heads_dw_blocked_kernel<J><<<div_up(M, rows), 256, 0, s>>>(X, nb, chunk0, K, M, dpre, col0, G, rows);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+}  // namespace
+
+#define EO_TRY(expr)                \
+  do {                              \
+    int _r = (expr);                \
+    if (_r != EONERF_OK) return _r; \
+  } while (0)
+
+int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
+  EO_REQUIRE(a->field == EONERF_FIELD_EONERF, "fused precision mode supports the EO-NeRF field only");
+  const int64_t N = a->n_pts;
+  const EonerfFieldParams* prm = a->params;
+  const EonerfFieldParams* G = a->grads;
+  const PrepLayout W = prep_layout(EONERF_FIELD_EONERF, EONERF_PREC_BF16, prm->n_images);
+  const FusedPrepLayout F = fused_prep_layout(prm->n_images);
+  const uint8_t* ext = (const uint8_t*)a->prepared + W.total;
+  const FusedStashLayout S = fused_stash_layout(N, a->density_only);
+  const FusedScratchLayout C = fused_scratch_layout(N, prm->n_images, 0);
+  const uint8_t* st = (const uint8_t*)a->stash;
+  uint8_t* sc = (uint8_t*)a->scratch;
+  const bool want_x = a->g_x != nullptr;
+
+  FusedBwdParams p{};
+  p.M = N; p.n_tiles = S.n_tiles; p.density_only = a->density_only;
+  p.wblob = ext + F.bblob; p.consts = (const float*)(ext + F.consts);
+  {
+    int o = 0;
+    for (int i = 0; i < kBwdStages; ++i) { p.blk_off[i] = o; o += kBwdBlkCount[i]; }
+    int n = 0;
+    for (int i = a->density_only ? 5 : 0; i < kBwdStages; ++i) {
+      if ((i == 7 || i == 13) && !want_x) continue;
+      p.prog[n++] = (int8_t)i;
+    }
+    p.n_prog = n;
+  }
+  for (int i = 0; i < kNumMask; ++i) p.mask[i] = S.mask[i] >= 0 ? (const uint32_t*)(st + S.mask[i]) : nullptr;
+  for (int i = 0; i < 13; ++i) p.garr[i] = (a->density_only && i >= 8) ? nullptr : sc + C.g[i];
+  p.xf = (const float*)(st + S.xf);
+  p.sigma = a->sigma; p.rgb = a->rgb; p.ts = a->transient_s; p.tb = a->transient_beta;
+  p.g_sigma = a->g_sigma; p.g_rgb = a->g_rgb; p.g_ts = a->g_transient_s; p.g_tb = a->g_transient_beta;
+  p.dpre = (float*)(sc + C.dpre);
+  p.g_x = a->g_x;
+  static bool configured = false;
+  if (!configured) {
+    EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
+    configured = true;
+  }
+  const int64_t n_pairs = (p.n_tiles + 1) / 2;
+  const double flops = (double)N * (a->density_only ? 982528.0 : 1345280.0);
+  profile_begin(4, flops, 0.0, s);
+  fused_bwd_kernel<<<fused_grid(n_pairs), kFusedThreads, kSmemFused, s>>>(p);
+  profile_end(s);
+  EO_LAUNCH_CHECK();
+  if (!G) return EONERF_OK;
+
+  // ---- parameter gradients: dW = G^T X over the blocked arrays ----
+  auto garr = [&](int i) { return (const uint8_t*)(sc + C.g[i]); };
+  auto sarr = [&](int i) { return st + S.arr[i]; };
+  auto dW = [&](const uint8_t* Gp, int g_nb, int g_blk0, int mt, const uint8_t* Xp, int x_nb, int x_blk0, int x_cnt, int k_valid,
+                float* d0, int64_t ld0, float* b0, float* d1, int64_t ld1, float* b1) {
+    GemmTNBlocked t;
+    t.G = Gp; t.g_nb = g_nb; t.g_blk0 = g_blk0; t.mt_count = mt;
+    t.X = Xp; t.x_nb = x_nb; t.x_blk0 = x_blk0; t.x_cnt = x_cnt; t.k_valid = k_valid;
+    t.n_tiles = S.n_tiles;
+    t.D[0] = d0; t.ldd[0] = ld0; t.db[0] = b0; t.D[1] = d1; t.ldd[1] = ld1; t.db[1] = b1;
+    return gemm_tn_blocked(t, s);
+  };
+  const float* dpre = p.dpre;
+  if (!a->density_only) {
+    // transient_mlp.3 / .2 / .1 : G_T3^T T2, G_T2^T T1, G_T1^T HD0[:,128:256]
+    EO_TRY(dW(garr(12), 2, 0, 1, sarr(11), 2, 0, 2, kHid, G->trans_w[3], kHid, G->trans_b[3], nullptr, 0, nullptr));
+    EO_TRY(dW(garr(11), 2, 0, 1, sarr(10), 2, 0, 2, kHid, G->trans_w[2], kHid, G->trans_b[2], nullptr, 0, nullptr));
+    EO_TRY(dW(garr(10), 2, 0, 1, sarr(9), 4, 2, 2, kHid, G->trans_w[1], kHid, G->trans_b[1], nullptr, 0, nullptr));
+    // [albedo_mlp.0 ; transient_mlp.0[:, :256]] : G_HD0^T BOTT
+    EO_TRY(dW(garr(9), 4, 0, 2, sarr(8), 4, 0, 4, kW, G->head0_w, kW, G->head0_b, G->trans_w[0], 260, G->trans_b[0]));
+    // bottleneck : G_BOTT^T H7
+    EO_TRY(dW(garr(8), 4, 0, 2, sarr(7), 4, 0, 4, kW, G->bott_w, kW, G->bott_b, G->bott_w + (int64_t)kHid * kW, kW, G->bott_b + kHid));
+    {  // narrow heads
+      HeadGradsB hg{{G->ts_w, G->tb_w, nullptr}, {G->ts_b, G->tb_b, nullptr}};
+      EO_TRY(run_heads_dw_blocked<2>(sarr(12), 2, 0, kHid, N, dpre, 4, hg, s));
+      HeadGradsB ha{{G->head1_w, G->head1_w + kHid, G->head1_w + 2 * kHid}, {G->head1_b, G->head1_b + 1, G->head1_b + 2}};
+      EO_TRY(run_heads_dw_blocked<3>(sarr(9), 4, 0, kHid, N, dpre, 1, ha, s));
+    }
+    {  // transient embedding / W_t0[:,256:260] through the per-image bias rows
+      float* dcb = (float*)(sc + C.dcb);
+      EO_CUDA(cudaMemsetAsync(dcb, 0, prm->n_images * kHid * 4, s));
+      const int64_t tab_bytes = prm->n_images * kHid * 4;
+      const int use_smem = tab_bytes <= 40 * 1024;
+      int64_t rows = 2048;
+      while (div_up(N, rows) > 4 * 148) rows *= 2;
+      class_grad_blocked_kernel<<<div_up(N, rows), 256, use_smem ? tab_bytes : 0, s>>>(garr(9), (const int32_t*)(st + S.cls), N, prm->n_images,
+                                                                                       dcb, rows, use_smem);
+      EO_LAUNCH_CHECK();
+      const int nthreads = (int)(prm->n_images * 4 > kHid * 4 ? prm->n_images * 4 : kHid * 4);
+      emb_grad_fused_kernel<<<div_up(nthreads, 128), 128, 0, s>>>(dcb, prm->trans_w[0], prm->transient_emb, prm->n_images, G->transient_emb,
+                                                                   G->trans_w[0]);
+      EO_LAUNCH_CHECK();
+    }
+  }
+  {  // sigma head
+    HeadGradsB hs{{G->sigma_w, nullptr, nullptr}, {G->sigma_b, nullptr, nullptr}};
+    EO_TRY(run_heads_dw_blocked<1>(sarr(7), 4, 0, kW, N, dpre, 0, hs, s));
+  }
+  // trunk: layer i reads X = H_{i-1} (layer 5: [H4 | enc], layer 0: enc)
+  for (int i = 7; i >= 1; --i) {
+    float* w = G->trunk_w[i];
+    const int64_t ld = trunk_k(i);
+    EO_TRY(dW(garr(i), 4, 0, 2, sarr(i - 1), 4, 0, 4, kW, w, ld, G->trunk_b[i], w + (int64_t)kHid * ld, ld, G->trunk_b[i] + kHid));
+    if (i == 5)
+      EO_TRY(dW(garr(5), 4, 0, 2, sarr(kArrEnc), 1, 0, 1, 63, w + kW, ld, nullptr, w + (int64_t)kHid * ld + kW, ld, nullptr));
+  }
+  EO_TRY(dW(garr(0), 4, 0, 2, sarr(kArrEnc), 1, 0, 1, 63, G->trunk_w[0], 63, G->trunk_b[0], G->trunk_w[0] + (int64_t)kHid * 63, 63,
+            G->trunk_b[0] + kHid));
+  return EONERF_OK;
+}
+
+}  // namespace eonerf

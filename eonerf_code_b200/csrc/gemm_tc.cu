@@ -14,7 +14,7 @@
 //   K-major  SW128: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), 16-byte chunks XOR-swizzled by row%8
 //   MN-major SW128: the same physical image read the other way round: 64 contiguous MN elements x 8 K-rows per
 //                   atom, K groups SBO = 1024 B apart, 64-wide MN blocks LBO = (one TMA box) apart.
-#include "gemm.cuh"
+#include "field_fused.cuh"
 #include "tc_ptx.cuh"
 
 namespace eonerf {
@@ -480,6 +480,183 @@ int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
   if ((r = make_map(&tmX, g.X, g.M, g.K, g.ldx, kBlockK)) != EONERF_OK) return r;
   profile_begin(1, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.N * p.k_tiles + (double)g.M * g.K) + 4.0 * g.N * g.K, s);
   gemm_tn_tc_kernel<kTNStages><<<(unsigned)(splits * p.k_tiles), kThreads, kSmemTN, s>>>(tmA, tmX, p);
+  profile_end(s);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// TN over tile-blocked operands (field_fused.cuh): D[n,k] += sum_m G[m,n] X[m,k], db[n] += sum_m G[m,n].
+// A 64-sample half of a 16 KB block [128 samples x 64 features] is 8 KB contiguous and already the MN-major SW128
+// image the MMA wants, so operands arrive with plain cp.async.bulk copies (no tensor maps).  The four epilogue warps
+// are idle during the main loop: they sum the columns of the G tiles in shared memory (the bias gradient) while the
+// tensor core consumes the same tiles.
+// ------------------------------------------------------------------------------------------------
+struct TNBParams {
+  const uint8_t* G; int g_nb, g_blk0, mt_count;
+  const uint8_t* X; int x_nb, x_blk0, x_cnt;
+  int64_t chunks, chunks_per_cta;
+  int n_valid[2]; int k_valid;
+  float* D[2]; int64_t ldd[2]; float* db[2];
+};
+
+constexpr int kTNBStages = 3;
+constexpr int kSmemTNB = kTNBStages * 8 * kBoxBytes + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __grid_constant__ TNBParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int a_boxes = p.mt_count * 2;
+  const int stage_bytes = (a_boxes + p.x_cnt) * kBoxBytes;
+  __shared__ uint64_t full_bar[kTNBStages], empty_bar[kTNBStages], acc_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTNBStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 5); }   // MMA commit + 4 epilogue warps
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int64_t c_begin = (int64_t)blockIdx.x * p.chunks_per_cta;
+  const int64_t c_end = (c_begin + p.chunks_per_cta < p.chunks) ? c_begin + p.chunks_per_cta : p.chunks;
+  const int64_t my_chunks = c_end > c_begin ? c_end - c_begin : 0;
+  const int block_k = p.x_cnt * 64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t c = c_begin; c < c_end; ++c) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* s0 = smem + (size_t)stage * stage_bytes;
+        mbar_expect_tx(&full_bar[stage], stage_bytes);
+        const int64_t tile = c >> 1;
+        const size_t hoff = (size_t)(c & 1) * kBoxBytes;
+        for (int b = 0; b < a_boxes; ++b)
+          bulk_load(s0 + b * kBoxBytes, p.G + ((size_t)tile * p.g_nb + p.g_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
+        for (int b = 0; b < p.x_cnt; ++b)
+          bulk_load(s0 + (a_boxes + b) * kBoxBytes, p.X + ((size_t)tile * p.x_nb + p.x_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
+        if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(kBlockM, block_k, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t c = 0; c < my_chunks; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t s0 = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sx = s0 + a_boxes * kBoxBytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t dx = smem_desc(sx + k * 2048, kBoxBytes, 1024);
+          for (int mt = 0; mt < p.mt_count; ++mt) {
+            const uint64_t da = smem_desc(s0 + mt * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
+            umma_bf16(tmem_base + mt * 256, da, dx, idesc, (c | k) != 0);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&acc_full);
+    }
+  } else {
+    // ===== epilogue warps: bias-gradient side job during the main loop, then TMEM -> red.global =====
+    const int t = threadIdx.x - 64;                       // 0..127: box t/32, 32-bit word `lane` of each 128-byte row
+    const int box = t >> 5;
+    const bool do_sum = box < a_boxes && p.db[box >> 1] != nullptr;
+    float s_lo = 0.f, s_hi = 0.f;
+    {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t c = 0; c < my_chunks; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        if (do_sum) {
+          const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes + box * kBoxBytes) + (lane & 3) * 4;
+#pragma unroll 8
+          for (int rr = 0; rr < 64; ++rr) {
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4)) : "memory");
+            s_lo += __uint_as_float(w << 16);
+            s_hi += __uint_as_float(w & 0xFFFF0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    if (do_sum && my_chunks > 0) {
+      const int mt = box >> 1;
+      const int n = (box & 1) * 64 + 2 * lane;
+      if (n < p.n_valid[mt]) atomicAdd(p.db[mt] + n, s_lo);
+      if (n + 1 < p.n_valid[mt]) atomicAdd(p.db[mt] + n + 1, s_hi);
+    }
+    if (my_chunks > 0) {
+      const int quarter = warp & 3;
+      mbar_wait(&acc_full, 0);
+      tc_fence_after();
+      for (int mt = 0; mt < p.mt_count; ++mt) {
+        const int n = quarter * 32 + lane;                 // output row (feature of G) inside this 128-row block
+        const uint32_t taddr = tmem_base + mt * 256 + ((uint32_t)(quarter * 32) << 16);
+        const bool vec = (p.ldd[mt] & 3) == 0 && ((uintptr_t)p.D[mt] & 15) == 0;
+        for (int c = 0; c < block_k; c += 32) {
+          __syncwarp();
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tmem_ld_wait();
+          if (n >= p.n_valid[mt] || p.D[mt] == nullptr) continue;
+          float* drow = p.D[mt] + (int64_t)n * p.ldd[mt] + c;
+          if (vec && c + 32 <= p.k_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + j), "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
+                           "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c + j < p.k_valid) atomicAdd(drow + j, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int gemm_tn_blocked(const GemmTNBlocked& g, cudaStream_t s) {
+  if (g.n_tiles <= 0) return EONERF_OK;
+  EO_REQUIRE(g.mt_count >= 1 && g.mt_count <= 2 && g.x_cnt >= 1 && g.x_cnt <= 4, "gemm_tn_blocked: unsupported shape");
+  static bool configured = false;
+  if (!configured) {
+    EO_CUDA(cudaFuncSetAttribute(gemm_tn_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTNB));
+    configured = true;
+  }
+  TNBParams p{};
+  p.G = g.G; p.g_nb = g.g_nb; p.g_blk0 = g.g_blk0; p.mt_count = g.mt_count;
+  p.X = g.X; p.x_nb = g.x_nb; p.x_blk0 = g.x_blk0; p.x_cnt = g.x_cnt;
+  p.chunks = g.n_tiles * 2;
+  int64_t splits = sm_count();
+  if (splits > p.chunks) splits = p.chunks;
+  p.chunks_per_cta = (p.chunks + splits - 1) / splits;
+  splits = (p.chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
+  for (int i = 0; i < 2; ++i) { p.n_valid[i] = g.n_valid[i]; p.D[i] = g.D[i]; p.ldd[i] = g.ldd[i]; p.db[i] = g.db[i]; }
+  p.k_valid = g.k_valid;
+  const double M = (double)g.n_tiles * kTileM;
+  profile_begin(1, 2.0 * M * g.mt_count * 128 * g.k_valid, 2.0 * M * (g.mt_count * 128 + g.x_cnt * 64), s);
+  gemm_tn_blocked_kernel<<<(unsigned)splits, kThreads, kSmemTNB, s>>>(p);
   profile_end(s);
   EO_LAUNCH_CHECK();
   return EONERF_OK;

@@ -134,3 +134,41 @@ def test_fused_forward_golden(cuda, golden, precision):
         dens = m.query_density(x)
     check_outputs(outs, [t(g[k]) for k in NAMES], "bf16")
     check_outputs([dens], [t(g["density"])], "bf16")
+
+
+def l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+@pytest.mark.parametrize("n", [100, 1000, 4099])
+@pytest.mark.parametrize("density_only", [False, True])
+def test_fused_backward_matches_layered(cuda, n, density_only):
+    """Parameter gradients and dL/dx of the fused chain vs the layer-by-layer bf16 kernels on the same inputs and the same
+    upstream gradients (both round G to bf16 at every layer; they differ by summation order and rounding flips)."""
+    n_img = 6
+    p = O.init_params(n_img, seed=5, bias_scale=0.1)
+    g = torch.Generator().manual_seed(100 + n)
+    x = (torch.rand(n, 3, generator=g) * 2 - 1).to(cuda)
+    img = torch.sort(torch.randint(0, n_img, (n,), generator=g))[0][:, None].to(cuda)
+    gs, g3 = torch.randn(n, generator=g).to(cuda), torch.randn(n, 3, generator=g).to(cuda)
+    gts, gtb = torch.randn(n, generator=g).to(cuda), torch.randn(n, generator=g).to(cuda)
+    res = {}
+    for mode in ("bf16", "bf16_fused"):
+        m = make_model(p, n_img, cuda, mode)
+        e = m._engine()
+        f = e.fwd(n, density_only, x=x, img_idx=None if density_only else img)
+        flat, views, gstruct = e.new_grads()
+        gx = e.bwd(n, density_only, f, g_sigma=gs, g_rgb=None if density_only else g3, g_ts=None if density_only else gts,
+                   g_tb=None if density_only else gtb, grads_struct=gstruct, want_gx=density_only)
+        torch.cuda.synchronize()
+        res[mode] = (views, gx)
+    va, vb = res["bf16"][0], res["bf16_fused"][0]
+    for k in va:
+        if float(va[k].abs().max()) == 0.0:
+            assert float(vb[k].abs().max()) == 0.0, k
+            continue
+        assert torch.isfinite(vb[k]).all(), k
+        assert l2(vb[k], va[k]) <= 2e-2, (k, l2(vb[k], va[k]))
+    if density_only:
+        assert l2(res["bf16_fused"][1], res["bf16"][1]) <= 2e-2

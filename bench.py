@@ -137,7 +137,7 @@ def run_product(args, rank, world, local):
     torch.cuda.set_device(dev)
     K.require_device()
     torch.manual_seed(42)
-    model = EONerfMLP(N_IMAGES, radiometric_normalization=True, precision="bf16").to(dev)
+    model = EONerfMLP(N_IMAGES, radiometric_normalization=True, precision=args.precision).to(dev)
     step_fn = TrainStep(model, n_samples=N_SAMPLES, world=world)
     lib = K.lib()
 
@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precision", default="bf16_fused", choices=["bf16_fused", "bf16"], help="bf16_fused: fused tcgen05 MLP kernels (product); bf16: layer-by-layer")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup
     from eonerf_code_b200.parallel import init_from_env

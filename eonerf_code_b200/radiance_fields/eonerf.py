@@ -2,8 +2,9 @@
 (/root/reference/radiance_fields/eonerf.py:69-248; state_dict contract in SURVEY.md Appendix B).
 
 The module owns fp32 master parameters under the reference's names; every forward/backward runs in the
-sm_100a kernels behind the C ABI.  `precision` selects bf16 tensor cores ("bf16", production) or the fp32
-exactness mode ("fp32") used for the 1e-5 parity tests."""
+sm_100a kernels behind the C ABI.  `precision` selects the fused bf16 tensor-core kernels ("bf16_fused", production),
+the layer-by-layer bf16 tensor-core kernels ("bf16", cross-check) or the fp32 exactness mode ("fp32") used for the 1e-5
+parity tests."""
 import torch
 import torch.nn as nn
 
@@ -16,7 +17,7 @@ class EONerfMLP(nn.Module, _EngineMixin):
     _field_kind = K.FIELD_EONERF
 
     def __init__(self, n_input_images, net_depth=8, net_width=256, skip_layer=4, radiometric_normalization=False,
-                 precision="bf16"):
+                 precision="bf16_fused"):
         super().__init__()
         if (net_depth, net_width, skip_layer) != (8, 256, 4):
             raise ValueError("the sm_100a kernels are built for the 8x256 skip-4 network: the reference never builds "

@@ -31,7 +31,7 @@ def grad_err(a, b, precision):
     return rel_err(a, b) if precision == "fp32" else l2_err(a, b)
 
 
-GRAD_TOL = {"fp32": 2e-4, "bf16": 3e-2, "bf16_simt": 3e-2}
+GRAD_TOL = {"fp32": 2e-4, "bf16": 3e-2, "bf16_simt": 3e-2, "bf16_fused": 3e-2}
 
 
 def check_outputs(outs, refs, precision):
@@ -59,7 +59,7 @@ def test_forward_golden(cuda, golden, precision):
     check_outputs([dens], [t(g["density"])], precision)
 
 
-@pytest.mark.parametrize("precision,N", [("fp32", 777), ("bf16_simt", 777), ("bf16", 777), ("bf16", 5000)])
+@pytest.mark.parametrize("precision,N", [("fp32", 777), ("bf16_simt", 777), ("bf16", 777), ("bf16", 5000), ("bf16_fused", 777), ("bf16_fused", 5000)])
 def test_backward_vs_oracle_autograd(cuda, precision, N):
     n_img = 7
     p = O.init_params(n_img, seed=5, bias_scale=0.1)
@@ -94,7 +94,7 @@ def test_backward_vs_oracle_autograd(cuda, precision, N):
     assert grad_err(xc.grad, xo.grad, precision) <= tol, grad_err(xc.grad, xo.grad, precision)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16_fused"])
 def test_density_backward_golden(cuda, golden, precision):
     """d sigma / d x through the positional encoding — what the shadow pass needs (sat_rendering.py:90)."""
     g = golden["field"]

@@ -147,7 +147,7 @@ def test_operator_level_api_fp32(cuda, golden):
     assert float(gd.abs().max()) > 0
 
 
-@pytest.mark.parametrize("precision", ["bf16_simt", "bf16"])
+@pytest.mark.parametrize("precision", ["bf16_simt", "bf16", "bf16_fused"])
 def test_render_image_bf16(cuda, golden, precision):
     """bf16 MLP: sample indices still bit-exact (same n_rendering_samples, pts_per_ray); composited outputs within the
     tolerance the bf16 MLP allows (1e-3 abs on MLP outputs -> 5e-3 abs on composited colours / depth)."""
@@ -164,7 +164,7 @@ def test_render_image_bf16(cuda, golden, precision):
     assert all(torch.isfinite(v.grad).all() for v in m.parameters() if v.grad is not None)
 
 
-@pytest.mark.parametrize("precision", ["bf16"])
+@pytest.mark.parametrize("precision", ["bf16", "bf16_fused"])
 def test_sum_of_weights_and_determinism_at_full_size(cuda, precision):
     """Size-independent properties at BASELINE config 3 size (8192 rays x 128 samples): two runs with the same uniforms
     are bit-identical (no atomics in compositing), pts_per_ray sums to n_rendering_samples, outputs finite and in range."""

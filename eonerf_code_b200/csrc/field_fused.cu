@@ -14,6 +14,8 @@
 //
 // Rounding points are those of the layer-by-layer bf16 path (field.cu): bf16 activations and weights, fp32 accumulate,
 // fp32 biases and narrow heads.
+#include <stdlib.h>
+
 #include "fused_common.cuh"
 
 namespace eonerf {
@@ -49,88 +51,39 @@ struct FusedFwdParams {
   const int64_t* ray_indices; const float* t_starts; const float* t_ends; float* z_mid;
   const int64_t* img_idx; int64_t img_stride;
   const uint8_t* wblob; const float* consts; const float* class_delta;   // class_delta: [n_img,128] fp32
-  int blk_off[kFwdStages];
+  MmaProgram prog;
   uint8_t* arr[kNumArr];
   uint32_t* mask[kNumMask];
   float* xf; int32_t* cls;
   float* sigma; float* rgb; float* ts; float* tb;
 };
 
-template <bool kTrain>
+template <bool kTrain, int kCG>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __grid_constant__ FusedFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* w_full = (uint64_t*)(smem + kOffBar);
-  uint64_t* w_empty = w_full + kRingStages;
-  uint64_t* acc_full = w_empty + kRingStages;
-  uint64_t* act_ready = acc_full + 2;
-  uint32_t* tmem_base_s = (uint32_t*)(act_ready + 2);
   float* cst = (float*)(smem + kOffConst);
   float* part = (float*)(smem + kOffPart);
-
+  const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0;
+  FusedBars B;
+  uint32_t* tmem_base_s;
+  fused_setup<kCG>(smem, B, tmem_base_s, rank);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kRingStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&act_ready[s], 1); }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_base_s, 512);
   for (int i = threadIdx.x; i < kCFloats; i += kFusedThreads) cst[i] = __ldg(p.consts + i);
   tc_fence_before();
-  __syncthreads();
+  if (kCG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
-  const int64_t n_pairs = (p.n_tiles + 1) / 2;
+  // work items: 2*kCG consecutive tiles; this CTA owns tiles (2*kCG*it + 2*rank + slot)
+  const int64_t n_items = (p.n_tiles + 2 * kCG - 1) / (2 * kCG);
+  const int64_t it0 = blockIdx.x / kCG, it_stride = gridDim.x / kCG;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== weight producer =====
-      int rs = 0; uint32_t rph = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-        for (int s = 0; s < p.n_stages; ++s) {
-          const int nblk = c_fstage[s].halves * c_fstage[s].nkb;
-          const uint8_t* src = p.wblob + (size_t)p.blk_off[s] * kBlkBytes;
-          for (int rep = 0; rep < 2; ++rep)
-            for (int b = 0; b < nblk; ++b) {
-              mbar_wait(&w_empty[rs], rph ^ 1);
-              mbar_expect_tx(&w_full[rs], kBlkBytes);
-              bulk_load(smem + kOffRing + rs * kBlkBytes, src + (size_t)b * kBlkBytes, kBlkBytes, &w_full[rs]);
-              if (++rs == kRingStages) { rs = 0; rph ^= 1; }
-            }
-        }
-    }
+    if (lane == 0) fused_producer<kCG>(p.prog, p.wblob, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = instr_desc(128, 128, 0, 0);
-      int rs = 0; uint32_t rph = 0;
-      uint32_t aph = 0;                                  // bit `slot` = phase of act_ready[slot]
-      const uint32_t ring0 = smem_u32(smem + kOffRing);
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-        for (int s = 0; s < p.n_stages; ++s) {
-          const FStage d = c_fstage[s];
-          for (int slot = 0; slot < 2; ++slot) {
-            mbar_wait(&act_ready[slot], (aph >> slot) & 1u);
-            aph ^= 1u << slot;
-            tc_fence_after();
-            const uint32_t slot0 = smem_u32(smem + kOffSlot + slot * kSlotBytes);
-            for (int h = 0; h < d.halves; ++h) {
-              const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
-              for (int kb = 0; kb < d.nkb; ++kb) {
-                mbar_wait(&w_full[rs], rph);
-                tc_fence_after();
-                const uint32_t sa = slot0 + d.a[kb] * kBlkBytes;
-                const uint32_t sb = ring0 + rs * kBlkBytes;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0);
-                umma_commit(&w_empty[rs]);
-                if (++rs == kRingStages) { rs = 0; rph ^= 1; }
-              }
-            }
-            umma_commit(&acc_full[slot]);
-          }
-        }
+      if (rank == 0) fused_mma_issuer<kCG>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);
+      else fused_forwarder(p.prog, B, it0, n_items, it_stride);
     }
   } else {
     // ===== epilogue warps =====
@@ -141,13 +94,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
     const uint32_t s_cst = smem_u32(cst);
     const uint32_t s_part = smem_u32(part);
     uint32_t cph = 0;                               // bit `slot` = phase of acc_full[slot]
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    uint64_t* const acc_full = B.acc_full;
+    for (int64_t it = it0; it < n_items; it += it_stride) {
       uint32_t cls_pack = 0;                        // image index of this row in slot 0 (low 16 bits) / slot 1
       // ---- positional encoding of both tiles ----
       if (e == 0) tma_store_wait_read<0>();
       named_bar_sync(1, kEpiThreads);
       for (int slot = 0; slot < 2; ++slot) {
-        const int64_t tile = 2 * pair + slot;
+        const int64_t tile = 2 * kCG * it + 2 * rank + slot;
         const int64_t pt = tile * kTileM + r;
         const bool valid = pt < p.M;
         float x[3] = {0.f, 0.f, 0.f};
@@ -190,11 +144,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
       fence_proxy_async();
       named_bar_sync(1, kEpiThreads);
       if (e == 0) {
-        mbar_arrive(&act_ready[0]);
-        mbar_arrive(&act_ready[1]);
+        signal_act_ready<kCG>(B, 0, rank);
+        signal_act_ready<kCG>(B, 1, rank);
         if (kTrain) {
           for (int slot = 0; slot < 2; ++slot) {
-            const int64_t tile = 2 * pair + slot;
+            const int64_t tile = 2 * kCG * it + 2 * rank + slot;
             if (tile < p.n_tiles)
               bulk_store(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
           }
@@ -209,7 +163,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         const int col0 = half * cpt;
         const float relu_lo = d.relu ? 0.f : -INFINITY;
         for (int slot = 0; slot < 2; ++slot) {
-          const int64_t tile = 2 * pair + slot;
+          const int64_t tile = 2 * kCG * it + 2 * rank + slot;
           const int64_t pt = tile * kTileM + r;
           const bool valid = pt < p.M;
           const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
@@ -296,7 +250,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           fence_proxy_async();
           named_bar_sync(1, kEpiThreads);
           if (e == 0) {
-            if (s + 1 < p.n_stages) mbar_arrive(&act_ready[slot]);
+            if (s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
             if (kTrain && tile < p.n_tiles) {
               const int nb = d.halves * 2;
               for (int bb = 0; bb < nb; ++bb)
@@ -324,13 +278,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
     }
     if (e == 0) tma_store_wait_all();
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
+  fused_teardown<kCG>(tmem_base);
 }
 
 // ---- prepare: weight blocks + constants ----------------------------------------------------------------------------
@@ -389,10 +337,34 @@ int64_t fused_scratch_bytes(int64_t n_pts, int64_t n_images, int density_only) {
   return fused_scratch_layout(n_pts, n_images, density_only).total;
 }
 
-static void fwd_block_offsets(int* off) {
-  static const int nb[kFwdStages] = {2, 8, 8, 8, 8, 10, 8, 8, 8, 8, 2, 2, 2};
-  int o = 0;
-  for (int s = 0; s < kFwdStages; ++s) { off[s] = o; o += nb[s]; }
+// MMA side of the forward program (host copy of the A-block lists of c_fstage)
+static MmaProgram fwd_program(int n_stages) {
+  static const int8_t halves[kFwdStages] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1};
+  static const int8_t nkb[kFwdStages] = {1, 4, 4, 4, 4, 5, 4, 4, 4, 4, 2, 2, 2};
+  static const int8_t a[kFwdStages][5] = {{4, 0, 0, 0, 0}, {0, 1, 2, 3, 0}, {0, 1, 2, 3, 0}, {0, 1, 2, 3, 0}, {0, 1, 2, 3, 0}, {0, 1, 2, 3, 4},
+                                          {0, 1, 2, 3, 0}, {0, 1, 2, 3, 0}, {0, 1, 2, 3, 0}, {0, 1, 2, 3, 0}, {2, 3, 0, 0, 0}, {0, 1, 0, 0, 0},
+                                          {2, 3, 0, 0, 0}};
+  MmaProgram P{};
+  P.n = n_stages;
+  int off = 0;
+  for (int s = 0; s < kFwdStages; ++s) {
+    if (s < n_stages) {
+      P.st[s].halves = halves[s]; P.st[s].nkb = nkb[s]; P.st[s].blk_off = off;
+      for (int k = 0; k < 5; ++k) P.st[s].a[k] = a[s][k];
+    }
+    off += halves[s] * nkb[s];
+  }
+  return P;
+}
+
+// 1: every CTA on its own (cta_group::1);  2: CTA pairs (cta_group::2).  EONERF_FUSED_CG overrides (debug / A-B timing).
+int fused_cta_group() {
+  static int cg = 0;
+  if (!cg) {
+    const char* e = getenv("EONERF_FUSED_CG");
+    cg = (e && e[0] == '1') ? 1 : 2;
+  }
+  return cg;
 }
 
 int fused_prepare(const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
@@ -474,7 +446,7 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   p.img_idx = a->density_only ? nullptr : a->img_idx; p.img_stride = a->img_idx_stride;
   p.wblob = ext + F.fblob; p.consts = (const float*)(ext + F.consts);
   p.class_delta = (const float*)(ext + F.delta);
-  fwd_block_offsets(p.blk_off);
+  p.prog = fwd_program(p.n_stages);
   if (train) {
     const FusedStashLayout S = fused_stash_layout(N, a->density_only);
     uint8_t* st = (uint8_t*)a->stash;
@@ -486,17 +458,21 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   p.sigma = a->sigma; p.rgb = a->rgb; p.ts = a->transient_s; p.tb = a->transient_beta;
   static bool configured = false;
   if (!configured) {
-    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
-    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
+    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
+    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
+    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
+    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
     configured = true;
   }
-  const int64_t n_pairs = (p.n_tiles + 1) / 2;
-  const int grid = fused_grid(n_pairs);
+  const int cg = fused_cta_group();
+  const int n_ctas = fused_ctas(p.n_tiles, cg);
   const double flops = (double)N * (a->density_only ? 982528.0 : 1345280.0);
   profile_begin(3, flops, 0.0, s);
-  if (train) fused_fwd_kernel<true><<<grid, kFusedThreads, kSmemFused, s>>>(p);
-  else fused_fwd_kernel<false><<<grid, kFusedThreads, kSmemFused, s>>>(p);
+  int rc;
+  if (cg == 2) rc = train ? launch_fused(fused_fwd_kernel<true, 2>, 2, n_ctas, p, s) : launch_fused(fused_fwd_kernel<false, 2>, 2, n_ctas, p, s);
+  else rc = train ? launch_fused(fused_fwd_kernel<true, 1>, 1, n_ctas, p, s) : launch_fused(fused_fwd_kernel<false, 1>, 1, n_ctas, p, s);
   profile_end(s);
+  if (rc != EONERF_OK) return rc;
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }

@@ -114,5 +114,6 @@ struct GemmTNBlocked {
   float* db[2] = {nullptr, nullptr};
 };
 int gemm_tn_blocked(const GemmTNBlocked& g, cudaStream_t s);
+int fused_cta_group();
 
 }  // namespace eonerf

@@ -88,4 +88,165 @@ static inline int fused_grid(int64_t n_pairs) {
   return (int)(n_pairs < sms ? n_pairs : sms);
 }
 
+// ---- the tensor-core side of both fused kernels -------------------------------------------------------------------
+// A "program" is a list of GEMM stages; per stage the A operand is a list of 16 KB activation blocks of the slot
+// (0..3 = ACT, 4 = ENC) and the B operand a run of weight blocks in the prepared blob ([output half][k block]).
+struct StageMma { int8_t halves, nkb, a[5], pad; int32_t blk_off; };
+struct MmaProgram { int32_t n; StageMma st[14]; };
+
+struct FusedBars { uint64_t* w_full; uint64_t* w_empty; uint64_t* acc_full; uint64_t* act_ready; };
+
+// kCG = 1: every CTA is on its own.  kCG = 2: CTA pair; work item `it` covers 4 tiles (2 per CTA), the leader (rank 0)
+// issues cta_group::2 MMAs over both CTAs' tiles, each CTA streams only its half of every weight block.
+template <int kCG>
+__device__ __forceinline__ void fused_setup(uint8_t* smem, FusedBars& B, uint32_t*& tmem_base_s, uint32_t rank) {
+  B.w_full = (uint64_t*)(smem + kOffBar);
+  B.w_empty = B.w_full + kRingStages;
+  B.acc_full = B.w_empty + kRingStages;
+  B.act_ready = B.acc_full + 2;
+  tmem_base_s = (uint32_t*)(B.act_ready + 2);
+  if (threadIdx.x == 0) {
+    const uint32_t n_arr = (kCG == 2 && rank == 0) ? 2 : 1;   // leader of a pair: + the peer's forwarded / remote arrival
+    for (int s = 0; s < kRingStages; ++s) { mbar_init(&B.w_full[s], n_arr); mbar_init(&B.w_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&B.acc_full[s], 1); mbar_init(&B.act_ready[s], n_arr); }
+    fence_barrier_init();
+  }
+  if ((threadIdx.x >> 5) == 1) {
+    if (kCG == 2) tmem_alloc_2cta(tmem_base_s, 512); else tmem_alloc(tmem_base_s, 512);
+  }
+}
+
+template <int kCG>
+__device__ __forceinline__ void fused_teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  if (kCG == 2) cluster_sync_all(); else __syncthreads();
+  if ((threadIdx.x >> 5) == 1) {
+    __syncwarp();
+    tc_fence_after();
+    if (kCG == 2) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// one thread: stream this CTA's weight blocks through the ring
+template <int kCG>
+__device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uint8_t* wblob, uint8_t* smem, const FusedBars& B, int64_t it0,
+                                               int64_t n_items, int64_t it_stride, uint32_t rank) {
+  int rs = 0; uint32_t rph = 0;
+  for (int64_t it = it0; it < n_items; it += it_stride)
+    for (int s = 0; s < prog.n; ++s) {
+      const StageMma d = prog.st[s];
+      const uint8_t* src = wblob + (size_t)d.blk_off * kBlkBytes;
+      const int nblk = kCG == 1 ? d.halves * d.nkb : d.nkb;
+      const uint32_t bytes = (kCG == 2 && d.halves == 1) ? kBlkBytes / 2 : kBlkBytes;
+      const size_t base = kCG == 1 ? 0 : (d.halves == 2 ? (size_t)rank * d.nkb * kBlkBytes : (size_t)rank * (kBlkBytes / 2));
+      for (int rep = 0; rep < 2; ++rep)
+        for (int b = 0; b < nblk; ++b) {
+          mbar_wait(&B.w_empty[rs], rph ^ 1);
+          mbar_expect_tx(&B.w_full[rs], bytes);
+          bulk_load(smem + kOffRing + rs * kBlkBytes, src + base + (size_t)b * kBlkBytes, bytes, &B.w_full[rs]);
+          if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+        }
+    }
+}
+
+// kCG = 2, peer CTA, one thread: tell the leader when this CTA's half of a ring stage has landed
+__device__ __forceinline__ void fused_forwarder(const MmaProgram& prog, const FusedBars& B, int64_t it0, int64_t n_items, int64_t it_stride) {
+  int rs = 0; uint32_t rph = 0;
+  for (int64_t it = it0; it < n_items; it += it_stride)
+    for (int s = 0; s < prog.n; ++s) {
+      const int nblk = prog.st[s].nkb;
+      for (int rep = 0; rep < 2; ++rep)
+        for (int b = 0; b < nblk; ++b) {
+          mbar_wait(&B.w_full[rs], rph);
+          mbar_arrive_remote(&B.w_full[rs], 0);
+          if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+        }
+    }
+}
+
+// one thread (kCG = 2: of the leader CTA): issue the MMAs of every stage for both slots
+template <int kCG>
+__device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t* smem, const FusedBars& B, uint32_t tmem_base, int64_t it0,
+                                                 int64_t n_items, int64_t it_stride) {
+  int rs = 0; uint32_t rph = 0;
+  uint32_t aph = 0;                                  // bit `slot` = phase of act_ready[slot]
+  const uint32_t ring0 = smem_u32(smem + kOffRing);
+  for (int64_t it = it0; it < n_items; it += it_stride)
+    for (int s = 0; s < prog.n; ++s) {
+      const StageMma d = prog.st[s];
+      for (int slot = 0; slot < 2; ++slot) {
+        mbar_wait(&B.act_ready[slot], (aph >> slot) & 1u);
+        aph ^= 1u << slot;
+        tc_fence_after();
+        const uint32_t slot0 = smem_u32(smem + kOffSlot + slot * kSlotBytes);
+        if (kCG == 1) {
+          const uint32_t idesc = instr_desc(128, 128, 0, 0);
+          for (int h = 0; h < d.halves; ++h) {
+            const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
+            for (int kb = 0; kb < d.nkb; ++kb) {
+              mbar_wait(&B.w_full[rs], rph);
+              tc_fence_after();
+              const uint32_t sa = slot0 + d.a[kb] * kBlkBytes;
+              const uint32_t sb = ring0 + rs * kBlkBytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0);
+              umma_commit(&B.w_empty[rs]);
+              if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+            }
+          }
+          umma_commit(&B.acc_full[slot]);
+        } else {
+          const uint32_t idesc = instr_desc(256, d.halves * 128, 0, 0);
+          const uint32_t d_tmem = tmem_base + slot * 256;
+          for (int kb = 0; kb < d.nkb; ++kb) {
+            mbar_wait(&B.w_full[rs], rph);
+            tc_fence_after();
+            const uint32_t sa = slot0 + d.a[kb] * kBlkBytes;
+            const uint32_t sb = ring0 + rs * kBlkBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_2cta(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0);
+            umma_commit_2cta(&B.w_empty[rs]);
+            if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+          }
+          umma_commit_2cta(&B.acc_full[slot]);
+        }
+      }
+    }
+}
+
+// epilogue side: "this slot's A operand for the next stage is in shared memory and its accumulator is drained"
+template <int kCG>
+__device__ __forceinline__ void signal_act_ready(const FusedBars& B, int slot, uint32_t rank) {
+  if (kCG == 2 && rank != 0) mbar_arrive_remote(&B.act_ready[slot], 0);
+  else mbar_arrive(&B.act_ready[slot]);
+}
+
+template <class Kernel, class Params>
+static int launch_fused(Kernel kernel, int cg, int n_ctas, const Params& p, cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)n_ctas);
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = kSmemFused;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EO_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  return EONERF_OK;
+}
+
+// number of CTAs for n_tiles tiles: kCG CTAs per work item of 2*kCG tiles, at most one CTA per SM
+static inline int fused_ctas(int64_t n_tiles, int cg) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t items = (n_tiles + 2 * cg - 1) / (2 * cg);
+  const int64_t max_items = sms / cg;
+  return (int)((items < max_items ? items : max_items) * cg);
+}
+
 }  // namespace eonerf

@@ -52,7 +52,7 @@ struct FusedBwdParams {
   int n_prog; int8_t prog[kBwdStages];
   int density_only;
   const uint8_t* wblob; const float* consts;
-  int blk_off[kBwdStages];
+  MmaProgram mma;      // MMA side of prog[]
   const uint32_t* mask[kNumMask];
   uint8_t* garr[13];
   const float* xf;
@@ -74,80 +74,30 @@ __device__ __forceinline__ uint32_t apply_mask(uint32_t pk, uint32_t m, int j) {
   return pk & (sel * 0xFFFFu);
 }
 
+template <int kCG>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __grid_constant__ FusedBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* w_full = (uint64_t*)(smem + kOffBar);
-  uint64_t* w_empty = w_full + kRingStages;
-  uint64_t* acc_full = w_empty + kRingStages;
-  uint64_t* act_ready = acc_full + 2;
-  uint32_t* tmem_base_s = (uint32_t*)(act_ready + 2);
   float* hw = (float*)(smem + kOffConst);                   // head weights: w_sigma 256 | w_alb 384 | w_ts 128 | w_tb 128
-
+  const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0;
+  FusedBars B;
+  uint32_t* tmem_base_s;
+  fused_setup<kCG>(smem, B, tmem_base_s, rank);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kRingStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&act_ready[s], 1); }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_base_s, 512);
   for (int i = threadIdx.x; i < 896; i += kFusedThreads) hw[i] = __ldg(p.consts + kCWSigma + i);
   tc_fence_before();
-  __syncthreads();
+  if (kCG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
-  const int64_t n_pairs = (p.n_tiles + 1) / 2;
+  const int64_t n_items = (p.n_tiles + 2 * kCG - 1) / (2 * kCG);
+  const int64_t it0 = blockIdx.x / kCG, it_stride = gridDim.x / kCG;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== weight producer =====
-      int rs = 0; uint32_t rph = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-        for (int i = 0; i < p.n_prog; ++i) {
-          const int s = p.prog[i];
-          const int nblk = c_bstage[s].halves * c_bstage[s].nkb;
-          const uint8_t* src = p.wblob + (size_t)p.blk_off[s] * kBlkBytes;
-          for (int rep = 0; rep < 2; ++rep)
-            for (int b = 0; b < nblk; ++b) {
-              mbar_wait(&w_empty[rs], rph ^ 1);
-              mbar_expect_tx(&w_full[rs], kBlkBytes);
-              bulk_load(smem + kOffRing + rs * kBlkBytes, src + (size_t)b * kBlkBytes, kBlkBytes, &w_full[rs]);
-              if (++rs == kRingStages) { rs = 0; rph ^= 1; }
-            }
-        }
-    }
+    if (lane == 0) fused_producer<kCG>(p.mma, p.wblob, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = instr_desc(128, 128, 0, 0);
-      int rs = 0; uint32_t rph = 0;
-      uint32_t aph = 0;
-      const uint32_t ring0 = smem_u32(smem + kOffRing);
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-        for (int i = 0; i < p.n_prog; ++i) {
-          const BStage d = c_bstage[p.prog[i]];
-          for (int slot = 0; slot < 2; ++slot) {
-            mbar_wait(&act_ready[slot], (aph >> slot) & 1u);
-            aph ^= 1u << slot;
-            tc_fence_after();
-            const uint32_t slot0 = smem_u32(smem + kOffSlot + slot * kSlotBytes);
-            for (int h = 0; h < d.halves; ++h) {
-              const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
-              for (int kb = 0; kb < d.nkb; ++kb) {
-                mbar_wait(&w_full[rs], rph);
-                tc_fence_after();
-                const uint32_t sa = slot0 + d.a[kb] * kBlkBytes;
-                const uint32_t sb = ring0 + rs * kBlkBytes;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0);
-                umma_commit(&w_empty[rs]);
-                if (++rs == kRingStages) { rs = 0; rph ^= 1; }
-              }
-            }
-            umma_commit(&acc_full[slot]);
-          }
-        }
+      if (rank == 0) fused_mma_issuer<kCG>(p.mma, smem, B, tmem_base, it0, n_items, it_stride);
+      else fused_forwarder(p.mma, B, it0, n_items, it_stride);
     }
   } else {
     // ===== epilogue warps =====
@@ -157,12 +107,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
     const int r = q * 32 + lane;
     const uint32_t s_hw = smem_u32(hw);
     uint32_t cph = 0;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    uint64_t* const acc_full = B.acc_full;
+    for (int64_t it = it0; it < n_items; it += it_stride) {
       // ---- head gradients -> first G of the chain ----
       if (e == 0) tma_store_wait_read<0>();
       named_bar_sync(1, kEpiThreads);
       for (int slot = 0; slot < 2; ++slot) {
-        const int64_t tile = 2 * pair + slot;
+        const int64_t tile = 2 * kCG * it + 2 * rank + slot;
         const int64_t pt = tile * kTileM + r;
         const bool valid = pt < p.M;
         const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
@@ -240,12 +191,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
       fence_proxy_async();
       named_bar_sync(1, kEpiThreads);
       if (e == 0) {
-        mbar_arrive(&act_ready[0]);
-        mbar_arrive(&act_ready[1]);
+        signal_act_ready<kCG>(B, 0, rank);
+        signal_act_ready<kCG>(B, 1, rank);
         const int ga = p.density_only ? 7 : 12;
         const int nb = p.density_only ? 4 : 2;
         for (int slot = 0; slot < 2; ++slot) {
-          const int64_t tile = 2 * pair + slot;
+          const int64_t tile = 2 * kCG * it + 2 * rank + slot;
           if (tile < p.n_tiles)
             for (int bb = 0; bb < nb; ++bb)
               bulk_store(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
@@ -260,7 +211,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
         const int cpt = d.halves == 2 ? 128 : 64;
         const int col0 = half * cpt;
         for (int slot = 0; slot < 2; ++slot) {
-          const int64_t tile = 2 * pair + slot;
+          const int64_t tile = 2 * kCG * it + 2 * rank + slot;
           const int64_t pt = tile * kTileM + r;
           const bool valid = pt < p.M;
           const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
@@ -382,7 +333,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           fence_proxy_async();
           named_bar_sync(1, kEpiThreads);
           if (e == 0) {
-            if (i + 1 < p.n_prog) mbar_arrive(&act_ready[slot]);
+            if (i + 1 < p.n_prog) signal_act_ready<kCG>(B, slot, rank);
             if (d.garr >= 0 && tile < p.n_tiles) {
               const int nb = d.kind == 1 ? 4 : d.halves * 2;
               const int b0 = d.kind == 1 ? 0 : d.out_blk;
@@ -397,13 +348,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
     }
     if (e == 0) tma_store_wait_all();
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
+  fused_teardown<kCG>(tmem_base);
 }
 
 // ---- SIMT side kernels over the blocked layout ------------------------------------------------------------------------
@@ -589,14 +534,22 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   p.M = N; p.n_tiles = S.n_tiles; p.density_only = a->density_only;
   p.wblob = ext + F.bblob; p.consts = (const float*)(ext + F.consts);
   {
+    static const int8_t halves[kBwdStages] = {1, 1, 1, 2, 2, 2, 2, 1, 2, 2, 2, 2, 2, 1};
+    static const int8_t nkb[kBwdStages] = {2, 2, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
+    static const int8_t ablk[kBwdStages][4] = {{0, 1, 0, 0}, {2, 3, 0, 0}, {0, 1, 0, 0}, {0, 1, 2, 3}, {0, 1, 2, 3}, {0, 1, 2, 3}, {0, 1, 2, 3},
+                                               {0, 1, 2, 3}, {0, 1, 2, 3}, {0, 1, 2, 3}, {0, 1, 2, 3}, {0, 1, 2, 3}, {0, 1, 2, 3}, {0, 1, 2, 3}};
+    int blk_off[kBwdStages];
     int o = 0;
-    for (int i = 0; i < kBwdStages; ++i) { p.blk_off[i] = o; o += kBwdBlkCount[i]; }
+    for (int i = 0; i < kBwdStages; ++i) { blk_off[i] = o; o += kBwdBlkCount[i]; }
     int n = 0;
     for (int i = a->density_only ? 5 : 0; i < kBwdStages; ++i) {
       if ((i == 7 || i == 13) && !want_x) continue;
+      p.mma.st[n].halves = halves[i]; p.mma.st[n].nkb = nkb[i]; p.mma.st[n].blk_off = blk_off[i];
+      for (int k = 0; k < 4; ++k) p.mma.st[n].a[k] = ablk[i][k];
       p.prog[n++] = (int8_t)i;
     }
     p.n_prog = n;
+    p.mma.n = n;
   }
   for (int i = 0; i < kNumMask; ++i) p.mask[i] = S.mask[i] >= 0 ? (const uint32_t*)(st + S.mask[i]) : nullptr;
   for (int i = 0; i < 13; ++i) p.garr[i] = (a->density_only && i >= 8) ? nullptr : sc + C.g[i];
@@ -607,14 +560,17 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   p.g_x = a->g_x;
   static bool configured = false;
   if (!configured) {
-    EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
+    EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
+    EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
     configured = true;
   }
-  const int64_t n_pairs = (p.n_tiles + 1) / 2;
+  const int cg = fused_cta_group();
+  const int n_ctas = fused_ctas(p.n_tiles, cg);
   const double flops = (double)N * (a->density_only ? 982528.0 : 1345280.0);
   profile_begin(4, flops, 0.0, s);
-  fused_bwd_kernel<<<fused_grid(n_pairs), kFusedThreads, kSmemFused, s>>>(p);
+  const int rc = cg == 2 ? launch_fused(fused_bwd_kernel<2>, 2, n_ctas, p, s) : launch_fused(fused_bwd_kernel<1>, 1, n_ctas, p, s);
   profile_end(s);
+  if (rc != EONERF_OK) return rc;
   EO_LAUNCH_CHECK();
   if (!G) return EONERF_OK;
 

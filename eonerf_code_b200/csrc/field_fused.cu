@@ -81,10 +81,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
   if (warp == 0) {
     if (lane == 0) fused_producer<kCG>(p.prog, p.wblob, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
-    if (lane == 0) {
-      if (rank == 0) fused_mma_issuer<kCG>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);
-      else fused_forwarder(p.prog, B, it0, n_items, it_stride);
-    }
+    if (rank == 0) fused_mma_issuer<kCG>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);      // whole warp, converged
+    else if (lane == 0) fused_forwarder(p.prog, B, it0, n_items, it_stride);
   } else {
     // ===== epilogue warps =====
     const int e = threadIdx.x - 64;
@@ -169,11 +167,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
           // per-image part of the HD0 bias (transient half only): W[:,256:260] . emb[img]
           const float* delta = (d.kind == 2 && half == 1) ? p.class_delta + (size_t)((cls_pack >> (16 * slot)) & 0xFFFFu) * kHid : nullptr;
-          mbar_wait(&acc_full[slot], (cph >> slot) & 1u);
+          { EO_T0(); mbar_wait(&acc_full[slot], (cph >> slot) & 1u); if (e == 0) EO_T1(3); }
           cph ^= 1u << slot;
           tc_fence_after();
-          if (e == 0) tma_store_wait_read<1>();             // this slot's previous stash store has drained (the other slot's may be in flight)
-          named_bar_sync(1, kEpiThreads);
+          {
+            EO_T0();
+            if (e == 0) tma_store_wait_read<1>();           // this slot's previous stash store has drained (the other slot's may be in flight)
+            named_bar_sync(1, kEpiThreads);
+            if (e == 0) EO_T1(4);
+          }
           const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + col0;
           float h0 = 0.f, h1 = 0.f, h2 = 0.f;               // head partial sums
           uint32_t* mrow = (kTrain && d.mask >= 0 && valid) ? p.mask[d.mask] + pt * 8 + col0 / 32 : nullptr;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           if (half == 1 && (d.kind == 1 || d.kind == 3)) sts_f2(s_part + r * 8, h0, h1);
           tc_fence_before();
           fence_proxy_async();
-          named_bar_sync(1, kEpiThreads);
+          { EO_T0(); named_bar_sync(1, kEpiThreads); if (e == 32) EO_T1(5); }
           if (e == 0) {
             if (s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
             if (kTrain && tile < p.n_tiles) {
@@ -478,3 +480,12 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
 }
 
 }  // namespace eonerf
+
+#ifdef EONERF_TIMING
+extern "C" int eonerf_debug_timing(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, eonerf::g_fused_timing, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(eonerf::g_fused_timing, z, sizeof(z)); }
+  return 0;
+}
+#endif

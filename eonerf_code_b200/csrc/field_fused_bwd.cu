@@ -95,10 +95,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
   if (warp == 0) {
     if (lane == 0) fused_producer<kCG>(p.mma, p.wblob, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
-    if (lane == 0) {
-      if (rank == 0) fused_mma_issuer<kCG>(p.mma, smem, B, tmem_base, it0, n_items, it_stride);
-      else fused_forwarder(p.mma, B, it0, n_items, it_stride);
-    }
+    if (rank == 0) fused_mma_issuer<kCG>(p.mma, smem, B, tmem_base, it0, n_items, it_stride);       // whole warp, converged
+    else if (lane == 0) fused_forwarder(p.mma, B, it0, n_items, it_stride);
   } else {
     // ===== epilogue warps =====
     const int e = threadIdx.x - 64;
@@ -636,3 +634,12 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
 }
 
 }  // namespace eonerf
+
+#ifdef EONERF_TIMING
+extern "C" int eonerf_debug_timing_bwd(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, eonerf::g_fused_timing, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(eonerf::g_fused_timing, z, sizeof(z)); }
+  return 0;
+}
+#endif

@@ -88,6 +88,18 @@ static inline int fused_grid(int64_t n_pairs) {
   return (int)(n_pairs < sms ? n_pairs : sms);
 }
 
+// Optional wait-time instrumentation (build with -DEONERF_TIMING): cycles CTA 0's role threads spend blocked on each
+// barrier class.  g_fused_timing: 0 mma<-act_ready, 1 mma<-weights, 2 producer<-ring slot, 3 epilogue<-accumulator,
+// 4 epilogue start barrier (incl. stash-store drain), 5 epilogue end barrier, 6 total cycles of the MMA thread
+#ifdef EONERF_TIMING
+static __device__ unsigned long long g_fused_timing[8];   // one copy per translation unit
+#define EO_T0() const long long _t0 = clock64()
+#define EO_T1(slot) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_fused_timing[slot] += (unsigned long long)(clock64() - _t0); } while (0)
+#else
+#define EO_T0() do {} while (0)
+#define EO_T1(slot) do {} while (0)
+#endif
+
 // ---- the tensor-core side of both fused kernels -------------------------------------------------------------------
 // A "program" is a list of GEMM stages; per stage the A operand is a list of 16 KB activation blocks of the slot
 // (0..3 = ACT, 4 = ENC) and the B operand a run of weight blocks in the prepared blob ([output half][k block]).
@@ -141,7 +153,7 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
       const size_t base = kCG == 1 ? 0 : (d.halves == 2 ? (size_t)rank * d.nkb * kBlkBytes : (size_t)rank * (kBlkBytes / 2));
       for (int rep = 0; rep < 2; ++rep)
         for (int b = 0; b < nblk; ++b) {
-          mbar_wait(&B.w_empty[rs], rph ^ 1);
+          { EO_T0(); mbar_wait(&B.w_empty[rs], rph ^ 1); EO_T1(2); }
           mbar_expect_tx(&B.w_full[rs], bytes);
           bulk_load(smem + kOffRing + rs * kBlkBytes, src + base + (size_t)b * kBlkBytes, bytes, &B.w_full[rs]);
           if (++rs == kRingStages) { rs = 0; rph ^= 1; }
@@ -164,56 +176,54 @@ __device__ __forceinline__ void fused_forwarder(const MmaProgram& prog, const Fu
     }
 }
 
-// one thread (kCG = 2: of the leader CTA): issue the MMAs of every stage for both slots
+// the whole MMA warp (kCG = 2: of the leader CTA), converged: issue the MMAs of every stage for both slots
 template <int kCG>
 __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t* smem, const FusedBars& B, uint32_t tmem_base, int64_t it0,
                                                  int64_t n_items, int64_t it_stride) {
   int rs = 0; uint32_t rph = 0;
   uint32_t aph = 0;                                  // bit `slot` = phase of act_ready[slot]
   const uint32_t ring0 = smem_u32(smem + kOffRing);
+  const bool elected = elect_one_sync();
+#ifdef EONERF_TIMING
+  const long long t_begin = clock64();
+#endif
   for (int64_t it = it0; it < n_items; it += it_stride)
     for (int s = 0; s < prog.n; ++s) {
       const StageMma d = prog.st[s];
+      const int n_h = kCG == 1 ? d.halves : 1;                          // kCG = 2: one MMA covers both output halves
+      const uint32_t idesc = kCG == 1 ? instr_desc(128, 128, 0, 0) : instr_desc(256, d.halves * 128, 0, 0);
       for (int slot = 0; slot < 2; ++slot) {
-        mbar_wait(&B.act_ready[slot], (aph >> slot) & 1u);
+        { EO_T0(); mbar_wait(&B.act_ready[slot], (aph >> slot) & 1u); EO_T1(0); }
         aph ^= 1u << slot;
         tc_fence_after();
         const uint32_t slot0 = smem_u32(smem + kOffSlot + slot * kSlotBytes);
-        if (kCG == 1) {
-          const uint32_t idesc = instr_desc(128, 128, 0, 0);
-          for (int h = 0; h < d.halves; ++h) {
-            const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
-            for (int kb = 0; kb < d.nkb; ++kb) {
-              mbar_wait(&B.w_full[rs], rph);
-              tc_fence_after();
-              const uint32_t sa = slot0 + d.a[kb] * kBlkBytes;
-              const uint32_t sb = ring0 + rs * kBlkBytes;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0);
-              umma_commit(&B.w_empty[rs]);
-              if (++rs == kRingStages) { rs = 0; rph ^= 1; }
-            }
-          }
-          umma_commit(&B.acc_full[slot]);
-        } else {
-          const uint32_t idesc = instr_desc(256, d.halves * 128, 0, 0);
-          const uint32_t d_tmem = tmem_base + slot * 256;
+        for (int h = 0; h < n_h; ++h) {
+          const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
           for (int kb = 0; kb < d.nkb; ++kb) {
-            mbar_wait(&B.w_full[rs], rph);
+            { EO_T0(); mbar_wait(&B.w_full[rs], rph); EO_T1(1); }
             tc_fence_after();
-            const uint32_t sa = slot0 + d.a[kb] * kBlkBytes;
-            const uint32_t sb = ring0 + rs * kBlkBytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_2cta(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0);
-            umma_commit_2cta(&B.w_empty[rs]);
+            const uint32_t la = desc_lo_k128(slot0 + d.a[kb] * kBlkBytes);
+            const uint32_t lb = desc_lo_k128(ring0 + rs * kBlkBytes);
+            if (elected) {
+              umma_k128<kCG>(d_tmem, la, lb, idesc, kb != 0);           // 16 K elements = 32 bytes = +2 in the address field
+              umma_k128<kCG>(d_tmem, la + 2, lb + 2, idesc, 1);
+              umma_k128<kCG>(d_tmem, la + 4, lb + 4, idesc, 1);
+              umma_k128<kCG>(d_tmem, la + 6, lb + 6, idesc, 1);
+              if (kCG == 2) umma_commit_2cta(&B.w_empty[rs]); else umma_commit(&B.w_empty[rs]);
+            }
+            __syncwarp();
             if (++rs == kRingStages) { rs = 0; rph ^= 1; }
           }
-          umma_commit_2cta(&B.acc_full[slot]);
         }
+        if (elected) {
+          if (kCG == 2) umma_commit_2cta(&B.acc_full[slot]); else umma_commit(&B.acc_full[slot]);
+        }
+        __syncwarp();
       }
     }
+#ifdef EONERF_TIMING
+  if (blockIdx.x == 0 && elected) g_fused_timing[6] += (unsigned long long)(clock64() - t_begin);
+#endif
 }
 
 // epilogue side: "this slot's A operand for the next stage is in shared memory and its accumulator is drained"

@@ -184,4 +184,37 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a,
       : "memory");
 }
 
+// ---- warp-uniform MMA issue -------------------------------------------------------------------------------------------
+// tcgen05.mma takes its operands from UNIFORM registers.  Issued under `if (lane == 0)` the compiler cannot prove the
+// operands warp-uniform and wraps every MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~25 dependent
+// instructions per MMA: the issuing thread becomes slower than the tensor core).  The issuer therefore runs with the
+// whole warp converged on uniform values and only predicates the MMA / commit with elect.sync.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// K-major SW128 descriptor split in halves: hi is constant (SBO = 1024 B, version 1, SWIZZLE_128B), lo carries the address
+constexpr uint32_t kDescHiK128 = (1024u >> 4) | (1u << 14) | (kSwizzle128 << 29);
+__device__ __forceinline__ uint32_t desc_lo_k128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+template <int kCG>
+__device__ __forceinline__ void umma_k128(uint32_t tmem_d, uint32_t lo_a, uint32_t lo_b, uint32_t idesc, uint32_t accumulate) {
+  if (kCG == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(lo_a), "r"(lo_b), "r"(kDescHiK128), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(lo_a), "r"(lo_b), "r"(kDescHiK128), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 }  // namespace eonerf

@@ -58,30 +58,31 @@ struct FusedFwdParams {
   float* sigma; float* rgb; float* ts; float* tb;
 };
 
-template <bool kTrain, int kCG>
+template <bool kTrain, int kCG, int kMC>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __grid_constant__ FusedFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* cst = (float*)(smem + kOffConst);
   float* part = (float*)(smem + kOffPart);
-  const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0;
+  constexpr int kCl = kCG * kMC;                              // CTAs per cluster
+  const uint32_t rank = kCl > 1 ? cluster_ctarank() : 0;
   FusedBars B;
   uint32_t* tmem_base_s;
-  fused_setup<kCG>(smem, B, tmem_base_s, rank);
+  fused_setup<kCG, kMC>(smem, B, tmem_base_s, rank);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < kCFloats; i += kFusedThreads) cst[i] = __ldg(p.consts + i);
   tc_fence_before();
-  if (kCG == 2) cluster_sync_all(); else __syncthreads();
+  if (kCl > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
-  // work items: 2*kCG consecutive tiles; this CTA owns tiles (2*kCG*it + 2*rank + slot)
-  const int64_t n_items = (p.n_tiles + 2 * kCG - 1) / (2 * kCG);
-  const int64_t it0 = blockIdx.x / kCG, it_stride = gridDim.x / kCG;
+  // work items: 2 tiles per CTA of the cluster; this CTA owns tiles (2*kCl*it + 2*rank + slot)
+  const int64_t n_items = (p.n_tiles + 2 * kCl - 1) / (2 * kCl);
+  const int64_t it0 = blockIdx.x / kCl, it_stride = gridDim.x / kCl;
 
   if (warp == 0) {
-    if (lane == 0) fused_producer<kCG>(p.prog, p.wblob, smem, B, it0, n_items, it_stride, rank);
+    if (lane == 0) fused_producer<kCG, kMC>(p.prog, p.wblob, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
-    if (rank == 0) fused_mma_issuer<kCG>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);      // whole warp, converged
+    if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);      // whole warp, converged
     else if (lane == 0) fused_forwarder(p.prog, B, it0, n_items, it_stride);
   } else {
     // ===== epilogue warps =====
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
       if (e == 0) tma_store_wait_read<0>();
       named_bar_sync(1, kEpiThreads);
       for (int slot = 0; slot < 2; ++slot) {
-        const int64_t tile = 2 * kCG * it + 2 * rank + slot;
+        const int64_t tile = 2 * kCl * it + 2 * rank + slot;
         const int64_t pt = tile * kTileM + r;
         const bool valid = pt < p.M;
         float x[3] = {0.f, 0.f, 0.f};
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         signal_act_ready<kCG>(B, 1, rank);
         if (kTrain) {
           for (int slot = 0; slot < 2; ++slot) {
-            const int64_t tile = 2 * kCG * it + 2 * rank + slot;
+            const int64_t tile = 2 * kCl * it + 2 * rank + slot;
             if (tile < p.n_tiles)
               bulk_store(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
           }
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         const int col0 = half * cpt;
         const float relu_lo = d.relu ? 0.f : -INFINITY;
         for (int slot = 0; slot < 2; ++slot) {
-          const int64_t tile = 2 * kCG * it + 2 * rank + slot;
+          const int64_t tile = 2 * kCl * it + 2 * rank + slot;
           const int64_t pt = tile * kTileM + r;
           const bool valid = pt < p.M;
           const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
     }
     if (e == 0) tma_store_wait_all();
   }
-  fused_teardown<kCG>(tmem_base);
+  fused_teardown<kCG, kMC>(tmem_base);
 }
 
 // ---- prepare: weight blocks + constants ----------------------------------------------------------------------------
@@ -359,14 +360,19 @@ static MmaProgram fwd_program(int n_stages) {
   return P;
 }
 
-// 1: every CTA on its own (cta_group::1);  2: CTA pairs (cta_group::2).  EONERF_FUSED_CG overrides (debug / A-B timing).
+// How the CTAs of the fused kernels cooperate (EONERF_FUSED_MODE overrides, for A/B timing):
+//    1  every CTA on its own
+//    2  CTA pairs issuing cta_group::2 MMAs (each CTA streams half of every weight block)
+//   12  clusters of 2 sharing the weight stream by TMA multicast (independent cta_group::1 MMAs)   <- default
+//   14  clusters of 4 sharing the weight stream
 int fused_cta_group() {
-  static int cg = 0;
-  if (!cg) {
-    const char* e = getenv("EONERF_FUSED_CG");
-    cg = (e && e[0] == '1') ? 1 : 2;
+  static int mode = 0;
+  if (!mode) {
+    const char* e = getenv("EONERF_FUSED_MODE");
+    mode = e ? atoi(e) : 12;
+    if (mode != 1 && mode != 2 && mode != 12 && mode != 14) mode = 12;
   }
-  return cg;
+  return mode;
 }
 
 int fused_prepare(const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
@@ -458,21 +464,27 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
     p.cls = a->density_only ? nullptr : (int32_t*)(st + S.cls);
   }
   p.sigma = a->sigma; p.rgb = a->rgb; p.ts = a->transient_s; p.tb = a->transient_beta;
-  static bool configured = false;
-  if (!configured) {
-    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
-    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
-    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
-    EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
-    configured = true;
-  }
-  const int cg = fused_cta_group();
-  const int n_ctas = fused_ctas(p.n_tiles, cg);
+  const int mode = fused_cta_group();
+  const int csz = mode == 1 ? 1 : (mode == 14 ? 4 : 2);
+  const int n_ctas = fused_ctas(p.n_tiles, csz);
   const double flops = (double)N * (a->density_only ? 982528.0 : 1345280.0);
-  profile_begin(3, flops, 0.0, s);
-  int rc;
-  if (cg == 2) rc = train ? launch_fused(fused_fwd_kernel<true, 2>, 2, n_ctas, p, s) : launch_fused(fused_fwd_kernel<false, 2>, 2, n_ctas, p, s);
-  else rc = train ? launch_fused(fused_fwd_kernel<true, 1>, 1, n_ctas, p, s) : launch_fused(fused_fwd_kernel<false, 1>, 1, n_ctas, p, s);
+  int rc = EONERF_OK;
+#define EO_LAUNCH_FWD(CG, MC)                                                                                                   \
+  do {                                                                                                                          \
+    static bool configured = false;                                                                                             \
+    if (!configured) {                                                                                                          \
+      EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true, CG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));  \
+      EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false, CG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused)); \
+      configured = true;                                                                                                        \
+    }                                                                                                                           \
+    profile_begin(3, flops, 0.0, s);                                                                                            \
+    rc = train ? launch_fused(fused_fwd_kernel<true, CG, MC>, csz, n_ctas, p, s) : launch_fused(fused_fwd_kernel<false, CG, MC>, csz, n_ctas, p, s); \
+  } while (0)
+  if (mode == 1) EO_LAUNCH_FWD(1, 1);
+  else if (mode == 2) EO_LAUNCH_FWD(2, 1);
+  else if (mode == 14) EO_LAUNCH_FWD(1, 4);
+  else EO_LAUNCH_FWD(1, 2);
+#undef EO_LAUNCH_FWD
   profile_end(s);
   if (rc != EONERF_OK) return rc;
   EO_LAUNCH_CHECK();

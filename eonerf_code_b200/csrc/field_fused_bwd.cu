@@ -74,28 +74,29 @@ __device__ __forceinline__ uint32_t apply_mask(uint32_t pk, uint32_t m, int j) {
   return pk & (sel * 0xFFFFu);
 }
 
-template <int kCG>
+template <int kCG, int kMC>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __grid_constant__ FusedBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* hw = (float*)(smem + kOffConst);                   // head weights: w_sigma 256 | w_alb 384 | w_ts 128 | w_tb 128
-  const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0;
+  constexpr int kCl = kCG * kMC;                              // CTAs per cluster
+  const uint32_t rank = kCl > 1 ? cluster_ctarank() : 0;
   FusedBars B;
   uint32_t* tmem_base_s;
-  fused_setup<kCG>(smem, B, tmem_base_s, rank);
+  fused_setup<kCG, kMC>(smem, B, tmem_base_s, rank);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 896; i += kFusedThreads) hw[i] = __ldg(p.consts + kCWSigma + i);
   tc_fence_before();
-  if (kCG == 2) cluster_sync_all(); else __syncthreads();
+  if (kCl > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
-  const int64_t n_items = (p.n_tiles + 2 * kCG - 1) / (2 * kCG);
-  const int64_t it0 = blockIdx.x / kCG, it_stride = gridDim.x / kCG;
+  const int64_t n_items = (p.n_tiles + 2 * kCl - 1) / (2 * kCl);
+  const int64_t it0 = blockIdx.x / kCl, it_stride = gridDim.x / kCl;
 
   if (warp == 0) {
-    if (lane == 0) fused_producer<kCG>(p.mma, p.wblob, smem, B, it0, n_items, it_stride, rank);
+    if (lane == 0) fused_producer<kCG, kMC>(p.mma, p.wblob, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
-    if (rank == 0) fused_mma_issuer<kCG>(p.mma, smem, B, tmem_base, it0, n_items, it_stride);       // whole warp, converged
+    if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC>(p.mma, smem, B, tmem_base, it0, n_items, it_stride);       // whole warp, converged
     else if (lane == 0) fused_forwarder(p.mma, B, it0, n_items, it_stride);
   } else {
     // ===== epilogue warps =====
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
       if (e == 0) tma_store_wait_read<0>();
       named_bar_sync(1, kEpiThreads);
       for (int slot = 0; slot < 2; ++slot) {
-        const int64_t tile = 2 * kCG * it + 2 * rank + slot;
+        const int64_t tile = 2 * kCl * it + 2 * rank + slot;
         const int64_t pt = tile * kTileM + r;
         const bool valid = pt < p.M;
         const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
         const int ga = p.density_only ? 7 : 12;
         const int nb = p.density_only ? 4 : 2;
         for (int slot = 0; slot < 2; ++slot) {
-          const int64_t tile = 2 * kCG * it + 2 * rank + slot;
+          const int64_t tile = 2 * kCl * it + 2 * rank + slot;
           if (tile < p.n_tiles)
             for (int bb = 0; bb < nb; ++bb)
               bulk_store(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
         const int cpt = d.halves == 2 ? 128 : 64;
         const int col0 = half * cpt;
         for (int slot = 0; slot < 2; ++slot) {
-          const int64_t tile = 2 * kCG * it + 2 * rank + slot;
+          const int64_t tile = 2 * kCl * it + 2 * rank + slot;
           const int64_t pt = tile * kTileM + r;
           const bool valid = pt < p.M;
           const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
     }
     if (e == 0) tma_store_wait_all();
   }
-  fused_teardown<kCG>(tmem_base);
+  fused_teardown<kCG, kMC>(tmem_base);
 }
 
 // ---- SIMT side kernels over the blocked layout ------------------------------------------------------------------------
@@ -556,17 +557,26 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   p.g_sigma = a->g_sigma; p.g_rgb = a->g_rgb; p.g_ts = a->g_transient_s; p.g_tb = a->g_transient_beta;
   p.dpre = (float*)(sc + C.dpre);
   p.g_x = a->g_x;
-  static bool configured = false;
-  if (!configured) {
-    EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
-    EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));
-    configured = true;
-  }
-  const int cg = fused_cta_group();
-  const int n_ctas = fused_ctas(p.n_tiles, cg);
+  const int mode = fused_cta_group();
+  const int csz = mode == 1 ? 1 : (mode == 14 ? 4 : 2);
+  const int n_ctas = fused_ctas(p.n_tiles, csz);
   const double flops = (double)N * (a->density_only ? 982528.0 : 1345280.0);
-  profile_begin(4, flops, 0.0, s);
-  const int rc = cg == 2 ? launch_fused(fused_bwd_kernel<2>, 2, n_ctas, p, s) : launch_fused(fused_bwd_kernel<1>, 1, n_ctas, p, s);
+  int rc = EONERF_OK;
+#define EO_LAUNCH_BWD(CG, MC)                                                                                             \
+  do {                                                                                                                    \
+    static bool configured = false;                                                                                       \
+    if (!configured) {                                                                                                    \
+      EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<CG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));  \
+      configured = true;                                                                                                  \
+    }                                                                                                                     \
+    profile_begin(4, flops, 0.0, s);                                                                                      \
+    rc = launch_fused(fused_bwd_kernel<CG, MC>, csz, n_ctas, p, s);                                                       \
+  } while (0)
+  if (mode == 1) EO_LAUNCH_BWD(1, 1);
+  else if (mode == 2) EO_LAUNCH_BWD(2, 1);
+  else if (mode == 14) EO_LAUNCH_BWD(1, 4);
+  else EO_LAUNCH_BWD(1, 2);
+#undef EO_LAUNCH_BWD
   profile_end(s);
   if (rc != EONERF_OK) return rc;
   EO_LAUNCH_CHECK();

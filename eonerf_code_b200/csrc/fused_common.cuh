@@ -110,7 +110,11 @@ struct FusedBars { uint64_t* w_full; uint64_t* w_empty; uint64_t* acc_full; uint
 
 // kCG = 1: every CTA is on its own.  kCG = 2: CTA pair; work item `it` covers 4 tiles (2 per CTA), the leader (rank 0)
 // issues cta_group::2 MMAs over both CTAs' tiles, each CTA streams only its half of every weight block.
-template <int kCG>
+// kMC > 1 (with kCG = 1): weight multicast.  The CTAs of a cluster of kMC run independently (own tiles, own MMAs) but share
+// the weight stream: each CTA loads 1/kMC of every weight block and multicasts it, so L2 is read once per cluster.  A ring
+// slot is refilled only when ALL CTAs of the cluster have consumed it (every CTA's tcgen05.commit arrives on every
+// CTA's w_empty), which keeps the rings in lockstep.
+template <int kCG, int kMC = 1>
 __device__ __forceinline__ void fused_setup(uint8_t* smem, FusedBars& B, uint32_t*& tmem_base_s, uint32_t rank) {
   B.w_full = (uint64_t*)(smem + kOffBar);
   B.w_empty = B.w_full + kRingStages;
@@ -119,7 +123,7 @@ __device__ __forceinline__ void fused_setup(uint8_t* smem, FusedBars& B, uint32_
   tmem_base_s = (uint32_t*)(B.act_ready + 2);
   if (threadIdx.x == 0) {
     const uint32_t n_arr = (kCG == 2 && rank == 0) ? 2 : 1;   // leader of a pair: + the peer's forwarded / remote arrival
-    for (int s = 0; s < kRingStages; ++s) { mbar_init(&B.w_full[s], n_arr); mbar_init(&B.w_empty[s], 1); }
+    for (int s = 0; s < kRingStages; ++s) { mbar_init(&B.w_full[s], n_arr); mbar_init(&B.w_empty[s], kMC); }
     for (int s = 0; s < 2; ++s) { mbar_init(&B.acc_full[s], 1); mbar_init(&B.act_ready[s], n_arr); }
     fence_barrier_init();
   }
@@ -128,10 +132,10 @@ __device__ __forceinline__ void fused_setup(uint8_t* smem, FusedBars& B, uint32_
   }
 }
 
-template <int kCG>
+template <int kCG, int kMC = 1>
 __device__ __forceinline__ void fused_teardown(uint32_t tmem_base) {
   tc_fence_before();
-  if (kCG == 2) cluster_sync_all(); else __syncthreads();
+  if (kCG == 2 || kMC > 1) cluster_sync_all(); else __syncthreads();
   if ((threadIdx.x >> 5) == 1) {
     __syncwarp();
     tc_fence_after();
@@ -140,7 +144,7 @@ __device__ __forceinline__ void fused_teardown(uint32_t tmem_base) {
 }
 
 // one thread: stream this CTA's weight blocks through the ring
-template <int kCG>
+template <int kCG, int kMC = 1>
 __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uint8_t* wblob, uint8_t* smem, const FusedBars& B, int64_t it0,
                                                int64_t n_items, int64_t it_stride, uint32_t rank) {
   int rs = 0; uint32_t rph = 0;
@@ -155,6 +159,11 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
         for (int b = 0; b < nblk; ++b) {
           { EO_T0(); mbar_wait(&B.w_empty[rs], rph ^ 1); EO_T1(2); }
           mbar_expect_tx(&B.w_full[rs], bytes);
+          if (kMC > 1) {
+            constexpr uint32_t piece = kBlkBytes / kMC;          // this CTA's share of the block, broadcast to the whole cluster
+            bulk_load_multicast(smem + kOffRing + rs * kBlkBytes + rank * piece, src + (size_t)b * kBlkBytes + rank * piece, piece, &B.w_full[rs],
+                                (uint16_t)((1u << kMC) - 1));
+          } else
           bulk_load(smem + kOffRing + rs * kBlkBytes, src + base + (size_t)b * kBlkBytes, bytes, &B.w_full[rs]);
           if (++rs == kRingStages) { rs = 0; rph ^= 1; }
         }
@@ -177,7 +186,7 @@ __device__ __forceinline__ void fused_forwarder(const MmaProgram& prog, const Fu
 }
 
 // the whole MMA warp (kCG = 2: of the leader CTA), converged: issue the MMAs of every stage for both slots
-template <int kCG>
+template <int kCG, int kMC = 1>
 __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t* smem, const FusedBars& B, uint32_t tmem_base, int64_t it0,
                                                  int64_t n_items, int64_t it_stride) {
   int rs = 0; uint32_t rph = 0;
@@ -209,7 +218,9 @@ __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t
               umma_k128<kCG>(d_tmem, la + 2, lb + 2, idesc, 1);
               umma_k128<kCG>(d_tmem, la + 4, lb + 4, idesc, 1);
               umma_k128<kCG>(d_tmem, la + 6, lb + 6, idesc, 1);
-              if (kCG == 2) umma_commit_2cta(&B.w_empty[rs]); else umma_commit(&B.w_empty[rs]);
+              if (kCG == 2) umma_commit_2cta(&B.w_empty[rs]);
+              else if (kMC > 1) umma_commit_multicast(&B.w_empty[rs], (uint16_t)((1u << kMC) - 1));
+              else umma_commit(&B.w_empty[rs]);
             }
             __syncwarp();
             if (++rs == kRingStages) { rs = 0; rph ^= 1; }
@@ -249,7 +260,7 @@ static int launch_fused(Kernel kernel, int cg, int n_ctas, const Params& p, cuda
   return EONERF_OK;
 }
 
-// number of CTAs for n_tiles tiles: kCG CTAs per work item of 2*kCG tiles, at most one CTA per SM
+// number of CTAs for n_tiles tiles: `cg` CTAs (cluster size) per work item of 2*cg tiles, at most one CTA per SM
 static inline int fused_ctas(int64_t n_tiles, int cg) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -217,4 +217,18 @@ __device__ __forceinline__ void umma_k128(uint32_t tmem_d, uint32_t lo_a, uint32
         : "memory");
 }
 
+// ---- weight multicast inside a cluster (each CTA loads 1/n of a block and broadcasts it to all CTAs of the cluster) ----
+__device__ __forceinline__ void bulk_load_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 }  // namespace eonerf

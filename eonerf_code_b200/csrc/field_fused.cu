@@ -59,7 +59,7 @@ struct FusedFwdParams {
 };
 
 template <bool kTrain, int kCG, int kMC>
-__global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __grid_constant__ FusedFwdParams p) {
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __grid_constant__ FusedFwdParams p, const __grid_constant__ CUtensorMap wmap) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* cst = (float*)(smem + kOffConst);
@@ -80,10 +80,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
   const int64_t it0 = blockIdx.x / kCl, it_stride = gridDim.x / kCl;
 
   if (warp == 0) {
-    if (lane == 0) fused_producer<kCG, kMC>(p.prog, p.wblob, smem, B, it0, n_items, it_stride, rank);
+    if (lane == 0) fused_producer<kCG, kMC>(p.prog, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
     if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);      // whole warp, converged
-    else if (lane == 0) fused_forwarder(p.prog, B, it0, n_items, it_stride);
   } else {
     // ===== epilogue warps =====
     const int e = threadIdx.x - 64;
@@ -179,7 +178,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           }
           const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + col0;
           float h0 = 0.f, h1 = 0.f, h2 = 0.f;               // head partial sums
-          uint32_t* mrow = (kTrain && d.mask >= 0 && valid) ? p.mask[d.mask] + pt * 8 + col0 / 32 : nullptr;
+          uint32_t* mrow = (kTrain && d.mask >= 0 && valid && !(p.training & 4)) ? p.mask[d.mask] + pt * 8 + col0 / 32 : nullptr;
 #pragma unroll 1
           for (int c = 0; c < cpt / 32; ++c) {
             uint32_t v[32];
@@ -254,7 +253,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           { EO_T0(); named_bar_sync(1, kEpiThreads); if (e == 32) EO_T1(5); }
           if (e == 0) {
             if (s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
-            if (kTrain && tile < p.n_tiles) {
+            if (kTrain && tile < p.n_tiles && !(p.training & 2)) {
               const int nb = d.halves * 2;
               for (int bb = 0; bb < nb; ++bb)
                 bulk_store(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes,
@@ -362,15 +361,15 @@ static MmaProgram fwd_program(int n_stages) {
 
 // How the CTAs of the fused kernels cooperate (EONERF_FUSED_MODE overrides, for A/B timing):
 //    1  every CTA on its own
-//    2  CTA pairs issuing cta_group::2 MMAs (each CTA streams half of every weight block)
-//   12  clusters of 2 sharing the weight stream by TMA multicast (independent cta_group::1 MMAs)   <- default
+//    2  CTA pairs issuing cta_group::2 MMAs (each CTA streams half of every weight block)            <- default
+//   12  clusters of 2 sharing the weight stream by TMA multicast (independent cta_group::1 MMAs)
 //   14  clusters of 4 sharing the weight stream
 int fused_cta_group() {
   static int mode = 0;
   if (!mode) {
     const char* e = getenv("EONERF_FUSED_MODE");
-    mode = e ? atoi(e) : 12;
-    if (mode != 1 && mode != 2 && mode != 12 && mode != 14) mode = 12;
+    mode = e ? atoi(e) : 2;
+    if (mode != 1 && mode != 2 && mode != 12 && mode != 14) mode = 2;
   }
   return mode;
 }
@@ -448,6 +447,7 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   p.n_tiles = (N + kTileM - 1) / kTileM;
   p.n_stages = a->density_only ? 8 : kFwdStages;
   p.training = train;
+  if (const char* dbg = getenv("EONERF_FUSED_DBG")) p.training |= atoi(dbg);   // experiment knob: 2 = skip stash stores, 4 = skip masks
   p.x = a->x;
   p.origins = a->origins; p.o_stride = a->origins_stride; p.viewdirs = a->viewdirs; p.d_stride = a->viewdirs_stride;
   p.ray_indices = a->ray_indices; p.t_starts = a->t_starts; p.t_ends = a->t_ends; p.z_mid = a->z_mid;
@@ -469,6 +469,8 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   const int n_ctas = fused_ctas(p.n_tiles, csz);
   const double flops = (double)N * (a->density_only ? 982528.0 : 1345280.0);
   int rc = EONERF_OK;
+  CUtensorMap wmap;
+  if ((rc = make_blob_map(&wmap, p.wblob, kFwdBlocks)) != EONERF_OK) return rc;
 #define EO_LAUNCH_FWD(CG, MC)                                                                                                   \
   do {                                                                                                                          \
     static bool configured = false;                                                                                             \
@@ -478,7 +480,7 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
       configured = true;                                                                                                        \
     }                                                                                                                           \
     profile_begin(3, flops, 0.0, s);                                                                                            \
-    rc = train ? launch_fused(fused_fwd_kernel<true, CG, MC>, csz, n_ctas, p, s) : launch_fused(fused_fwd_kernel<false, CG, MC>, csz, n_ctas, p, s); \
+    rc = train ? launch_fused(fused_fwd_kernel<true, CG, MC>, csz, n_ctas, p, wmap, s) : launch_fused(fused_fwd_kernel<false, CG, MC>, csz, n_ctas, p, wmap, s); \
   } while (0)
   if (mode == 1) EO_LAUNCH_FWD(1, 1);
   else if (mode == 2) EO_LAUNCH_FWD(2, 1);

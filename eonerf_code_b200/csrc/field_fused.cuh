@@ -7,6 +7,8 @@
 // with one cp.async.bulk and no tensor map.  Read the other way round the same image is the MN-major operand of the
 // parameter-gradient GEMM (contraction over the samples).
 #pragma once
+#include <cuda.h>
+
 #include "field_layout.cuh"
 
 namespace eonerf {
@@ -114,6 +116,9 @@ struct GemmTNBlocked {
   float* db[2] = {nullptr, nullptr};
 };
 int gemm_tn_blocked(const GemmTNBlocked& g, cudaStream_t s);
+// all GEMMs of `list` in one persistent launch (at most 16 per launch; longer lists are cut)
+int gemm_tn_blocked_group(const GemmTNBlocked* list, int n, cudaStream_t s);
 int fused_cta_group();
+int make_blob_map(CUtensorMap* map, const void* base, int64_t n_blocks);
 
 }  // namespace eonerf

@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t apply_mask(uint32_t pk, uint32_t m, int j) {
 }
 
 template <int kCG, int kMC>
-__global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __grid_constant__ FusedBwdParams p) {
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __grid_constant__ FusedBwdParams p, const __grid_constant__ CUtensorMap wmap) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* hw = (float*)(smem + kOffConst);                   // head weights: w_sigma 256 | w_alb 384 | w_ts 128 | w_tb 128
@@ -94,10 +94,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
   const int64_t it0 = blockIdx.x / kCl, it_stride = gridDim.x / kCl;
 
   if (warp == 0) {
-    if (lane == 0) fused_producer<kCG, kMC>(p.mma, p.wblob, smem, B, it0, n_items, it_stride, rank);
+    if (lane == 0) fused_producer<kCG, kMC>(p.mma, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
     if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC>(p.mma, smem, B, tmem_base, it0, n_items, it_stride);       // whole warp, converged
-    else if (lane == 0) fused_forwarder(p.mma, B, it0, n_items, it_stride);
   } else {
     // ===== epilogue warps =====
     const int e = threadIdx.x - 64;
@@ -562,6 +561,8 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   const int n_ctas = fused_ctas(p.n_tiles, csz);
   const double flops = (double)N * (a->density_only ? 982528.0 : 1345280.0);
   int rc = EONERF_OK;
+  CUtensorMap wmap;
+  if ((rc = make_blob_map(&wmap, p.wblob, kBwdBlocks)) != EONERF_OK) return rc;
 #define EO_LAUNCH_BWD(CG, MC)                                                                                             \
   do {                                                                                                                    \
     static bool configured = false;                                                                                       \
@@ -570,7 +571,7 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
       configured = true;                                                                                                  \
     }                                                                                                                     \
     profile_begin(4, flops, 0.0, s);                                                                                      \
-    rc = launch_fused(fused_bwd_kernel<CG, MC>, csz, n_ctas, p, s);                                                       \
+    rc = launch_fused(fused_bwd_kernel<CG, MC>, csz, n_ctas, p, wmap, s);                                                       \
   } while (0)
   if (mode == 1) EO_LAUNCH_BWD(1, 1);
   else if (mode == 2) EO_LAUNCH_BWD(2, 1);
@@ -583,6 +584,8 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   if (!G) return EONERF_OK;
 
   // ---- parameter gradients: dW = G^T X over the blocked arrays ----
+  GemmTNBlocked gemms[16];
+  int n_gemms = 0;
   auto garr = [&](int i) { return (const uint8_t*)(sc + C.g[i]); };
   auto sarr = [&](int i) { return st + S.arr[i]; };
   auto dW = [&](const uint8_t* Gp, int g_nb, int g_blk0, int mt, const uint8_t* Xp, int x_nb, int x_blk0, int x_cnt, int k_valid,
@@ -592,7 +595,8 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
     t.X = Xp; t.x_nb = x_nb; t.x_blk0 = x_blk0; t.x_cnt = x_cnt; t.k_valid = k_valid;
     t.n_tiles = S.n_tiles;
     t.D[0] = d0; t.ldd[0] = ld0; t.db[0] = b0; t.D[1] = d1; t.ldd[1] = ld1; t.db[1] = b1;
-    return gemm_tn_blocked(t, s);
+    gemms[n_gemms++] = t;                                     // launched together at the end (one persistent kernel)
+    return (int)EONERF_OK;
   };
   const float* dpre = p.dpre;
   if (!a->density_only) {
@@ -640,7 +644,7 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   }
   EO_TRY(dW(garr(0), 4, 0, 2, sarr(kArrEnc), 1, 0, 1, 63, G->trunk_w[0], 63, G->trunk_b[0], G->trunk_w[0] + (int64_t)kHid * 63, 63,
             G->trunk_b[0] + kHid));
-  return EONERF_OK;
+  return gemm_tn_blocked_group(gemms, n_gemms, s);
 }
 
 }  // namespace eonerf

@@ -122,8 +122,8 @@ __device__ __forceinline__ void fused_setup(uint8_t* smem, FusedBars& B, uint32_
   B.act_ready = B.acc_full + 2;
   tmem_base_s = (uint32_t*)(B.act_ready + 2);
   if (threadIdx.x == 0) {
-    const uint32_t n_arr = (kCG == 2 && rank == 0) ? 2 : 1;   // leader of a pair: + the peer's forwarded / remote arrival
-    for (int s = 0; s < kRingStages; ++s) { mbar_init(&B.w_full[s], n_arr); mbar_init(&B.w_empty[s], kMC); }
+    const uint32_t n_arr = (kCG == 2 && rank == 0) ? 2 : 1;   // leader of a pair: + the peer epilogue's remote arrival
+    for (int s = 0; s < kRingStages; ++s) { mbar_init(&B.w_full[s], 1); mbar_init(&B.w_empty[s], kMC); }
     for (int s = 0; s < 2; ++s) { mbar_init(&B.acc_full[s], 1); mbar_init(&B.act_ready[s], n_arr); }
     fence_barrier_init();
   }
@@ -145,8 +145,8 @@ __device__ __forceinline__ void fused_teardown(uint32_t tmem_base) {
 
 // one thread: stream this CTA's weight blocks through the ring
 template <int kCG, int kMC = 1>
-__device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uint8_t* wblob, uint8_t* smem, const FusedBars& B, int64_t it0,
-                                               int64_t n_items, int64_t it_stride, uint32_t rank) {
+__device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uint8_t* wblob, const CUtensorMap* wmap, uint8_t* smem,
+                                               const FusedBars& B, int64_t it0, int64_t n_items, int64_t it_stride, uint32_t rank) {
   int rs = 0; uint32_t rph = 0;
   for (int64_t it = it0; it < n_items; it += it_stride)
     for (int s = 0; s < prog.n; ++s) {
@@ -158,6 +158,17 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
       for (int rep = 0; rep < 2; ++rep)
         for (int b = 0; b < nblk; ++b) {
           { EO_T0(); mbar_wait(&B.w_empty[rs], rph ^ 1); EO_T1(2); }
+          if (kCG == 2) {
+            // pair: both CTAs' copies are counted on the leader's barrier; block (stage, half = rank, kb) or, for the
+            // 128-wide stages, rows rank*64.. of block kb
+            if (rank == 0) mbar_expect_tx(&B.w_full[rs], 2 * bytes);
+            uint8_t* dst = smem + kOffRing + rs * kBlkBytes;
+            const int row0 = (d.blk_off + (d.halves == 2 ? (int)rank * d.nkb + b : b)) * 128 + (d.halves == 2 ? 0 : (int)rank * 64);
+            tma_load_2d_2cta(dst, wmap, &B.w_full[rs], 0, row0);
+            if (d.halves == 2) tma_load_2d_2cta(dst + kBlkBytes / 2, wmap, &B.w_full[rs], 0, row0 + 64);
+            if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&B.w_full[rs], bytes);
           if (kMC > 1) {
             constexpr uint32_t piece = kBlkBytes / kMC;          // this CTA's share of the block, broadcast to the whole cluster
@@ -165,21 +176,6 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
                                 (uint16_t)((1u << kMC) - 1));
           } else
           bulk_load(smem + kOffRing + rs * kBlkBytes, src + base + (size_t)b * kBlkBytes, bytes, &B.w_full[rs]);
-          if (++rs == kRingStages) { rs = 0; rph ^= 1; }
-        }
-    }
-}
-
-// kCG = 2, peer CTA, one thread: tell the leader when this CTA's half of a ring stage has landed
-__device__ __forceinline__ void fused_forwarder(const MmaProgram& prog, const FusedBars& B, int64_t it0, int64_t n_items, int64_t it_stride) {
-  int rs = 0; uint32_t rph = 0;
-  for (int64_t it = it0; it < n_items; it += it_stride)
-    for (int s = 0; s < prog.n; ++s) {
-      const int nblk = prog.st[s].nkb;
-      for (int rep = 0; rep < 2; ++rep)
-        for (int b = 0; b < nblk; ++b) {
-          mbar_wait(&B.w_full[rs], rph);
-          mbar_arrive_remote(&B.w_full[rs], 0);
           if (++rs == kRingStages) { rs = 0; rph ^= 1; }
         }
     }
@@ -245,7 +241,7 @@ __device__ __forceinline__ void signal_act_ready(const FusedBars& B, int slot, u
 }
 
 template <class Kernel, class Params>
-static int launch_fused(Kernel kernel, int cg, int n_ctas, const Params& p, cudaStream_t s) {
+static int launch_fused(Kernel kernel, int cg, int n_ctas, const Params& p, const CUtensorMap& wmap, cudaStream_t s) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)n_ctas);
   cfg.blockDim = dim3(kFusedThreads);
@@ -256,7 +252,7 @@ static int launch_fused(Kernel kernel, int cg, int n_ctas, const Params& p, cuda
   attr[0].val.clusterDim.x = (unsigned)cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EO_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  EO_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, wmap));
   return EONERF_OK;
 }
 

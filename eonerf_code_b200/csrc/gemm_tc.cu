@@ -14,6 +14,8 @@
 //   K-major  SW128: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), 16-byte chunks XOR-swizzled by row%8
 //   MN-major SW128: the same physical image read the other way round: 64 contiguous MN elements x 8 K-rows per
 //                   atom, K groups SBO = 1024 B apart, 64-wide MN blocks LBO = (one TMA box) apart.
+#include <stdlib.h>
+
 #include "field_fused.cuh"
 #include "tc_ptx.cuh"
 
@@ -368,6 +370,21 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D bf16 row-major [rows, cols] (leading dimension ld elements); box = 64 columns x box_rows rows, 128-byte swizzle;
 // out-of-bounds elements read as zero (ragged M / K tails need no special casing in the kernels)
+// plain (un-swizzled) map over the pre-tiled weight blob of the fused kernels: rows of 64 bf16 (one 128-byte row of a
+// block image), boxes of 64 rows = 8 KB, copied verbatim
+int make_blob_map(CUtensorMap* map, const void* base, int64_t n_blocks) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EONERF_ECUDA; }
+  cuuint64_t gdim[2] = {64, (cuuint64_t)n_blocks * 128};
+  cuuint64_t gstr[1] = {128};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weight blob) failed (%d)", (int)r); return EONERF_ECUDA; }
+  return EONERF_OK;
+}
+
 static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   if (rows <= 0 || cols <= 0) { set_error("empty tensor map"); return EONERF_EINVAL; }
   EncodeTiledFn fn = encode_fn();
@@ -487,35 +504,60 @@ int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
 
 
 // ------------------------------------------------------------------------------------------------
-// TN over tile-blocked operands (field_fused.cuh): D[n,k] += sum_m G[m,n] X[m,k], db[n] += sum_m G[m,n].
-// A 64-sample half of a 16 KB block [128 samples x 64 features] is 8 KB contiguous and already the MN-major SW128
-// image the MMA wants, so operands arrive with plain cp.async.bulk copies (no tensor maps).  The four epilogue warps
-// are idle during the main loop: they sum the columns of the G tiles in shared memory (the bias gradient) while the
-// tensor core consumes the same tiles.
+// Grouped TN over tile-blocked operands (field_fused.cuh): for every GEMM g of a list
+//     D_g[n,k] += sum_m G_g[m,n] X_g[m,k],      db_g[n] += sum_m G_g[m,n]
+// in ONE persistent launch.  A 64-sample half of a 16 KB block [128 samples x 64 features] is 8 KB contiguous and already
+// the MN-major SW128 image the MMA wants, so operands arrive with plain cp.async.bulk copies (no tensor maps).
+//
+// Work split: the list is laid out on one axis of "cost" (8 KB boxes to stream); CTA b owns the interval
+// [b, b+1) * total / gridDim.x and walks the GEMMs it overlaps.  A GEMM is therefore shared by only ~total/148-sized
+// pieces (about 7 CTAs for a 23-GEMM backward pass) instead of by all 148 CTAs: the fp32 partial tiles are merged with
+// red.global and the L2 atomic units, not HBM, were the bottleneck when every CTA contributed to every GEMM
+// (measured: 4.26 ms -> 2.53 ms for the dW GEMMs of one training step with the merge switched off).
+// The four epilogue warps are idle during the main loop: they sum the columns of the G tiles in shared memory (the bias
+// gradient) while the tensor core consumes the same tiles.
 // ------------------------------------------------------------------------------------------------
-struct TNBParams {
-  const uint8_t* G; int g_nb, g_blk0, mt_count;
-  const uint8_t* X; int x_nb, x_blk0, x_cnt;
-  int64_t chunks, chunks_per_cta;
-  int n_valid[2]; int k_valid;
+constexpr int kTNGroupMax = 16;
+struct TNBGemm {
+  const uint8_t* G; const uint8_t* X;
+  int32_t g_nb, g_blk0, mt_count, x_nb, x_blk0, x_cnt;
+  int32_t n_valid[2]; int32_t k_valid;
   float* D[2]; int64_t ldd[2]; float* db[2];
+  int64_t chunks;          // 64-sample chunks
+  int64_t cost0;           // cumulative cost (boxes) before this GEMM
+};
+struct TNBParams {
+  int32_t n; int32_t dbg_skip_tail;
+  int64_t total_cost;
+  TNBGemm g[kTNGroupMax];
 };
 
 constexpr int kTNBStages = 3;
-constexpr int kSmemTNB = kTNBStages * 8 * kBoxBytes + 1024;
+constexpr int kTNBStageBytes = 8 * kBoxBytes;
+constexpr int kSmemTNB = kTNBStages * kTNBStageBytes + 1024;
+
+// chunk range [c0, c1) of GEMM gi owned by the CTA whose cost interval is [lo, hi)
+__device__ __forceinline__ void tnb_range(const TNBGemm& g, int64_t lo, int64_t hi, int64_t& c0, int64_t& c1) {
+  const int64_t per = 2 * g.mt_count + g.x_cnt;                   // boxes per chunk
+  const int64_t end = g.cost0 + g.chunks * per;
+  const int64_t a = lo > g.cost0 ? lo : g.cost0, b = hi < end ? hi : end;
+  if (b <= a) { c0 = c1 = 0; return; }
+  c0 = (a - g.cost0 + per - 1) / per;                             // a chunk belongs to the CTA that owns its first box
+  c1 = (b - g.cost0 + per - 1) / per;
+  if (c1 > g.chunks) c1 = g.chunks;
+}
 
 __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __grid_constant__ TNBParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int a_boxes = p.mt_count * 2;
-  const int stage_bytes = (a_boxes + p.x_cnt) * kBoxBytes;
-  __shared__ uint64_t full_bar[kTNBStages], empty_bar[kTNBStages], acc_full;
+  __shared__ uint64_t full_bar[kTNBStages], empty_bar[kTNBStages], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTNBStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 5); }   // MMA commit + 4 epilogue warps
     mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, 512);
@@ -523,61 +565,87 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int64_t c_begin = (int64_t)blockIdx.x * p.chunks_per_cta;
-  const int64_t c_end = (c_begin + p.chunks_per_cta < p.chunks) ? c_begin + p.chunks_per_cta : p.chunks;
-  const int64_t my_chunks = c_end > c_begin ? c_end - c_begin : 0;
-  const int block_k = p.x_cnt * 64;
+  const int64_t lo = p.total_cost * blockIdx.x / gridDim.x, hi = p.total_cost * (blockIdx.x + 1) / gridDim.x;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t c = c_begin; c < c_end; ++c) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* s0 = smem + (size_t)stage * stage_bytes;
-        mbar_expect_tx(&full_bar[stage], stage_bytes);
-        const int64_t tile = c >> 1;
-        const size_t hoff = (size_t)(c & 1) * kBoxBytes;
-        for (int b = 0; b < a_boxes; ++b)
-          bulk_load(s0 + b * kBoxBytes, p.G + ((size_t)tile * p.g_nb + p.g_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
-        for (int b = 0; b < p.x_cnt; ++b)
-          bulk_load(s0 + (a_boxes + b) * kBoxBytes, p.X + ((size_t)tile * p.x_nb + p.x_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
-        if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
+      for (int gi = 0; gi < p.n; ++gi) {
+        const TNBGemm& g = p.g[gi];
+        int64_t c0, c1;
+        tnb_range(g, lo, hi, c0, c1);
+        const int a_boxes = g.mt_count * 2;
+        for (int64_t c = c0; c < c1; ++c) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* s0 = smem + (size_t)stage * kTNBStageBytes;
+          mbar_expect_tx(&full_bar[stage], (a_boxes + g.x_cnt) * kBoxBytes);
+          const int64_t tile = c >> 1;
+          const size_t hoff = (size_t)(c & 1) * kBoxBytes;
+          for (int b = 0; b < a_boxes; ++b)
+            bulk_load(s0 + b * kBoxBytes, g.G + ((size_t)tile * g.g_nb + g.g_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
+          for (int b = 0; b < g.x_cnt; ++b)
+            bulk_load(s0 + (a_boxes + b) * kBoxBytes, g.X + ((size_t)tile * g.x_nb + g.x_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
+          if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = instr_desc(kBlockM, block_k, 1, 1);
-      int stage = 0; uint32_t phase = 0;
-      for (int64_t c = 0; c < my_chunks; ++c) {
+    // whole warp converged, MMAs predicated on one elected lane: keeps the descriptors in uniform registers (tc_ptx.cuh)
+    const bool elected = elect_one_sync();
+    int stage = 0; uint32_t phase = 0;
+    uint32_t items = 0;
+    for (int gi = 0; gi < p.n; ++gi) {
+      const TNBGemm& g = p.g[gi];
+      int64_t c0, c1;
+      tnb_range(g, lo, hi, c0, c1);
+      if (c1 <= c0) continue;
+      const uint32_t idesc = instr_desc(kBlockM, g.x_cnt * 64, 1, 1);
+      const int a_boxes = g.mt_count * 2;
+      if (items > 0) {                                           // the epilogue has drained the previous item's accumulators
+        mbar_wait(&acc_empty, (items - 1) & 1u);
+        tc_fence_after();
+      }
+      for (int64_t c = c0; c < c1; ++c) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t s0 = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t s0 = smem_u32(smem + (size_t)stage * kTNBStageBytes);
         const uint32_t sx = s0 + a_boxes * kBoxBytes;
+        if (elected) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t dx = smem_desc(sx + k * 2048, kBoxBytes, 1024);
-          for (int mt = 0; mt < p.mt_count; ++mt) {
-            const uint64_t da = smem_desc(s0 + mt * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
-            umma_bf16(tmem_base + mt * 256, da, dx, idesc, (c | k) != 0);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t dx = smem_desc(sx + k * 2048, kBoxBytes, 1024);
+            umma_bf16(tmem_base, smem_desc(s0 + k * 2048, kBoxBytes, 1024), dx, idesc, (c > c0) || k != 0);
+            if (g.mt_count == 2) umma_bf16(tmem_base + 256, smem_desc(s0 + 2 * kBoxBytes + k * 2048, kBoxBytes, 1024), dx, idesc, (c > c0) || k != 0);
           }
+          umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&acc_full);
+      if (elected) umma_commit(&acc_full);
+      __syncwarp();
+      ++items;
     }
   } else {
     // ===== epilogue warps: bias-gradient side job during the main loop, then TMEM -> red.global =====
     const int t = threadIdx.x - 64;                       // 0..127: box t/32, 32-bit word `lane` of each 128-byte row
     const int box = t >> 5;
-    const bool do_sum = box < a_boxes && p.db[box >> 1] != nullptr;
-    float s_lo = 0.f, s_hi = 0.f;
-    {
-      int stage = 0; uint32_t phase = 0;
-      for (int64_t c = 0; c < my_chunks; ++c) {
+    const int quarter = warp & 3;
+    int stage = 0; uint32_t phase = 0;
+    uint32_t items = 0;
+    for (int gi = 0; gi < p.n; ++gi) {
+      const TNBGemm& g = p.g[gi];
+      int64_t c0, c1;
+      tnb_range(g, lo, hi, c0, c1);
+      if (c1 <= c0) continue;
+      const int a_boxes = g.mt_count * 2;
+      const int block_k = g.x_cnt * 64;
+      const bool do_sum = box < a_boxes && g.db[box >> 1] != nullptr;
+      float s_lo = 0.f, s_hi = 0.f;
+      for (int64_t c = c0; c < c1; ++c) {
         mbar_wait(&full_bar[stage], phase);
         if (do_sum) {
-          const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes + box * kBoxBytes) + (lane & 3) * 4;
+          const uint32_t base = smem_u32(smem + (size_t)stage * kTNBStageBytes + box * kBoxBytes) + (lane & 3) * 4;
 #pragma unroll 8
           for (int rr = 0; rr < 64; ++rr) {
             uint32_t w;
@@ -590,29 +658,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
         if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
       }
-    }
-    if (do_sum && my_chunks > 0) {
-      const int mt = box >> 1;
-      const int n = (box & 1) * 64 + 2 * lane;
-      if (n < p.n_valid[mt]) atomicAdd(p.db[mt] + n, s_lo);
-      if (n + 1 < p.n_valid[mt]) atomicAdd(p.db[mt] + n + 1, s_hi);
-    }
-    if (my_chunks > 0) {
-      const int quarter = warp & 3;
-      mbar_wait(&acc_full, 0);
+      if (do_sum) {
+        const int mt = box >> 1;
+        const int n = (box & 1) * 64 + 2 * lane;
+        if (n < g.n_valid[mt]) atomicAdd(g.db[mt] + n, s_lo);
+        if (n + 1 < g.n_valid[mt]) atomicAdd(g.db[mt] + n + 1, s_hi);
+      }
+      mbar_wait(&acc_full, items & 1u);
       tc_fence_after();
-      for (int mt = 0; mt < p.mt_count; ++mt) {
+      for (int mt = 0; mt < g.mt_count; ++mt) {
         const int n = quarter * 32 + lane;                 // output row (feature of G) inside this 128-row block
         const uint32_t taddr = tmem_base + mt * 256 + ((uint32_t)(quarter * 32) << 16);
-        const bool vec = (p.ldd[mt] & 3) == 0 && ((uintptr_t)p.D[mt] & 15) == 0;
+        const bool vec = (g.ldd[mt] & 3) == 0 && ((uintptr_t)g.D[mt] & 15) == 0;
         for (int c = 0; c < block_k; c += 32) {
           __syncwarp();
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
-          if (n >= p.n_valid[mt] || p.D[mt] == nullptr) continue;
-          float* drow = p.D[mt] + (int64_t)n * p.ldd[mt] + c;
-          if (vec && c + 32 <= p.k_valid) {
+          if (n >= g.n_valid[mt] || g.D[mt] == nullptr || p.dbg_skip_tail) continue;
+          float* drow = g.D[mt] + (int64_t)n * g.ldd[mt] + c;
+          if (vec && c + 32 <= g.k_valid) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + j), "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
@@ -621,10 +686,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c + j < p.k_valid) atomicAdd(drow + j, __uint_as_float(r[j]));
+              if (c + j < g.k_valid) atomicAdd(drow + j, __uint_as_float(r[j]));
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty);
+      ++items;
     }
   }
   tc_fence_before();
@@ -636,30 +705,47 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
   }
 }
 
-int gemm_tn_blocked(const GemmTNBlocked& g, cudaStream_t s) {
-  if (g.n_tiles <= 0) return EONERF_OK;
-  EO_REQUIRE(g.mt_count >= 1 && g.mt_count <= 2 && g.x_cnt >= 1 && g.x_cnt <= 4, "gemm_tn_blocked: unsupported shape");
+int gemm_tn_blocked_group(const GemmTNBlocked* list, int n, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     EO_CUDA(cudaFuncSetAttribute(gemm_tn_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTNB));
     configured = true;
   }
-  TNBParams p{};
-  p.G = g.G; p.g_nb = g.g_nb; p.g_blk0 = g.g_blk0; p.mt_count = g.mt_count;
-  p.X = g.X; p.x_nb = g.x_nb; p.x_blk0 = g.x_blk0; p.x_cnt = g.x_cnt;
-  p.chunks = g.n_tiles * 2;
-  int64_t splits = sm_count();
-  if (splits > p.chunks) splits = p.chunks;
-  p.chunks_per_cta = (p.chunks + splits - 1) / splits;
-  splits = (p.chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
-  for (int i = 0; i < 2; ++i) { p.n_valid[i] = g.n_valid[i]; p.D[i] = g.D[i]; p.ldd[i] = g.ldd[i]; p.db[i] = g.db[i]; }
-  p.k_valid = g.k_valid;
-  const double M = (double)g.n_tiles * kTileM;
-  profile_begin(1, 2.0 * M * g.mt_count * 128 * g.k_valid, 2.0 * M * (g.mt_count * 128 + g.x_cnt * 64), s);
-  gemm_tn_blocked_kernel<<<(unsigned)splits, kThreads, kSmemTNB, s>>>(p);
-  profile_end(s);
-  EO_LAUNCH_CHECK();
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("EONERF_TN_DBG"); dbg = e ? atoi(e) : 0; }
+  for (int i0 = 0; i0 < n; i0 += kTNGroupMax) {
+    TNBParams p{};
+    double flops = 0, bytes = 0;
+    int64_t cost = 0, chunks_total = 0;
+    for (int i = i0; i < n && i < i0 + kTNGroupMax; ++i) {
+      const GemmTNBlocked& g = list[i];
+      if (g.n_tiles <= 0) continue;
+      EO_REQUIRE(g.mt_count >= 1 && g.mt_count <= 2 && g.x_cnt >= 1 && g.x_cnt <= 4, "gemm_tn_blocked: unsupported shape");
+      TNBGemm& q = p.g[p.n++];
+      q.G = g.G; q.X = g.X; q.g_nb = g.g_nb; q.g_blk0 = g.g_blk0; q.mt_count = g.mt_count;
+      q.x_nb = g.x_nb; q.x_blk0 = g.x_blk0; q.x_cnt = g.x_cnt; q.k_valid = g.k_valid;
+      for (int j = 0; j < 2; ++j) { q.n_valid[j] = g.n_valid[j]; q.D[j] = g.D[j]; q.ldd[j] = g.ldd[j]; q.db[j] = (dbg & 2) ? nullptr : g.db[j]; }
+      q.chunks = g.n_tiles * 2;
+      q.cost0 = cost;
+      cost += q.chunks * (2 * g.mt_count + g.x_cnt);
+      chunks_total += q.chunks;
+      const double M = (double)g.n_tiles * kTileM;
+      flops += 2.0 * M * g.mt_count * 128 * g.k_valid;
+      bytes += 2.0 * M * (g.mt_count * 128 + g.x_cnt * 64);
+    }
+    if (p.n == 0) continue;
+    p.total_cost = cost;
+    p.dbg_skip_tail = dbg & 1;
+    int64_t grid = sm_count();
+    if (grid > chunks_total) grid = chunks_total;
+    profile_begin(1, flops, bytes, s);
+    gemm_tn_blocked_kernel<<<(unsigned)grid, kThreads, kSmemTNB, s>>>(p);
+    profile_end(s);
+    EO_LAUNCH_CHECK();
+  }
   return EONERF_OK;
 }
+
+int gemm_tn_blocked(const GemmTNBlocked& g, cudaStream_t s) { return gemm_tn_blocked_group(&g, 1, s); }
 
 }  // namespace eonerf

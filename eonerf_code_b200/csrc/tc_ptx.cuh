@@ -231,4 +231,13 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
                : "memory");
 }
 
+// CTA-pair TMA: the copy lands in THIS CTA's shared memory but its bytes are counted on the LEADER CTA's mbarrier
+// (address with the peer bit cleared), so the MMA issuer waits on one barrier for both halves of a weight block
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 }  // namespace eonerf

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeonerf_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 COMP_COLS = 12
 OUT_COLS = 21
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16_FUSED = 0, 1, 2, 3
@@ -28,7 +28,8 @@ class Profile(C.Structure):
 class SampleArgs(C.Structure):
     _fields_ = [("origins", P), ("origins_stride", I64), ("viewdirs", P), ("viewdirs_stride", I64),
                 ("near", P), ("near_stride", I64), ("u", P), ("z_steps", P), ("n_rays", I64), ("n_samples", I32),
-                ("ray_indices", P), ("t_starts", P), ("t_ends", P), ("pts_per_ray", P), ("ray_offsets", P), ("stats", P)]
+                ("ray_indices", P), ("t_starts", P), ("t_ends", P), ("pts_per_ray", P), ("ray_offsets", P), ("stats", P),
+                ("run_if", P)]
 
 
 class WeightsFwdArgs(C.Structure):
@@ -108,7 +109,7 @@ class FieldFwdArgs(C.Structure):
                 ("x", P), ("origins", P), ("origins_stride", I64), ("viewdirs", P), ("viewdirs_stride", I64),
                 ("ray_indices", P), ("t_starts", P), ("t_ends", P), ("z_mid", P), ("img_idx", P), ("img_idx_stride", I64),
                 ("cond_dirs", P), ("cond_dirs_stride", I64), ("density_only", I32), ("stash", P),
-                ("sigma", P), ("rgb", P), ("transient_s", P), ("transient_beta", P)]
+                ("sigma", P), ("rgb", P), ("transient_s", P), ("transient_beta", P), ("n_pts_dev", P)]
 
 
 class FieldBwdArgs(C.Structure):
@@ -116,7 +117,7 @@ class FieldBwdArgs(C.Structure):
                 ("density_only", I32), ("stash", P), ("scratch", P),
                 ("sigma", P), ("rgb", P), ("transient_s", P), ("transient_beta", P),
                 ("g_sigma", P), ("g_rgb", P), ("g_transient_s", P), ("g_transient_beta", P),
-                ("grads", C.POINTER(FieldParams)), ("g_x", P)]
+                ("grads", C.POINTER(FieldParams)), ("g_x", P), ("n_pts_dev", P)]
 
 
 class AmbientFwdArgs(C.Structure):

@@ -46,6 +46,7 @@ __constant__ FStage c_fstage[kFwdStages] = {
 
 struct FusedFwdParams {
   int64_t M; int64_t n_tiles; int n_stages; int training;
+  const int64_t* M_dev;          // live sample count on the device (M, n_tiles are then capacities)
   const float* x;
   const float* origins; int64_t o_stride; const float* viewdirs; int64_t d_stride;
   const int64_t* ray_indices; const float* t_starts; const float* t_ends; float* z_mid;
@@ -75,8 +76,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
   if (kCl > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
+  const int64_t M = p.M_dev ? __ldg(p.M_dev) : p.M;
+  const int64_t n_tiles = p.M_dev ? (M + kTileM - 1) / kTileM : p.n_tiles;
   // work items: 2 tiles per CTA of the cluster; this CTA owns tiles (2*kCl*it + 2*rank + slot)
-  const int64_t n_items = (p.n_tiles + 2 * kCl - 1) / (2 * kCl);
+  const int64_t n_items = (n_tiles + 2 * kCl - 1) / (2 * kCl);
   const int64_t it0 = blockIdx.x / kCl, it_stride = gridDim.x / kCl;
 
   if (warp == 0) {
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
       for (int slot = 0; slot < 2; ++slot) {
         const int64_t tile = 2 * kCl * it + 2 * rank + slot;
         const int64_t pt = tile * kTileM + r;
-        const bool valid = pt < p.M;
+        const bool valid = pt < M;
         float x[3] = {0.f, 0.f, 0.f};
         int64_t ray = -1;
         if (valid) {
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         if (kTrain) {
           for (int slot = 0; slot < 2; ++slot) {
             const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-            if (tile < p.n_tiles)
+            if (tile < n_tiles)
               bulk_store(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
           }
           tma_store_commit();
@@ -159,51 +162,58 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         const FStage d = c_fstage[s];
         const int cpt = d.halves == 2 ? 128 : 64;          // columns per thread
         const int col0 = half * cpt;
-        const float relu_lo = d.relu ? 0.f : -INFINITY;
+        const bool want_mask = kTrain && d.mask >= 0 && !(p.training & 4);
         for (int slot = 0; slot < 2; ++slot) {
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
           const int64_t pt = tile * kTileM + r;
-          const bool valid = pt < p.M;
+          const bool valid = pt < M;
           const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
           // per-image part of the HD0 bias (transient half only): W[:,256:260] . emb[img]
           const float* delta = (d.kind == 2 && half == 1) ? p.class_delta + (size_t)((cls_pack >> (16 * slot)) & 0xFFFFu) * kHid : nullptr;
           { EO_T0(); mbar_wait(&acc_full[slot], (cph >> slot) & 1u); if (e == 0) EO_T1(3); }
           cph ^= 1u << slot;
           tc_fence_after();
-          {
-            EO_T0();
-            if (e == 0) tma_store_wait_read<1>();           // this slot's previous stash store has drained (the other slot's may be in flight)
-            named_bar_sync(1, kEpiThreads);
-            if (e == 0) EO_T1(4);
-          }
           const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + col0;
           float h0 = 0.f, h1 = 0.f, h2 = 0.f;               // head partial sums
-          uint32_t* mrow = (kTrain && d.mask >= 0 && valid && !(p.training & 4)) ? p.mask[d.mask] + pt * 8 + col0 / 32 : nullptr;
-#pragma unroll 1
-          for (int c = 0; c < cpt / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c * 32, v);
-            float b[32];
+
+          // one 32-column chunk: accumulator + bias -> (ReLU) -> bf16 -> next A operand in shared memory; returns the ReLU keep bits
+          // (column 2j -> bit 15-j, column 2j+1 -> bit 31-j: the complement of the pre-activation sign bits, funnel-shifted in)
+          auto chunk = [&](uint32_t (&v)[32], const int c) -> uint32_t {
+            float x[32];
             const uint32_t sb = s_cst + (uint32_t)(d.bias_off + col0 + c * 32) * 4u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) lds_f4(sb + j * 16, b[4 * j], b[4 * j + 1], b[4 * j + 2], b[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) {
+              float b0, b1, b2, b3;
+              lds_f4(sb + j * 16, b0, b1, b2, b3);
+              x[4 * j] = __uint_as_float(v[4 * j]) + b0; x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b1;
+              x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b2; x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b3;
+            }
             if (delta) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 t = __ldg((const float4*)(delta + c * 32) + j);
-                b[4 * j] += t.x; b[4 * j + 1] += t.y; b[4 * j + 2] += t.z; b[4 * j + 3] += t.w;
+                x[4 * j] += t.x; x[4 * j + 1] += t.y; x[4 * j + 2] += t.z; x[4 * j + 3] += t.w;
               }
             }
-            tmem_ld_wait();
+            uint32_t sign = 0u;
+            if (want_mask) {                                  // four independent funnel-shift chains of 8
+              uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                s0 = __funnelshift_l(__float_as_uint(x[2 * j + 1]), s0, 1);        // odd columns 1..15   -> bits 31..24
+                s1 = __funnelshift_l(__float_as_uint(x[2 * j + 17]), s1, 1);       // odd columns 17..31  -> bits 23..16
+                s2 = __funnelshift_l(__float_as_uint(x[2 * j]), s2, 1);            // even columns 0..14  -> bits 15..8
+                s3 = __funnelshift_l(__float_as_uint(x[2 * j + 16]), s3, 1);       // even columns 16..30 -> bits 7..0
+              }
+              sign = __byte_perm(__byte_perm(s3, s2, 0x0040), __byte_perm(s1, s0, 0x0040), 0x5410);
+            }
             uint32_t pk[16];
+            if (d.relu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              pk[j] = pack_bf16(fmaxf(__uint_as_float(v[2 * j]) + b[2 * j], relu_lo), fmaxf(__uint_as_float(v[2 * j + 1]) + b[2 * j + 1], relu_lo));
-            if (mrow) {                                       // ReLU sign bits: column 2j -> bit 15-j, column 2j+1 -> bit 31-j
-              uint32_t bits = 0u;
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16_relu(x[2 * j], x[2 * j + 1]);
+            } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) bits |= ((pk[j] + 0x7FFF7FFFu) >> j) & (0x80008000u >> j);
-              mrow[c] = bits;
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
             }
             if (d.kind == 1) {
               const uint32_t sw = s_cst + (uint32_t)(kCWSigma + col0 + c * 32) * 4u;
@@ -246,24 +256,51 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
             const int ch0 = (colg & 63) >> 3;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) sts_u4(blk + blk_off(r, ch0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+            return ~sign;
+          };
+
+          // software pipeline over the chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+          uint32_t va[32], vb[32];
+          uint32_t m0, m1, m2 = 0u, m3 = 0u;
+          tmem_ld32(taddr, va);
+          tmem_ld_wait_dep(va);
+          tmem_ld32(taddr + 32, vb);
+          m0 = chunk(va, 0);
+          tmem_ld_wait_dep(vb);
+          if (cpt == 128) tmem_ld32(taddr + 64, va);
+          m1 = chunk(vb, 1);
+          if (cpt == 128) {
+            tmem_ld_wait_dep(va);
+            tmem_ld32(taddr + 96, vb);
+            m2 = chunk(va, 2);
+            tmem_ld_wait_dep(vb);
+            m3 = chunk(vb, 3);
           }
-          if (half == 1 && (d.kind == 1 || d.kind == 3)) sts_f2(s_part + r * 8, h0, h1);
+          if (want_mask && valid) {
+            uint32_t* mrow = p.mask[d.mask] + pt * 8 + col0 / 32;
+            if (cpt == 128) *(uint4*)mrow = make_uint4(m0, m1, m2, m3);
+            else *(uint2*)mrow = make_uint2(m0, m1);
+          }
+          if (half == 1 && (d.kind == 1 || d.kind == 3)) sts_f2(s_part + slot * 1024 + r * 8, h0, h1);
           tc_fence_before();
           fence_proxy_async();
+          // the OTHER slot's latest stash store (issued one epilogue ago) must have finished reading shared memory before the
+          // next epilogue overwrites that slot
+          if (kTrain && e == 0) tma_store_wait_read<0>();
           { EO_T0(); named_bar_sync(1, kEpiThreads); if (e == 32) EO_T1(5); }
           if (e == 0) {
             if (s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
-            if (kTrain && tile < p.n_tiles && !(p.training & 2)) {
+            if (kTrain && tile < n_tiles && !(p.training & 2)) {
               const int nb = d.halves * 2;
               for (int bb = 0; bb < nb; ++bb)
                 bulk_store(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes,
                            kBlkBytes);
+              tma_store_commit();
             }
-            if (kTrain) tma_store_commit();                  // always one group per (stage, slot): wait_group.read 1 counts on it
           }
           if (valid && half == 0 && d.kind != 0) {
             float p0 = 0.f, p1 = 0.f;
-            if (d.kind != 2) lds_f2(s_part + r * 8, p0, p1);
+            if (d.kind != 2) lds_f2(s_part + slot * 1024 + r * 8, p0, p1);
             if (d.kind == 1) {
               p.sigma[pt] = softplus_f(h0 + p0 + cst[kCScalars + 0]);                          // eonerf.py:106,145
             } else if (d.kind == 2) {
@@ -444,6 +481,7 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   const bool train = a->stash != nullptr;
   FusedFwdParams p{};
   p.M = N;
+  p.M_dev = a->n_pts_dev;
   p.n_tiles = (N + kTileM - 1) / kTileM;
   p.n_stages = a->density_only ? 8 : kFwdStages;
   p.training = train;

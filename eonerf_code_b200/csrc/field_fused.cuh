@@ -110,6 +110,7 @@ struct GemmTNBlocked {
   const uint8_t* G = nullptr; int g_nb = 4; int g_blk0 = 0; int mt_count = 2;   // G features: mt_count*128 from block g_blk0
   const uint8_t* X = nullptr; int x_nb = 4; int x_blk0 = 0; int x_cnt = 4;      // X features: x_cnt*64 from block x_blk0
   int64_t n_tiles = 0;
+  const int64_t* n_pts_dev = nullptr;   // live sample count on the device (n_tiles is then the capacity)
   int n_valid[2] = {128, 128};        // valid output rows per 128-row block of G features
   int k_valid = 256;                  // valid X features
   float* D[2] = {nullptr, nullptr}; int64_t ldd[2] = {0, 0};

@@ -49,6 +49,7 @@ static const int kBwdBlkCount[kBwdStages] = {2, 2, 2, 8, 8, 8, 8, 4, 8, 8, 8, 8,
 
 struct FusedBwdParams {
   int64_t M; int64_t n_tiles;
+  const int64_t* M_dev;          // live sample count on the device (M, n_tiles are then capacities)
   int n_prog; int8_t prog[kBwdStages];
   int density_only;
   const uint8_t* wblob; const float* consts;
@@ -90,7 +91,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
   if (kCl > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
-  const int64_t n_items = (p.n_tiles + 2 * kCl - 1) / (2 * kCl);
+  const int64_t M = p.M_dev ? __ldg(p.M_dev) : p.M;
+  const int64_t n_tiles = p.M_dev ? (M + kTileM - 1) / kTileM : p.n_tiles;
+  const int64_t n_items = (n_tiles + 2 * kCl - 1) / (2 * kCl);
   const int64_t it0 = blockIdx.x / kCl, it_stride = gridDim.x / kCl;
 
   if (warp == 0) {
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
       for (int slot = 0; slot < 2; ++slot) {
         const int64_t tile = 2 * kCl * it + 2 * rank + slot;
         const int64_t pt = tile * kTileM + r;
-        const bool valid = pt < p.M;
+        const bool valid = pt < M;
         const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
         const uint32_t s_row = smem_u32(smem + kOffRows) + (uint32_t)(slot * 128 + r) * 16u;
         float dsig = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, dts = 0.f, dtb = 0.f;
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
         }
         if (half == 0) {
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_row), "f"(dsig), "f"(d0), "f"(d1), "f"(d2) : "memory");
-          if (tile < p.n_tiles) {                            // rows of the padded tail are zero: they add nothing to dW
+          if (tile < n_tiles) {                            // rows of the padded tail are zero: they add nothing to dW
             float* dp = p.dpre + pt * 8;
             *(float4*)dp = make_float4(dsig, d0, d1, d2);
             *(float4*)(dp + 4) = make_float4(dts, dtb, 0.f, 0.f);
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
         const int nb = p.density_only ? 4 : 2;
         for (int slot = 0; slot < 2; ++slot) {
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-          if (tile < p.n_tiles)
+          if (tile < n_tiles)
             for (int bb = 0; bb < nb; ++bb)
               bulk_store(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
         }
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
         for (int slot = 0; slot < 2; ++slot) {
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
           const int64_t pt = tile * kTileM + r;
-          const bool valid = pt < p.M;
+          const bool valid = pt < M;
           const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
           const uint32_t s_row = smem_u32(smem + kOffRows) + (uint32_t)(slot * 128 + r) * 16u;
           // ReLU sign bits of this thread's columns (and of the albedo half for stage 2), fetched while the MMA runs
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           named_bar_sync(1, kEpiThreads);
           if (e == 0) {
             if (i + 1 < p.n_prog) signal_act_ready<kCG>(B, slot, rank);
-            if (d.garr >= 0 && tile < p.n_tiles) {
+            if (d.garr >= 0 && tile < n_tiles) {
               const int nb = d.kind == 1 ? 4 : d.halves * 2;
               const int b0 = d.kind == 1 ? 0 : d.out_blk;
               for (int bb = 0; bb < nb; ++bb)
@@ -367,8 +370,10 @@ struct HeadGradsB { float* dw[3]; float* db[3]; };
 template <int J>
 __global__ void __launch_bounds__(256) heads_dw_blocked_kernel(const uint8_t* __restrict__ X, int nb, int chunk0, int K, int64_t M,
                                                                const float* __restrict__ dpre, int col0, HeadGradsB G,
-                                                               int64_t rows_per_block) {
+                                                               int64_t rows_per_block, const int64_t* __restrict__ M_dev) {
   __shared__ float red[8][J][264];
+  if (M_dev) M = __ldg(M_dev);
+  if ((int64_t)blockIdx.x * rows_per_block >= M) return;
   const int lpr = K >> 3, rows = 256 / lpr;
   const int sub = threadIdx.x % lpr, rsub = threadIdx.x / lpr;
   const int64_t m_begin = (int64_t)blockIdx.x * rows_per_block;
@@ -439,8 +444,10 @@ __global__ void __launch_bounds__(256) heads_dw_blocked_kernel(const uint8_t* __
 // dcb[img, j] += sum_{rows of image img} G_HD0[row, 128 + j]   (j < 128): gradient of the per-image bias rows
 __global__ void __launch_bounds__(256) class_grad_blocked_kernel(const uint8_t* __restrict__ G, const int32_t* __restrict__ cls, int64_t M,
                                                                  int64_t n_images, float* __restrict__ dcb, int64_t rows_per_block,
-                                                                 int use_smem) {
+                                                                 int use_smem, const int64_t* __restrict__ M_dev) {
   extern __shared__ float tab[];
+  if (M_dev) M = __ldg(M_dev);
+  if ((int64_t)blockIdx.x * rows_per_block >= M) return;
   const int sub = threadIdx.x & 15, rsub = threadIdx.x >> 4;
   const int64_t m_begin = (int64_t)blockIdx.x * rows_per_block;
   const int64_t m_end = m_begin + rows_per_block < M ? m_begin + rows_per_block : M;
@@ -498,10 +505,10 @@ __global__ void emb_grad_fused_kernel(const float* __restrict__ dcb, const float
 
 template <int J>
 static int run_heads_dw_blocked(const uint8_t* X, int nb, int chunk0, int K, int64_t M, const float* dpre, int col0, const HeadGradsB& G,
-                                cudaStream_t s) {
+                                cudaStream_t s, const int64_t* M_dev) {
   int64_t rows = 1024;
   while (div_up(M, rows) > 4 * 148) rows *= 2;
-  heads_dw_blocked_kernel<J><<<div_up(M, rows), 256, 0, s>>>(X, nb, chunk0, K, M, dpre, col0, G, rows);
+  heads_dw_blocked_kernel<J><<<div_up(M, rows), 256, 0, s>>>(X, nb, chunk0, K, M, dpre, col0, G, rows, M_dev);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -529,7 +536,7 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   const bool want_x = a->g_x != nullptr;
 
   FusedBwdParams p{};
-  p.M = N; p.n_tiles = S.n_tiles; p.density_only = a->density_only;
+  p.M = N; p.n_tiles = S.n_tiles; p.M_dev = a->n_pts_dev; p.density_only = a->density_only;
   p.wblob = ext + F.bblob; p.consts = (const float*)(ext + F.consts);
   {
     static const int8_t halves[kBwdStages] = {1, 1, 1, 2, 2, 2, 2, 1, 2, 2, 2, 2, 2, 1};
@@ -593,7 +600,7 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
     GemmTNBlocked t;
     t.G = Gp; t.g_nb = g_nb; t.g_blk0 = g_blk0; t.mt_count = mt;
     t.X = Xp; t.x_nb = x_nb; t.x_blk0 = x_blk0; t.x_cnt = x_cnt; t.k_valid = k_valid;
-    t.n_tiles = S.n_tiles;
+    t.n_tiles = S.n_tiles; t.n_pts_dev = a->n_pts_dev;
     t.D[0] = d0; t.ldd[0] = ld0; t.db[0] = b0; t.D[1] = d1; t.ldd[1] = ld1; t.db[1] = b1;
     gemms[n_gemms++] = t;                                     // launched together at the end (one persistent kernel)
     return (int)EONERF_OK;
@@ -610,9 +617,9 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
     EO_TRY(dW(garr(8), 4, 0, 2, sarr(7), 4, 0, 4, kW, G->bott_w, kW, G->bott_b, G->bott_w + (int64_t)kHid * kW, kW, G->bott_b + kHid));
     {  // narrow heads
       HeadGradsB hg{{G->ts_w, G->tb_w, nullptr}, {G->ts_b, G->tb_b, nullptr}};
-      EO_TRY(run_heads_dw_blocked<2>(sarr(12), 2, 0, kHid, N, dpre, 4, hg, s));
+      EO_TRY(run_heads_dw_blocked<2>(sarr(12), 2, 0, kHid, N, dpre, 4, hg, s, a->n_pts_dev));
       HeadGradsB ha{{G->head1_w, G->head1_w + kHid, G->head1_w + 2 * kHid}, {G->head1_b, G->head1_b + 1, G->head1_b + 2}};
-      EO_TRY(run_heads_dw_blocked<3>(sarr(9), 4, 0, kHid, N, dpre, 1, ha, s));
+      EO_TRY(run_heads_dw_blocked<3>(sarr(9), 4, 0, kHid, N, dpre, 1, ha, s, a->n_pts_dev));
     }
     {  // transient embedding / W_t0[:,256:260] through the per-image bias rows
       float* dcb = (float*)(sc + C.dcb);
@@ -622,7 +629,7 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
       int64_t rows = 2048;
       while (div_up(N, rows) > 4 * 148) rows *= 2;
       class_grad_blocked_kernel<<<div_up(N, rows), 256, use_smem ? tab_bytes : 0, s>>>(garr(9), (const int32_t*)(st + S.cls), N, prm->n_images,
-                                                                                       dcb, rows, use_smem);
+                                                                                       dcb, rows, use_smem, a->n_pts_dev);
       EO_LAUNCH_CHECK();
       const int nthreads = (int)(prm->n_images * 4 > kHid * 4 ? prm->n_images * 4 : kHid * 4);
       emb_grad_fused_kernel<<<div_up(nthreads, 128), 128, 0, s>>>(dcb, prm->trans_w[0], prm->transient_emb, prm->n_images, G->transient_emb,
@@ -632,7 +639,7 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   }
   {  // sigma head
     HeadGradsB hs{{G->sigma_w, nullptr, nullptr}, {G->sigma_b, nullptr, nullptr}};
-    EO_TRY(run_heads_dw_blocked<1>(sarr(7), 4, 0, kW, N, dpre, 0, hs, s));
+    EO_TRY(run_heads_dw_blocked<1>(sarr(7), 4, 0, kW, N, dpre, 0, hs, s, a->n_pts_dev));
   }
   // trunk: layer i reads X = H_{i-1} (layer 5: [H4 | enc], layer 0: enc)
   for (int i = 7; i >= 1; --i) {

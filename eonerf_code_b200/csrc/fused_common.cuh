@@ -12,8 +12,8 @@ constexpr int kOffRing = 0;
 constexpr int kOffSlot = kRingStages * kBlkBytes;          // 49152
 constexpr int kOffConst = kOffSlot + 2 * kSlotBytes;       // 212992
 constexpr int kConstBytes = 15872;
-constexpr int kOffPart = kOffConst + kConstBytes;          // [128][2] floats
-constexpr int kOffBar = kOffPart + 1024;
+constexpr int kOffPart = kOffConst + kConstBytes;          // [2 slots][128][2] floats
+constexpr int kOffBar = kOffPart + 2048;
 constexpr int kSmemFused = kOffBar + 128 + 1024;           // + alignment slack
 constexpr int kFusedThreads = 320;
 constexpr int kEpiThreads = 256;
@@ -28,6 +28,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// {hi, lo} -> packed bf16 pair with ReLU folded into the conversion (one F2FP instead of 2 FMNMX + F2FP)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ float bf_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
 
@@ -37,7 +43,8 @@ __device__ __forceinline__ uint32_t blk_off(int row, int chunk) { return (uint32
 // explicit shared-space accesses (the 1024-byte alignment arithmetic on the dynamic shared-memory base hides the address
 // space from the compiler, which would otherwise emit generic LD/ST)
 __device__ __forceinline__ void lds_f4(uint32_t a, float& x, float& y, float& z, float& w) {
-  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a));
+  // volatile: keeps the load where it is written (hoisted above the accumulator wait, 128 bias values would spill)
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a) : "memory");
 }
 __device__ __forceinline__ void lds_f2(uint32_t a, float& x, float& y) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a) : "memory");

@@ -523,12 +523,13 @@ struct TNBGemm {
   int32_t g_nb, g_blk0, mt_count, x_nb, x_blk0, x_cnt;
   int32_t n_valid[2]; int32_t k_valid;
   float* D[2]; int64_t ldd[2]; float* db[2];
-  int64_t chunks;          // 64-sample chunks
-  int64_t cost0;           // cumulative cost (boxes) before this GEMM
+  int64_t per0;            // boxes per chunk summed over the GEMMs before this one (cost0 = chunks * per0)
 };
 struct TNBParams {
   int32_t n; int32_t dbg_skip_tail;
-  int64_t total_cost;
+  int64_t chunks;          // 64-sample chunks of every GEMM of the group (they share the sample axis)
+  int64_t per_total;       // boxes per chunk summed over the group (total cost = chunks * per_total)
+  const int64_t* n_pts_dev;   // live sample count on the device: chunks = 2 * ceil(*n_pts_dev / 128)
   TNBGemm g[kTNGroupMax];
 };
 
@@ -537,14 +538,15 @@ constexpr int kTNBStageBytes = 8 * kBoxBytes;
 constexpr int kSmemTNB = kTNBStages * kTNBStageBytes + 1024;
 
 // chunk range [c0, c1) of GEMM gi owned by the CTA whose cost interval is [lo, hi)
-__device__ __forceinline__ void tnb_range(const TNBGemm& g, int64_t lo, int64_t hi, int64_t& c0, int64_t& c1) {
+__device__ __forceinline__ void tnb_range(const TNBGemm& g, int64_t chunks, int64_t lo, int64_t hi, int64_t& c0, int64_t& c1) {
   const int64_t per = 2 * g.mt_count + g.x_cnt;                   // boxes per chunk
-  const int64_t end = g.cost0 + g.chunks * per;
-  const int64_t a = lo > g.cost0 ? lo : g.cost0, b = hi < end ? hi : end;
+  const int64_t cost0 = chunks * g.per0;
+  const int64_t end = cost0 + chunks * per;
+  const int64_t a = lo > cost0 ? lo : cost0, b = hi < end ? hi : end;
   if (b <= a) { c0 = c1 = 0; return; }
-  c0 = (a - g.cost0 + per - 1) / per;                             // a chunk belongs to the CTA that owns its first box
-  c1 = (b - g.cost0 + per - 1) / per;
-  if (c1 > g.chunks) c1 = g.chunks;
+  c0 = (a - cost0 + per - 1) / per;                               // a chunk belongs to the CTA that owns its first box
+  c1 = (b - cost0 + per - 1) / per;
+  if (c1 > chunks) c1 = chunks;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __grid_constant__ TNBParams p) {
@@ -565,7 +567,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int64_t lo = p.total_cost * blockIdx.x / gridDim.x, hi = p.total_cost * (blockIdx.x + 1) / gridDim.x;
+  const int64_t chunks = p.n_pts_dev ? 2 * ((__ldg(p.n_pts_dev) + kTileM - 1) / kTileM) : p.chunks;
+  const int64_t total_cost = chunks * p.per_total;
+  const int64_t lo = total_cost * blockIdx.x / gridDim.x, hi = total_cost * (blockIdx.x + 1) / gridDim.x;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -573,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
       for (int gi = 0; gi < p.n; ++gi) {
         const TNBGemm& g = p.g[gi];
         int64_t c0, c1;
-        tnb_range(g, lo, hi, c0, c1);
+        tnb_range(g, chunks, lo, hi, c0, c1);
         const int a_boxes = g.mt_count * 2;
         for (int64_t c = c0; c < c1; ++c) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -597,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
     for (int gi = 0; gi < p.n; ++gi) {
       const TNBGemm& g = p.g[gi];
       int64_t c0, c1;
-      tnb_range(g, lo, hi, c0, c1);
+      tnb_range(g, chunks, lo, hi, c0, c1);
       if (c1 <= c0) continue;
       const uint32_t idesc = instr_desc(kBlockM, g.x_cnt * 64, 1, 1);
       const int a_boxes = g.mt_count * 2;
@@ -636,7 +640,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
     for (int gi = 0; gi < p.n; ++gi) {
       const TNBGemm& g = p.g[gi];
       int64_t c0, c1;
-      tnb_range(g, lo, hi, c0, c1);
+      tnb_range(g, chunks, lo, hi, c0, c1);
       if (c1 <= c0) continue;
       const int a_boxes = g.mt_count * 2;
       const int block_k = g.x_cnt * 64;
@@ -716,7 +720,8 @@ int gemm_tn_blocked_group(const GemmTNBlocked* list, int n, cudaStream_t s) {
   for (int i0 = 0; i0 < n; i0 += kTNGroupMax) {
     TNBParams p{};
     double flops = 0, bytes = 0;
-    int64_t cost = 0, chunks_total = 0;
+    int64_t per = 0, chunks_total = 0, n_tiles = -1;
+    const int64_t* n_dev = nullptr;
     for (int i = i0; i < n && i < i0 + kTNGroupMax; ++i) {
       const GemmTNBlocked& g = list[i];
       if (g.n_tiles <= 0) continue;
@@ -725,16 +730,19 @@ int gemm_tn_blocked_group(const GemmTNBlocked* list, int n, cudaStream_t s) {
       q.G = g.G; q.X = g.X; q.g_nb = g.g_nb; q.g_blk0 = g.g_blk0; q.mt_count = g.mt_count;
       q.x_nb = g.x_nb; q.x_blk0 = g.x_blk0; q.x_cnt = g.x_cnt; q.k_valid = g.k_valid;
       for (int j = 0; j < 2; ++j) { q.n_valid[j] = g.n_valid[j]; q.D[j] = g.D[j]; q.ldd[j] = g.ldd[j]; q.db[j] = (dbg & 2) ? nullptr : g.db[j]; }
-      q.chunks = g.n_tiles * 2;
-      q.cost0 = cost;
-      cost += q.chunks * (2 * g.mt_count + g.x_cnt);
-      chunks_total += q.chunks;
+      EO_REQUIRE(n_tiles < 0 || (n_tiles == g.n_tiles && n_dev == g.n_pts_dev), "gemm_tn_blocked: the GEMMs of a group share the sample axis");
+      n_tiles = g.n_tiles; n_dev = g.n_pts_dev;
+      q.per0 = per;
+      per += 2 * g.mt_count + g.x_cnt;
+      chunks_total += g.n_tiles * 2;
       const double M = (double)g.n_tiles * kTileM;
       flops += 2.0 * M * g.mt_count * 128 * g.k_valid;
       bytes += 2.0 * M * (g.mt_count * 128 + g.x_cnt * 64);
     }
     if (p.n == 0) continue;
-    p.total_cost = cost;
+    p.chunks = n_tiles * 2;
+    p.per_total = per;
+    p.n_pts_dev = n_dev;
     p.dbg_skip_tail = dbg & 1;
     int64_t grid = sm_count();
     if (grid > chunks_total) grid = chunks_total;

@@ -61,6 +61,7 @@ __device__ __forceinline__ RayGeom load_ray(const EonerfSampleArgs& a, int64_t r
 }
 
 __global__ void __launch_bounds__(256) sample_count_kernel(EonerfSampleArgs a) {
+  if (a.run_if && *a.run_if == 0) return;
   int lane = threadIdx.x & 31;
   int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ray >= a.n_rays) return;
@@ -83,6 +84,8 @@ __global__ void __launch_bounds__(1024) sample_scan_kernel(EonerfSampleArgs a) {
   __shared__ long long carry_s;
   __shared__ int empty_s;
   int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool redraw = a.run_if != nullptr;                   // conditional second draw: keeps pts_per_ray and stats[1]
+  if (redraw && *a.run_if == 0) return;
   if (tid == 0) { carry_s = 0; empty_s = 0; a.ray_offsets[0] = 0; }
   __syncthreads();
   int n_empty = 0;
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(1024) sample_scan_kernel(EonerfSampleArgs a) {
     int64_t i = base + tid;
     long long c = (i < a.n_rays) ? a.ray_offsets[i + 1] : 0;
     if (i < a.n_rays) {
-      a.pts_per_ray[i] = (float)c;
+      if (!redraw) a.pts_per_ray[i] = (float)c;
       n_empty += (c == 0);
     }
     long long v = c;
@@ -122,11 +125,12 @@ __global__ void __launch_bounds__(1024) sample_scan_kernel(EonerfSampleArgs a) {
   __syncthreads();
   if (tid == 0) {
     a.stats[0] = carry_s;
-    a.stats[1] = empty_s;
+    if (!redraw) a.stats[1] = empty_s;
   }
 }
 
 __global__ void __launch_bounds__(256) sample_scatter_kernel(EonerfSampleArgs a) {
+  if (a.run_if && *a.run_if == 0) return;
   int lane = threadIdx.x & 31;
   int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ray >= a.n_rays) return;
@@ -178,7 +182,7 @@ extern "C" int eonerf_sample_compact(const EonerfSampleArgs* a, eonerf_stream_t 
   EO_REQUIRE(a && a->n_samples >= 2 && a->n_rays >= 0, "sample_compact: need n_samples >= 2 and n_rays >= 0");
   EO_REQUIRE(a->ray_offsets && a->stats, "sample_compact: null ray_offsets / stats");
   EO_REQUIRE(a->n_rays == 0 || (a->origins && a->viewdirs && a->u && a->z_steps), "sample_compact: null input");
-  EO_REQUIRE(a->n_rays == 0 || (a->ray_indices && a->t_starts && a->t_ends && a->pts_per_ray), "sample_compact: null output");
+  EO_REQUIRE(a->n_rays == 0 || (a->ray_indices && a->t_starts && a->t_ends && (a->pts_per_ray || a->run_if)), "sample_compact: null output");
   cudaStream_t s = as_stream(stream);
   if (a->n_rays > 0) {
     int blocks = div_up(a->n_rays, 8);

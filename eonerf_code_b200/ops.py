@@ -59,10 +59,14 @@ def z_steps_for(n, device):
 # ------------------------------------------------------------------------------------------------
 # sampling
 # ------------------------------------------------------------------------------------------------
-def sample_compact(origins, viewdirs, near, u, z_steps=None):
+def sample_compact(origins, viewdirs, near, u, z_steps=None, redraw_of=None):
     """Stratified samples + cube mask + compaction (sat_rendering.py:56-84, :10-16).
     Returns worst-case-sized buffers (ray_indices, t_starts, t_ends), pts_per_ray[B] fp32, ray_offsets[B+1], stats[2]
-    (stats = [P, number of empty rays], still on the device)."""
+    (stats = [P, number of empty rays], still on the device).
+    `redraw_of` = the tuple returned by a first call: the sync-free form of the reference's "some ray kept no sample ->
+    draw again" (sat_rendering.py:259-262).  The kernels then run only if that first draw left an empty ray (decided on
+    the device) and overwrite its packed arrays, offsets and P in place; pts_per_ray and the empty-ray count keep the
+    first draw's values, as in the reference."""
     _need_cuda(origins, viewdirs, u)
     B, n = u.shape
     dev = origins.device
@@ -72,12 +76,15 @@ def sample_compact(origins, viewdirs, near, u, z_steps=None):
     if z_steps is None:
         z_steps = z_steps_for(n, dev)
     cap = B * (n - 1)
-    ri = torch.empty(cap, dtype=torch.int64, device=dev)
-    ts = torch.empty(cap, dtype=torch.float32, device=dev)
-    te = torch.empty(cap, dtype=torch.float32, device=dev)
-    ppr = torch.empty(B, dtype=torch.float32, device=dev)
-    offs = torch.empty(B + 1, dtype=torch.int64, device=dev)
-    stats = torch.empty(2, dtype=torch.int64, device=dev)
+    if redraw_of is not None:
+        ri, ts, te, ppr, offs, stats = redraw_of
+    else:
+        ri = torch.empty(cap, dtype=torch.int64, device=dev)
+        ts = torch.empty(cap, dtype=torch.float32, device=dev)
+        te = torch.empty(cap, dtype=torch.float32, device=dev)
+        ppr = torch.empty(B, dtype=torch.float32, device=dev)
+        offs = torch.empty(B + 1, dtype=torch.int64, device=dev)
+        stats = torch.empty(2, dtype=torch.int64, device=dev)
     a = K.SampleArgs()
     a.origins, a.origins_stride, a.viewdirs, a.viewdirs_stride = _p(o), os_, _p(d), ds_
     if near is not None:
@@ -86,6 +93,8 @@ def sample_compact(origins, viewdirs, near, u, z_steps=None):
     a.u, a.z_steps, a.n_rays, a.n_samples = _p(u), _p(z_steps), B, n
     a.ray_indices, a.t_starts, a.t_ends = _p(ri), _p(ts), _p(te)
     a.pts_per_ray, a.ray_offsets, a.stats = _p(ppr), _p(offs), _p(stats)
+    if redraw_of is not None:
+        a.run_if = stats.data_ptr() + 8
     K.call("sample_compact", a, _stream())
     return ri, ts, te, ppr, offs, stats
 
@@ -213,6 +222,8 @@ class FieldEngine:
         self._prepared = None
         self._prepared_key = None
         self.grad_sync = None        # optional callable(flat_grad) run at the end of backward (data parallel all-reduce)
+        self.grad_sink = None        # optional {name: fp32 tensor}: backward accumulates straight into these (see use_grad_sink)
+        self._sink_struct = None
 
     # --- parameters -------------------------------------------------------------------------
     def tensors(self):
@@ -226,6 +237,12 @@ class FieldEngine:
     def params_struct(self):
         self._check()
         return _fill_field_params(K.FieldParams(), lambda n: self.named[n].data_ptr(), self.field, self.n_images)
+
+    def refresh_prepared(self):
+        """Rebuild the operand-layout weights unconditionally.  A captured step starts with this: graph replays change the
+        parameters without bumping their Python-side versions."""
+        self._prepared_key = None
+        return self.prepared()
 
     def prepared(self):
         """Operand-layout weights, rebuilt when any parameter changed (optimizer steps bump ._version)."""
@@ -243,6 +260,26 @@ class FieldEngine:
         return self._prepared
 
     # --- gradients --------------------------------------------------------------------------
+    def use_grad_sink(self, sink):
+        """Training fast path: every backward kernel accumulates (atomic adds) directly into the caller's gradient tensors
+        `sink[name]` (same shapes as the parameters, typically the parameters' .grad views of one flat buffer) and the
+        autograd functions return no parameter gradients, instead of one fresh flat buffer per pass that autograd then
+        adds tensor by tensor (~90 tiny kernels per step).  The caller zeroes the sink before the step.  None: off."""
+        if sink is not None:
+            for k, t in self.named.items():
+                g = sink[k]
+                if not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.shape == t.shape):
+                    raise RuntimeError(f"gradient sink for {k} must be a contiguous fp32 CUDA tensor of shape {tuple(t.shape)}")
+            sink = OrderedDict((k, sink[k]) for k in self.named)
+            self._sink_struct = _fill_field_params(K.FieldParams(), lambda n: sink[n].data_ptr(), self.field, self.n_images)
+        self.grad_sink = sink
+
+    def grads_for_backward(self):
+        """(flat buffer or None, {name: tensor}, K.FieldParams, direct).  direct=True: the sink is in use."""
+        if self.grad_sink is not None:
+            return None, self.grad_sink, self._sink_struct, True
+        return self.new_grads() + (False,)
+
     def new_grads(self):
         """(flat fp32 zero buffer, {name: view}, K.FieldParams of the views)."""
         dev = next(iter(self.named.values())).device
@@ -262,9 +299,12 @@ class FieldEngine:
     def scratch_bytes(self, n):
         return K.lib().eonerf_field_scratch_bytes(self.field, self.precision, n, self.n_images)
 
-    def fwd(self, n, density_only, x=None, rays=None, img_idx=None, cond_dirs=None, want_z=False, keep=True):
+    def fwd(self, n, density_only, x=None, rays=None, img_idx=None, cond_dirs=None, want_z=False, keep=True, n_dev=None):
         """rays = (origins, viewdirs, ray_indices, t_starts, t_ends).  Returns dict of outputs + stash.
-        keep=False (inference): the fused mode keeps no activations at all; the layered modes still need the buffer."""
+        keep=False (inference): the fused mode keeps no activations at all; the layered modes still need the buffer.
+        n_dev: int64[1] device tensor holding the live sample count (n is then the capacity): no host read of P."""
+        if n_dev is not None and self.precision != K.PREC_BF16_FUSED:
+            raise RuntimeError("device-side sample counts need precision='bf16_fused'")
         dev = next(iter(self.named.values())).device
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         no_stash = not keep and self.precision == K.PREC_BF16_FUSED
@@ -300,6 +340,7 @@ class FieldEngine:
             a.cond_dirs, a.cond_dirs_stride = _p(cd), cs_
             keep.append(cd)
         a.density_only, a.stash, a.sigma = int(density_only), _p(out["stash"]), _p(out["sigma"])
+        a.n_pts_dev = _p(n_dev)
         if not density_only:
             out["rgb"] = f32(n, 3)
             a.rgb = _p(out["rgb"])
@@ -309,7 +350,8 @@ class FieldEngine:
         K.call("field_fwd", a, _stream())
         return out
 
-    def bwd(self, n, density_only, fwd_out, g_sigma=None, g_rgb=None, g_ts=None, g_tb=None, grads_struct=None, want_gx=False):
+    def bwd(self, n, density_only, fwd_out, g_sigma=None, g_rgb=None, g_ts=None, g_tb=None, grads_struct=None, want_gx=False,
+            n_dev=None):
         dev = fwd_out["sigma"].device
         scratch = torch.empty(self.scratch_bytes(n), dtype=torch.uint8, device=dev)
         gx = torch.empty(n, 3, dtype=torch.float32, device=dev) if want_gx else None
@@ -323,6 +365,7 @@ class FieldEngine:
         if grads_struct is not None:
             a.grads = C.pointer(grads_struct)
         a.g_x = _p(gx)
+        a.n_pts_dev = _p(n_dev)
         K.call("field_bwd", a, _stream())
         return gx
 
@@ -350,7 +393,9 @@ class FieldEngine:
         K.call("ambient_bwd", a, _stream())
 
 
-def _grads_tuple(engine, views, params):
+def _grads_tuple(engine, views, params, direct=False):
+    if direct:                      # already accumulated into the sink
+        return (None,) * len(params)
     return tuple(views[k] if p.requires_grad else None for (k, _), p in zip(engine.named.items(), params))
 
 
@@ -376,12 +421,12 @@ class _FieldFn(torch.autograd.Function):
         e = ctx.engine
         c = lambda g: None if g is None else _f32(g).contiguous()
         gs = [c(g) for g in gs] + [None] * 4
-        flat, views, gstruct = e.new_grads()
+        flat, views, gstruct, direct = e.grads_for_backward()
         gx = e.bwd(ctx.n, ctx.density_only, ctx.out, g_sigma=gs[0], g_rgb=gs[1], g_ts=gs[2], g_tb=gs[3],
                    grads_struct=gstruct, want_gx=ctx.x_needs_grad)
-        if e.grad_sync is not None:
+        if e.grad_sync is not None and not direct:
             e.grad_sync(flat)
-        return (None, None, gx, None, None) + _grads_tuple(e, views, ctx.params)
+        return (None, None, gx, None, None) + _grads_tuple(e, views, ctx.params, direct)
 
 
 class _AmbientFn(torch.autograd.Function):
@@ -395,11 +440,11 @@ class _AmbientFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         e = ctx.engine
-        flat, views, _ = e.new_grads()
+        flat, views, _, direct = e.grads_for_backward()
         e.ambient_bwd(ctx.amb, ctx.stash, _f32(g).contiguous(), views)
-        if e.grad_sync is not None:
+        if e.grad_sync is not None and not direct:
             e.grad_sync(flat)
-        return (None, None) + _grads_tuple(e, views, ctx.params)
+        return (None, None) + _grads_tuple(e, views, ctx.params, direct)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -416,7 +461,8 @@ class _CameraPassFn(torch.autograd.Function):
     Output comp[B,12]: 0:3 albedo, 3 depth, 4 beta(+0.05), 5 transient_s, 6:9 ambient (not yet x0.2), 9 sum(w)."""
 
     @staticmethod
-    def forward(ctx, engine, only_depth, origins, viewdirs, sundirs, img_idx, ri, ts, te, offs, *params):
+    def forward(ctx, engine, only_depth, origins, viewdirs, sundirs, img_idx, ri, ts, te, offs, n_dev, *params):
+        """n_dev: None, or int64[1] on the device = live sample count P (ri / ts / te then have their full capacity)."""
         _need_cuda(origins, viewdirs, ri, ts, te)
         for t in (ts, te):
             if not (t.dtype == torch.float32 and t.is_contiguous()):
@@ -424,7 +470,8 @@ class _CameraPassFn(torch.autograd.Function):
         B, P = origins.shape[0], ts.numel()
         ri = ri.contiguous()
         f = engine.fwd(P, density_only=only_depth, rays=(origins, viewdirs, ri, ts, te),
-                       img_idx=None if only_depth else _img_idx_2d(img_idx), want_z=True, keep=any(ctx.needs_input_grad))
+                       img_idx=None if only_depth else _img_idx_2d(img_idx), want_z=True, keep=any(ctx.needs_input_grad),
+                       n_dev=n_dev)
         set_last_t_end(te, offs)                                    # after z / positions were taken
         amb = amb_stash = None
         if not only_depth:
@@ -434,16 +481,16 @@ class _CameraPassFn(torch.autograd.Function):
                                _p(f.get("transient_beta")), _p(amb), _p(offs), B, P, BETA_MIN, _p(comp))
         K.call("composite_fwd", a, _stream())
         ctx.engine, ctx.only_depth, ctx.params = engine, only_depth, params
-        ctx.keep = (B, P, ts, te, offs, f, amb, amb_stash)
+        ctx.keep = (B, P, ts, te, offs, f, amb, amb_stash, n_dev)
         return comp
 
     @staticmethod
     def backward(ctx, g_comp):
         e = ctx.engine
-        B, P, ts, te, offs, f, amb, amb_stash = ctx.keep
+        B, P, ts, te, offs, f, amb, amb_stash, n_dev = ctx.keep
         dev = g_comp.device
         g_comp = _f32(g_comp).contiguous()
-        flat, views, gstruct = e.new_grads()
+        flat, views, gstruct, direct = e.grads_for_backward()
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         g_sigma = new(P)
         g_alb = g_ts = g_tb = g_amb = None
@@ -455,9 +502,11 @@ class _CameraPassFn(torch.autograd.Function):
         K.call("composite_bwd", a, _stream())
         if not ctx.only_depth:
             e.ambient_bwd(amb, amb_stash, g_amb, views)
-        e.bwd(P, ctx.only_depth, f, g_sigma=g_sigma, g_rgb=g_alb, g_ts=g_ts, g_tb=g_tb, grads_struct=gstruct)
+        e.bwd(P, ctx.only_depth, f, g_sigma=g_sigma, g_rgb=g_alb, g_ts=g_ts, g_tb=g_tb, grads_struct=gstruct, n_dev=n_dev)
         ctx.keep = None
-        return (None,) * 10 + _grads_tuple(e, views, ctx.params)
+        if e.grad_sync is not None and not direct:
+            e.grad_sync(flat)
+        return (None,) * 11 + _grads_tuple(e, views, ctx.params, direct)
 
 
 class _SunPassFn(torch.autograd.Function):
@@ -465,7 +514,8 @@ class _SunPassFn(torch.autograd.Function):
     query, transmittance in front of the last kept sample.  Differentiable in `depth` and the parameters."""
 
     @staticmethod
-    def forward(ctx, engine, origins, viewdirs, sundirs, depth, n_samples, u_sun, z_steps, info, *params):
+    def forward(ctx, engine, origins, viewdirs, sundirs, depth, n_samples, u_sun, z_steps, info, static, *params):
+        """static=True: no host read of the sun-sample count Q (buffers keep their capacity, kernels read Q on the device)."""
         _need_cuda(origins, viewdirs, sundirs, depth)
         B, dev = origins.shape[0], origins.device
         oo, os_ = _rows(origins)
@@ -478,40 +528,45 @@ class _SunPassFn(torch.autograd.Function):
         if u_sun is None:
             u_sun = torch.rand(B, n_samples, dtype=torch.float32, device=dev)      # sat_rendering.py:52 via :93
         ri2, ts2, te2, sc_ppr, offs2, stats2 = sample_compact(sun[:, 0:3], sun[:, 3:6], None, u_sun, z_steps)
-        Q = int(stats2[0])                                          # the one host sync of the sun pass
-        f2 = engine.fwd(Q, density_only=True, rays=(sun[:, 0:3], sun[:, 3:6], ri2, ts2, te2), keep=any(ctx.needs_input_grad))
+        n_dev = stats2[0:1] if static else None
+        Q = ts2.numel() if static else int(stats2[0])               # eager: the one host sync of the sun pass
+        f2 = engine.fwd(Q, density_only=True, rays=(sun[:, 0:3], sun[:, 3:6], ri2, ts2, te2), keep=any(ctx.needs_input_grad),
+                        n_dev=n_dev)
         geo = torch.empty(B, 1, dtype=torch.float32, device=dev)
         a = K.ShadowFwdArgs(_p(ts2), _p(te2), _p(f2["sigma"]), _p(offs2), B, Q, _p(geo))
         K.call("shadow_fwd", a, _stream())
-        info.update(sc_pts_per_ray=sc_ppr, n_sun_samples=Q, ray_indices=ri2[:Q], t_starts=ts2[:Q], t_ends=te2[:Q],
-                    sigma=f2["sigma"], sun_rays=sun)
+        info.update(sc_pts_per_ray=sc_ppr, n_sun_samples=stats2[0] if static else Q, ray_indices=ri2[:Q], t_starts=ts2[:Q],
+                    t_ends=te2[:Q], sigma=f2["sigma"], sun_rays=sun)
         ctx.engine, ctx.params = engine, params
-        ctx.keep = (B, Q, ts2, te2, offs2, f2, geo, dd, ds_)
+        ctx.keep = (B, Q, ts2, te2, offs2, f2, geo, dd, ds_, n_dev)
         return geo
 
     @staticmethod
     def backward(ctx, g_geo):
         e = ctx.engine
-        B, Q, ts2, te2, offs2, f2, geo, dd, ds_ = ctx.keep
+        B, Q, ts2, te2, offs2, f2, geo, dd, ds_, n_dev = ctx.keep
         dev = g_geo.device
         g_geo = _f32(g_geo).contiguous()
-        flat, views, gstruct = e.new_grads()
+        flat, views, gstruct, direct = e.grads_for_backward()
         g_sig2 = torch.empty(Q, dtype=torch.float32, device=dev)
         a = K.ShadowBwdArgs(_p(ts2), _p(te2), _p(offs2), B, Q, _p(geo), _p(g_geo), _p(g_sig2))
         K.call("shadow_bwd", a, _stream())
-        gx = e.bwd(Q, True, f2, g_sigma=g_sig2, grads_struct=gstruct, want_gx=True)
+        gx = e.bwd(Q, True, f2, g_sigma=g_sig2, grads_struct=gstruct, want_gx=True, n_dev=n_dev)
         g_depth = torch.zeros(B, 1, dtype=torch.float32, device=dev)
         a = K.SunOriginBwdArgs(_p(gx), _p(offs2), B, Q, _p(dd), ds_, _p(g_depth), 1)     # chain rule through :90
         K.call("sun_origin_bwd", a, _stream())
         ctx.keep = None
-        return (None, None, None, None, g_depth, None, None, None, None) + _grads_tuple(e, views, ctx.params)
+        if e.grad_sync is not None and not direct:
+            e.grad_sync(flat)
+        return (None, None, None, None, g_depth, None, None, None, None, None) + _grads_tuple(e, views, ctx.params, direct)
 
 
 class _EpilogueFn(torch.autograd.Function):
     """Irradiance model + radiometric normalisation + 21-column packing (sat_rendering.py:265,269-276,288-312)."""
 
     @staticmethod
-    def forward(ctx, comp, geo, ppr, sc_ppr, img_idx, eval_mode, rad, n_images):
+    def forward(ctx, comp, geo, ppr, sc_ppr, img_idx, eval_mode, rad, n_images, rad_sink=None):
+        """rad_sink: optional fp32 [n_img,9] tensor the radiometric-embedding gradient is accumulated into directly."""
         _need_cuda(comp)
         B = comp.shape[0]
         comp = _f32(comp).contiguous()
@@ -521,18 +576,18 @@ class _EpilogueFn(torch.autograd.Function):
         a = K.EpilogueFwdArgs(_p(comp), _p(geo), _p(ppr), _p(sc_ppr), _p(ii), ii.stride(0), int(bool(eval_mode)), _p(rad),
                               n_images, B, _p(out))
         K.call("epilogue_fwd", a, _stream())
-        ctx.keep = (comp, geo, ii, int(bool(eval_mode)), rad, n_images)
+        ctx.keep = (comp, geo, ii, int(bool(eval_mode)), rad, n_images, rad_sink)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        comp, geo, ii, eval_mode, rad, n_images = ctx.keep
+        comp, geo, ii, eval_mode, rad, n_images, rad_sink = ctx.keep
         B, dev = comp.shape[0], comp.device
         g_out = _f32(g_out).contiguous()
         g_comp = torch.empty(B, K.COMP_COLS, dtype=torch.float32, device=dev)
         g_geo = None if geo is None else torch.empty(B, 1, dtype=torch.float32, device=dev)
-        g_rad = None if rad is None else torch.zeros_like(rad)
+        g_rad = None if rad is None else (rad_sink if rad_sink is not None else torch.zeros_like(rad))
         a = K.EpilogueBwdArgs(_p(comp), _p(geo), _p(ii), ii.stride(0), eval_mode, _p(rad), n_images, B, _p(g_out),
                               _p(g_comp), _p(g_geo), _p(g_rad))
         K.call("epilogue_bwd", a, _stream())
-        return g_comp, g_geo, None, None, None, None, g_rad, None
+        return g_comp, g_geo, None, None, None, None, (None if rad_sink is not None else g_rad), None, None

@@ -64,7 +64,7 @@ class EONerfMLP(nn.Module, _EngineMixin):
         n_rays = chunk_rays.origins.shape[0]
         offs = ops.pack_info(ray_indices, n_rays)
         return ops._CameraPassFn.apply(e, only_depth, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs,
-                                       chunk_rays.img_idx, ray_indices, t_starts, t_ends, offs, *e.tensors())
+                                       chunk_rays.img_idx, ray_indices, t_starts, t_ends, offs, None, *e.tensors())
 
     def render_depth(self, chunk_rays, t_starts, t_ends, ray_indices):
         return self._camera_pass(chunk_rays, t_starts, t_ends, ray_indices, True)[:, 3:4]

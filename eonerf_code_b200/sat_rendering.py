@@ -53,7 +53,7 @@ def compute_geometric_shadows(chunk_rays, depth, radiance_field, occupancy_grid,
     n = n_samples_from_step(sampling_args["render_step_size"])
     info = {} if info is None else info
     geo = ops._SunPassFn.apply(e, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs, depth, n, u, z_steps, info,
-                               *e.tensors())
+                               False, *e.tensors())
     return geo, info["sc_pts_per_ray"]
 
 
@@ -77,9 +77,14 @@ def render_image(
     eval: bool = False,
     uniforms=None,
     z_steps=None,
+    static=False,
 ):
     """sat_rendering.py:176-335 -> (dict of 12 [..., C] tensors (or {"depth"}), n_rendering_samples).
-    `uniforms`: optional list with one dict per chunk {u_cam, u_sun, u_cam2} replacing the device RNG."""
+    `uniforms`: optional list with one dict per chunk {u_cam, u_sun, u_cam2} replacing the device RNG.
+    `static=True` (fused precision only): the sync-free form used under CUDA-graph capture.  Sample counts never reach
+    the host: packed arrays keep their B*(n-1) capacity and the kernels read P / Q on the device, the reference's
+    "some ray kept no sample -> draw again" branch becomes a device-side condition (its uniforms are always drawn), and
+    n_rendering_samples comes back as a 0-d int64 device tensor."""
     rays_shape = rays.origins.shape
     if len(rays_shape) == 3:
         num_rays = rays_shape[0] * rays_shape[1]
@@ -93,13 +98,23 @@ def render_image(
     for ci, i in enumerate(range(0, num_rays, chunk)):
         chunk_rays = namedtuple_map(lambda r: r[i:i + chunk], rays)
         us = uniforms[ci] if uniforms is not None else {}
-        ri, ts, te, ppr, offs, n_empty = _sample(chunk_rays.origins, chunk_rays.viewdirs, n, chunk_rays.t_near,
-                                                 us.get("u_cam"), z_steps)
-        if n_empty:                                         # :260-262 re-draw with near=None
-            ri, ts, te, _, offs, _ = _sample(chunk_rays.origins, chunk_rays.viewdirs, n, None, us.get("u_cam2"), z_steps)
-        n_rendering_samples += ts.numel()
+        n_dev = None
+        if static:
+            B_c, dev = chunk_rays.origins.shape[0], chunk_rays.origins.device
+            draw = lambda key: us[key] if us.get(key) is not None else torch.rand(B_c, n, dtype=torch.float32, device=dev)
+            first = ops.sample_compact(chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.t_near, draw("u_cam"), z_steps)
+            ri, ts, te, ppr, offs, stats = ops.sample_compact(chunk_rays.origins, chunk_rays.viewdirs, None, draw("u_cam2"),
+                                                              z_steps, redraw_of=first)     # :260-262, decided on the device
+            n_dev = stats[0:1]
+            n_rendering_samples = n_rendering_samples + stats[0]
+        else:
+            ri, ts, te, ppr, offs, n_empty = _sample(chunk_rays.origins, chunk_rays.viewdirs, n, chunk_rays.t_near,
+                                                     us.get("u_cam"), z_steps)
+            if n_empty:                                     # :260-262 re-draw with near=None
+                ri, ts, te, _, offs, _ = _sample(chunk_rays.origins, chunk_rays.viewdirs, n, None, us.get("u_cam2"), z_steps)
+            n_rendering_samples += ts.numel()
         comp = ops._CameraPassFn.apply(e, only_depth, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs,
-                                       chunk_rays.img_idx, ri, ts, te, offs, *e.tensors())
+                                       chunk_rays.img_idx, ri, ts, te, offs, n_dev, *e.tensors())
         if only_depth:                                      # :227-249
             outs.append(comp[:, 3:4])
             continue
@@ -107,10 +122,11 @@ def render_image(
         if epoch_idx >= 2:                                  # :269-276
             info = {}
             geo = ops._SunPassFn.apply(e, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs, comp[:, 3:4], n,
-                                       us.get("u_sun"), z_steps, info, *e.tensors())
+                                       us.get("u_sun"), z_steps, info, static, *e.tensors())
             sc_ppr = info["sc_pts_per_ray"]
         rad = radiance_field.radiometricT_enc.weight if radiance_field.radiometric_normalization else None
-        outs.append(ops._EpilogueFn.apply(comp, geo, ppr, sc_ppr, chunk_rays.img_idx, eval, rad, e.n_images))
+        rad_sink = e.grad_sink.get("radiometricT_enc.weight") if (rad is not None and e.grad_sink is not None) else None
+        outs.append(ops._EpilogueFn.apply(comp, geo, ppr, sc_ppr, chunk_rays.img_idx, eval, rad, e.n_images, rad_sink))
     out = torch.cat(outs, dim=0) if len(outs) != 1 else outs[0]
     if only_depth:
         return {"depth": out.view((*rays_shape[:-1], -1))}, n_rendering_samples

@@ -1,38 +1,120 @@
 """One EO-NeRF training step with the reference's semantics (/root/reference/train_eonerf.py:99-161): render_image on a
 batch of rays -> MSE (epoch < 2) or uncertainty-aware loss -> backward -> Adam(lr=5e-4).  GradScaler(1) in the reference
 is a no-op scale (train_eonerf.py:58,158-160) and is not reproduced.  Data parallel: gradients are averaged over ranks
-(equal shards, batch-mean losses => identical to the single-GPU gradient of the global batch)."""
+(equal shards, batch-mean losses => identical to the single-GPU gradient of the global batch).
+
+Two ways to run the same step:
+
+* eager (`graph=False`): the reference's control flow — the host reads the sample counts P and Q (two syncs per step,
+  the reference has more) and returns n_rendering_samples as an int.
+* CUDA graph (`graph=True`, fused precision): the whole step is sync-free (`render_image(static=True)`: sample counts
+  stay on the device), so it is captured once and replayed: ~200 kernel launches and all of Python leave the step.
+  With world > 1 the NCCL all-reduce stays outside the graphs (render + backward | all-reduce | Adam)."""
 import torch
 
+from . import _capi as K
 from . import metrics, sat_rendering
 from .datasets.satellite import define_satrays_from_tensors
 from .parallel import FlatGrads
 
 
 class TrainStep:
-    def __init__(self, radiance_field, n_samples=128, chunk=None, lr=5e-4, world=1):
+    def __init__(self, radiance_field, n_samples=128, chunk=None, lr=5e-4, world=1, graph=False):
         self.field = radiance_field
         self.n_samples = n_samples
         self.render_step_size = (torch.tensor(2.0) / n_samples).item()      # fp32 quotient (train_eonerf.py:50-53)
         self.chunk = chunk
         self.world = world
-        self.optimizer = torch.optim.Adam(radiance_field.parameters(), lr=lr)
-        self.grads = FlatGrads(radiance_field.parameters())
+        self.graph = graph
+        if graph and radiance_field.precision != "bf16_fused":
+            raise RuntimeError("graph=True needs precision='bf16_fused' (device-side sample counts)")
+        params = list(radiance_field.parameters())
+        self.optimizer = torch.optim.Adam(params, lr=lr, capturable=True, foreach=True) if graph else torch.optim.Adam(params, lr=lr)
+        self.grads = FlatGrads(params)
+        # backward kernels accumulate straight into the flat gradient buffer (no per-parameter autograd adds)
+        radiance_field._engine().use_grad_sink({k: p.grad for k, p in radiance_field.named_parameters()})
+        self._graphs = {}
+        self._first_done = False
+        self.launches_per_step = None           # kernels of libeonerf_b200 inside one captured step
+        self.n_rendered_total = None            # graph mode: running sum of n_rendering_samples, on the device
 
-    def __call__(self, rays, ts, pixels, epoch_idx):
-        """rays [B,11], ts [B,1] int64, pixels [B,3] on the device -> (loss tensor, n_rendering_samples)."""
+    # ------------------------------------------------------------------------------------------------------------------
+    def _forward_backward(self, rays, ts, pixels, epoch_idx, static):
         self.field.train()
         sat = define_satrays_from_tensors(rays, ts)
+        if static or self.graph:               # graph replays update the parameters behind Python's back
+            self.field._engine().refresh_prepared()
+        self.grads.zero()
         res, n_rendered = sat_rendering.render_image(self.field, None, sat, None, None, epoch_idx=epoch_idx,
-                                                     chunk=self.chunk or rays.shape[0], render_step_size=self.render_step_size)
-        if n_rendered == 0:                                                  # train_eonerf.py:135-136
+                                                     chunk=self.chunk or rays.shape[0], render_step_size=self.render_step_size,
+                                                     static=static)
+        if not static and n_rendered == 0:                                   # train_eonerf.py:135-136
             return None, 0
         if epoch_idx < 2:
             loss = metrics.mse(pixels, res["rgb"])
         else:
             loss, _ = metrics.uncertainty_aware_loss(pixels, res["rgb"], res["beta"])
-        self.grads.zero()
         loss.backward()
-        self.grads.all_reduce_mean(self.world)
-        self.optimizer.step()
         return loss.detach(), n_rendered
+
+    def _update(self, averaged):
+        if self.world > 1 and not averaged:
+            self.grads.flat.div_(self.world)
+        self.optimizer.step()
+
+    def eager(self, rays, ts, pixels, epoch_idx):
+        """rays [B,11], ts [B,1] int64, pixels [B,3] on the device -> (loss tensor, n_rendering_samples int)."""
+        loss, n_rendered = self._forward_backward(rays, ts, pixels, epoch_idx, static=False)
+        if loss is None:
+            return None, 0
+        self.grads.all_reduce_mean(self.world)
+        self._update(averaged=True)
+        return loss, n_rendered
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _capture(self, rays, ts, pixels, epoch_idx):
+        g = {"rays": rays.clone(), "ts": ts.clone(), "pixels": pixels.clone()}
+        lib = K.lib()
+        before = int(lib.eonerf_launch_count(0))
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1, capture_error_mode="thread_local"):
+            loss, n = self._forward_backward(g["rays"], g["ts"], g["pixels"], epoch_idx, static=True)
+            self.n_rendered_total += n
+            if self.world == 1:
+                self._update(averaged=True)
+        g["g1"], g["loss"], g["n"] = g1, loss, n
+        if self.world > 1:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, capture_error_mode="thread_local"):
+                self._update(averaged=False)
+            g["g2"] = g2
+        self.launches_per_step = int(lib.eonerf_launch_count(0)) - before
+        return g
+
+    def __call__(self, rays, ts, pixels, epoch_idx):
+        """Eager: as `eager`.  Graph mode: -> (loss, n_rendering_samples) as 0-d device tensors that the next call
+        overwrites; the very first call runs eagerly (it also initialises the optimiser state), the second captures."""
+        if not self.graph:
+            return self.eager(rays, ts, pixels, epoch_idx)
+        if self.n_rendered_total is None:
+            self.n_rendered_total = torch.zeros((), dtype=torch.int64, device=rays.device)
+        if not self._first_done:
+            self._first_done = True
+            loss, n = self._forward_backward(rays, ts, pixels, epoch_idx, static=True)
+            self.n_rendered_total += n
+            if self.world > 1:
+                torch.distributed.all_reduce(self.grads.flat)
+            self._update(averaged=False)
+            return loss, n
+        key = (epoch_idx >= 2, tuple(rays.shape), rays.device)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = self._capture(rays, ts, pixels, epoch_idx)
+        g["rays"].copy_(rays, non_blocking=True)
+        g["ts"].copy_(ts, non_blocking=True)
+        g["pixels"].copy_(pixels, non_blocking=True)
+        g["g1"].replay()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads.flat)
+            g["g2"].replay()
+        return g["loss"], g["n"]

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 7
+#define EONERF_ABI_VERSION 8
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -69,6 +69,10 @@ typedef struct {
   float* pts_per_ray;                               /* [B] fp32 counts (the reference returns fp32, :14) */
   int64_t* ray_offsets;                             /* [B+1] exclusive prefix of the counts (packed info) */
   int64_t* stats;                                   /* [2]: P, number of rays with 0 samples */
+  /* Device-side condition (NULL: always run).  When set, the whole call is a no-op unless *run_if != 0, and it writes
+   * stats[0] only: the sync-free form of the reference's "some ray kept no sample -> draw again" (sat_rendering.py:259-262),
+   * called with run_if = &stats[1] of the first draw and the same output buffers. */
+  const int64_t* run_if;
 } EonerfSampleArgs;
 int eonerf_sample_compact(const EonerfSampleArgs* a, eonerf_stream_t stream);
 
@@ -293,6 +297,10 @@ typedef struct {
   float* rgb;                      /* [N,3] albedo (eonerf) / rgb (vanilla) */
   float* transient_s;              /* [N] */
   float* transient_beta;           /* [N] */
+  /* Sync-free form (EONERF_PREC_BF16_FUSED only): when non-NULL the live sample count is read ON THE DEVICE from
+   * *n_pts_dev (<= n_pts); n_pts is then the capacity every buffer (stash included) is sized for, and rows >= *n_pts_dev
+   * of the outputs are left untouched.  Lets a whole training step run without a host read of P (CUDA-graph capture). */
+  const int64_t* n_pts_dev;
 } EonerfFieldFwdArgs;
 int eonerf_field_fwd(const EonerfFieldFwdArgs* a, eonerf_stream_t stream);
 
@@ -308,6 +316,7 @@ typedef struct {
   const float* g_sigma; const float* g_rgb; const float* g_transient_s; const float* g_transient_beta; /* may be NULL (=0) */
   const EonerfFieldParams* grads;  /* fp32 gradients, same shapes as params, ACCUMULATED into; NULL: skip parameter gradients */
   float* g_x;                      /* [N,3] gradient wrt positions, or NULL */
+  const int64_t* n_pts_dev;        /* as in EonerfFieldFwdArgs (must match the forward call) */
 } EonerfFieldBwdArgs;
 int eonerf_field_bwd(const EonerfFieldBwdArgs* a, eonerf_stream_t stream);
 

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
   if (warp == 0) {
     if (lane == 0) fused_producer<kCG, kMC>(p.prog, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
-    if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);      // whole warp, converged
+    if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC, true>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);      // whole warp, converged
   } else {
     // ===== epilogue warps =====
     const int e = threadIdx.x - 64;
@@ -142,6 +142,26 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) sts_u4(enc + blk_off(r, half * 4 + jj), w[4 * jj], w[4 * jj + 1], w[4 * jj + 2], w[4 * jj + 3]);
       }
+      // The accumulators start from the layer's bias: every epilogue writes the NEXT layer's bias over the columns it has
+      // just drained (tcgen05.st), so no bias add sits between the TMEM load and the bf16 pack.  Layer 0's goes in here.
+      {
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t b[32];
+          const uint32_t sb = s_cst + (uint32_t)(c_fstage[0].bias_off + half * 128 + c * 32) * 4u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float b0, b1, b2, b3;
+            lds_f4(sb + j * 16, b0, b1, b2, b3);
+            b[4 * j] = __float_as_uint(b0); b[4 * j + 1] = __float_as_uint(b1); b[4 * j + 2] = __float_as_uint(b2); b[4 * j + 3] = __float_as_uint(b3);
+          }
+          tmem_st32(t0 + c * 32, b);
+          tmem_st32(t0 + 256 + c * 32, b);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
       fence_proxy_async();
       named_bar_sync(1, kEpiThreads);
       if (e == 0) {
@@ -163,38 +183,51 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         const int cpt = d.halves == 2 ? 128 : 64;          // columns per thread
         const int col0 = half * cpt;
         const bool want_mask = kTrain && d.mask >= 0 && !(p.training & 4);
+        const bool has_next = s + 1 < p.n_stages;
+        const FStage dn = c_fstage[has_next ? s + 1 : s];
+        const int next_cols = dn.halves * 128;              // accumulator columns the next layer uses
         for (int slot = 0; slot < 2; ++slot) {
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
           const int64_t pt = tile * kTileM + r;
           const bool valid = pt < M;
           const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
           // per-image part of the HD0 bias (transient half only): W[:,256:260] . emb[img]
-          const float* delta = (d.kind == 2 && half == 1) ? p.class_delta + (size_t)((cls_pack >> (16 * slot)) & 0xFFFFu) * kHid : nullptr;
-          { EO_T0(); mbar_wait(&acc_full[slot], (cph >> slot) & 1u); if (e == 0) EO_T1(3); }
+          const float* delta_next = (has_next && dn.kind == 2) ? p.class_delta + (size_t)((cls_pack >> (16 * slot)) & 0xFFFFu) * kHid : nullptr;
+          EO_TN(ta); { EO_T0(); mbar_wait(&acc_full[slot], (cph >> slot) & 1u); if (e == 0) EO_T1(3); }
           cph ^= 1u << slot;
           tc_fence_after();
+          EO_TN(tb);
           const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + col0;
           float h0 = 0.f, h1 = 0.f, h2 = 0.f;               // head partial sums
 
           // one 32-column chunk: accumulator + bias -> (ReLU) -> bf16 -> next A operand in shared memory; returns the ReLU keep bits
           // (column 2j -> bit 15-j, column 2j+1 -> bit 31-j: the complement of the pre-activation sign bits, funnel-shifted in)
-          auto chunk = [&](uint32_t (&v)[32], const int c) -> uint32_t {
-            float x[32];
-            const uint32_t sb = s_cst + (uint32_t)(d.bias_off + col0 + c * 32) * 4u;
+          // next layer's bias for the 32 accumulator columns of chunk c (per-image rows of the HD0 transient half included)
+          auto next_bias = [&](const int c) {
+            const int colg = col0 + c * 32;
+            if (!has_next || colg >= next_cols) return;
+            uint32_t b[32];
+            const uint32_t sb = s_cst + (uint32_t)(dn.bias_off + colg) * 4u;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float b0, b1, b2, b3;
               lds_f4(sb + j * 16, b0, b1, b2, b3);
-              x[4 * j] = __uint_as_float(v[4 * j]) + b0; x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b1;
-              x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b2; x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b3;
+              b[4 * j] = __float_as_uint(b0); b[4 * j + 1] = __float_as_uint(b1); b[4 * j + 2] = __float_as_uint(b2); b[4 * j + 3] = __float_as_uint(b3);
             }
-            if (delta) {
+            if (delta_next && colg >= kHid) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 t = __ldg((const float4*)(delta + c * 32) + j);
-                x[4 * j] += t.x; x[4 * j + 1] += t.y; x[4 * j + 2] += t.z; x[4 * j + 3] += t.w;
+                const float4 t = __ldg((const float4*)(delta_next + colg - kHid) + j);
+                b[4 * j] = __float_as_uint(__uint_as_float(b[4 * j]) + t.x); b[4 * j + 1] = __float_as_uint(__uint_as_float(b[4 * j + 1]) + t.y);
+                b[4 * j + 2] = __float_as_uint(__uint_as_float(b[4 * j + 2]) + t.z); b[4 * j + 3] = __float_as_uint(__uint_as_float(b[4 * j + 3]) + t.w);
               }
             }
+            tmem_st32(tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + colg, b);
+          };
+          auto chunk = [&](uint32_t (&v)[32], const int c) -> uint32_t {
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
             uint32_t sign = 0u;
             if (want_mask) {                                  // four independent funnel-shift chains of 8
               uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u;
@@ -265,17 +298,23 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           tmem_ld32(taddr, va);
           tmem_ld_wait_dep(va);
           tmem_ld32(taddr + 32, vb);
+          next_bias(0);                                      // columns of chunk 0 are drained: refill them
           m0 = chunk(va, 0);
           tmem_ld_wait_dep(vb);
           if (cpt == 128) tmem_ld32(taddr + 64, va);
+          next_bias(1);
           m1 = chunk(vb, 1);
           if (cpt == 128) {
             tmem_ld_wait_dep(va);
             tmem_ld32(taddr + 96, vb);
+            next_bias(2);
             m2 = chunk(va, 2);
             tmem_ld_wait_dep(vb);
+            next_bias(3);
             m3 = chunk(vb, 3);
           }
+          if (has_next) tmem_st_wait();
+          EO_TN(tc);
           if (want_mask && valid) {
             uint32_t* mrow = p.mask[d.mask] + pt * 8 + col0 / 32;
             if (cpt == 128) *(uint4*)mrow = make_uint4(m0, m1, m2, m3);
@@ -286,8 +325,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           fence_proxy_async();
           // the OTHER slot's latest stash store (issued one epilogue ago) must have finished reading shared memory before the
           // next epilogue overwrites that slot
+          EO_TN(td);
           if (kTrain && e == 0) tma_store_wait_read<0>();
+          EO_TN(te);
           { EO_T0(); named_bar_sync(1, kEpiThreads); if (e == 32) EO_T1(5); }
+          EO_TN(tf);
           if (e == 0) {
             if (s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
             if (kTrain && tile < n_tiles && !(p.training & 2)) {
@@ -312,6 +354,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
               p.tb[pt] = softplus_f(h1 + p1 + cst[kCScalars + 5]);
             }
           }
+          EO_TN(tg);
+          EO_TD(7, tb, tc); EO_TD(8, tc, td); EO_TD(9, td, te); EO_TD(10, te, tf); EO_TD(11, tf, tg); EO_TD(12, ta, tg);
         }
       }
     }
@@ -536,8 +580,8 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
 #ifdef EONERF_TIMING
 extern "C" int eonerf_debug_timing(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, eonerf::g_fused_timing, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(eonerf::g_fused_timing, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(out, eonerf::g_fused_timing, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(eonerf::g_fused_timing, z, sizeof(z)); }
   return 0;
 }
 #endif

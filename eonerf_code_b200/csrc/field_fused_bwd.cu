@@ -659,8 +659,8 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
 #ifdef EONERF_TIMING
 extern "C" int eonerf_debug_timing_bwd(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, eonerf::g_fused_timing, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(eonerf::g_fused_timing, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(out, eonerf::g_fused_timing, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(eonerf::g_fused_timing, z, sizeof(z)); }
   return 0;
 }
 #endif

@@ -6,7 +6,10 @@
 
 namespace eonerf {
 
-constexpr int kRingStages = 3;
+#ifndef EONERF_RING_STAGES
+#define EONERF_RING_STAGES 3
+#endif
+constexpr int kRingStages = EONERF_RING_STAGES;   // weight ring depth (2 only for the latency experiment)
 constexpr int kSlotBytes = 5 * kBlkBytes;                  // ACT blocks 0..3 + ENC block 4
 constexpr int kOffRing = 0;
 constexpr int kOffSlot = kRingStages * kBlkBytes;          // 49152
@@ -99,11 +102,15 @@ static inline int fused_grid(int64_t n_pairs) {
 // barrier class.  g_fused_timing: 0 mma<-act_ready, 1 mma<-weights, 2 producer<-ring slot, 3 epilogue<-accumulator,
 // 4 epilogue start barrier (incl. stash-store drain), 5 epilogue end barrier, 6 total cycles of the MMA thread
 #ifdef EONERF_TIMING
-static __device__ unsigned long long g_fused_timing[8];   // one copy per translation unit
+static __device__ unsigned long long g_fused_timing[16];   // one copy per translation unit
 #define EO_T0() const long long _t0 = clock64()
+#define EO_TN(name) const long long name = clock64()
+#define EO_TD(slot, a, b) do { if (blockIdx.x == 0 && threadIdx.x == 64) g_fused_timing[slot] += (unsigned long long)((b) - (a)); } while (0)
 #define EO_T1(slot) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_fused_timing[slot] += (unsigned long long)(clock64() - _t0); } while (0)
 #else
 #define EO_T0() do {} while (0)
+#define EO_TN(name) do {} while (0)
+#define EO_TD(slot, a, b) do {} while (0)
 #define EO_T1(slot) do {} while (0)
 #endif
 
@@ -189,7 +196,8 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
 }
 
 // the whole MMA warp (kCG = 2: of the leader CTA), converged: issue the MMAs of every stage for both slots
-template <int kCG, int kMC = 1>
+// kAccInit: the epilogue warps have pre-loaded every accumulator (with the layer's bias): the first MMA of a stage accumulates too
+template <int kCG, int kMC = 1, bool kAccInit = false>
 __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t* smem, const FusedBars& B, uint32_t tmem_base, int64_t it0,
                                                  int64_t n_items, int64_t it_stride) {
   int rs = 0; uint32_t rph = 0;
@@ -217,7 +225,7 @@ __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t
             const uint32_t la = desc_lo_k128(slot0 + d.a[kb] * kBlkBytes);
             const uint32_t lb = desc_lo_k128(ring0 + rs * kBlkBytes);
             if (elected) {
-              umma_k128<kCG>(d_tmem, la, lb, idesc, kb != 0);           // 16 K elements = 32 bytes = +2 in the address field
+              umma_k128<kCG>(d_tmem, la, lb, idesc, kAccInit || kb != 0);           // 16 K elements = 32 bytes = +2 in the address field
               umma_k128<kCG>(d_tmem, la + 2, lb + 2, idesc, 1);
               umma_k128<kCG>(d_tmem, la + 4, lb + 4, idesc, 1);
               umma_k128<kCG>(d_tmem, la + 6, lb + 6, idesc, 1);

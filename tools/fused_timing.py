@@ -17,13 +17,14 @@ img = torch.randint(0, n_img, (n, 1), device=dev)
 m = EONerfMLP(n_img, radiometric_normalization=True, precision="bf16_fused").to(dev)
 e = m._engine()
 lib = K.lib()
-names = ["mma<-act_ready", "mma<-weights", "producer<-slot", "epi<-acc_full", "epi start barrier", "epi end barrier", "mma thread total"]
+names = ["mma<-act_ready", "mma<-weights", "producer<-slot", "epi<-acc_full", "epi start barrier", "epi end barrier", "mma thread total",
+         "epi chunks", "epi fences", "epi store-read wait", "epi barrier(t0)", "epi post-barrier", "epi total(t0)"]
 for dens in (False, True):
     for keep in (True, False):
         e.fwd(n, dens, x=x, img_idx=None if dens else img, keep=keep)
-        out = (C.c_ulonglong * 8)()
+        out = (C.c_ulonglong * 16)()
         lib.eonerf_debug_timing(out, 1)
         e.fwd(n, dens, x=x, img_idx=None if dens else img, keep=keep)
         lib.eonerf_debug_timing(out, 1)
         tot = out[6]
-        print(f"density_only={int(dens)} keep={int(keep)}: total {tot} cycles; " + ", ".join(f"{nm} {100 * out[i] / tot:.1f}%" for i, nm in enumerate(names[:6])))
+        print(f"density_only={int(dens)} keep={int(keep)}: total {tot} cycles; " + ", ".join(f"{nm} {100 * out[i] / tot:.1f}%" for i, nm in enumerate(names) if i != 6))

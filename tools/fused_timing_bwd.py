@@ -21,7 +21,7 @@ for dens in (False, True):
     f = e.fwd(n, dens, x=x, img_idx=None if dens else img)
     gs = torch.randn(n, device=dev)
     g3 = torch.randn(n, 3, device=dev)
-    out = (C.c_ulonglong * 8)()
+    out = (C.c_ulonglong * 16)()
     for rep in range(2):
         lib.eonerf_debug_timing_bwd(out, 1)
         e.bwd(n, dens, f, g_sigma=gs, g_rgb=None if dens else g3, g_ts=None if dens else gs, g_tb=None if dens else gs,

@@ -169,7 +169,7 @@ def test_fused_backward_matches_layered(cuda, n, density_only):
             assert float(vb[k].abs().max()) == 0.0, k
             continue
         assert torch.isfinite(vb[k]).all(), k
-        # both bf16 paths sit ~1e-1 (relative L2) from the fp32 gradient of these random upstream gradients (tools/_diag: 0.17 vs
+        # both bf16 paths sit ~1e-1 (relative L2) from the fp32 gradient of these random upstream gradients (tools/diag_grad_noise.py: 0.17 vs
         # 0.17 on transient_mlp.0 at n=100); their mutual distance is rounding-flip noise that shrinks with n
         assert l2(vb[k], va[k]) <= (4e-2 if n <= 1000 else 2e-2), (k, l2(vb[k], va[k]))
     if density_only:

@@ -44,6 +44,7 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None            # host-clock window of the timed region: only samples inside it count
 
     def start(self):
         try:
@@ -55,17 +56,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        rows = [r[1:] for r in self.rows if t0 <= r[0] <= t1 + 0.1] or [r[1:] for r in self.rows[-3:]]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -126,6 +135,40 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------------------------------------
+RENDER_HW = 1024
+
+
+def render_arm(args, model, rank, world, dev, barrier, max_over_ranks):
+    """BASELINE configs[3]: full-image eval render of a 1024x1024 crop (rgb + shadows + depth), rows sharded over the ranks,
+    rank 0 gathers the [rows, W, 21] result.  One warm-up image, one timed image; value = rays/s of the whole job."""
+    from eonerf_code_b200 import sat_rendering
+    from eonerf_code_b200.datasets.satellite import define_satrays_from_tensors
+    from eonerf_code_b200.datasets.synthetic import make_rays
+    from eonerf_code_b200.parallel import gather_rows, shard_bounds
+    r0, r1 = shard_bounds(RENDER_HW, rank, world)
+    rays, ts, _ = make_rays((r1 - r0) * RENDER_HW, N_IMAGES, seed=7 + rank, eval_mode=True)
+    rays, ts = rays.to(dev), ts.to(dev)
+    model.eval()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_samples = 0
+    with torch.no_grad():
+        for it in range(2):
+            barrier()
+            e0.record()
+            res, n_samples = sat_rendering.render_image(model, None, define_satrays_from_tensors(rays, ts), None, None,
+                                                        epoch_idx=EPOCH_IDX, chunk=65536, render_step_size=2.0 / N_SAMPLES, eval=True)
+            out = torch.cat([res["rgb"], res["geo_shadows"], res["depth"]], dim=1).view(r1 - r0, RENDER_HW, 5)
+            out = gather_rows(out, world)
+            e1.record()
+            barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    model.train()
+    return {"metric": "render_rays_per_sec", "value": RENDER_HW * RENDER_HW / (ms * 1e-3), "unit": "rays/s", "ms_per_image": ms,
+            "workload": f"BASELINE configs[3]: {RENDER_HW}x{RENDER_HW} eval render (rgb + geo_shadows + depth), n_samples={N_SAMPLES}, "
+                        f"65536-ray chunks, rows sharded over {world} GPU(s), gathered on rank 0",
+            "kept_camera_samples_rank0": int(n_samples)}
+
+
 def run_product(args, rank, world, local):
     from eonerf_code_b200 import _capi as K
     from eonerf_code_b200.radiance_fields import EONerfMLP
@@ -156,12 +199,13 @@ def run_product(args, rank, world, local):
     # ---- device-resident arm -------------------------------------------------------------------------------------
     n_batches = 4
     batches = [synthetic_batch(rank, i, dev) for i in range(n_batches)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                      # nvidia-smi needs a moment to come up: start it before the warm-up
     for i in range(args.warmup):            # graph mode: the 1st call runs eagerly, the 2nd captures, the rest replay
         step_fn(*batches[i % n_batches], EPOCH_IDX)
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    clocks.mark_begin()
     lib.eonerf_launch_count(1)
     if not use_graph:
         lib.eonerf_profile_enable(1)
@@ -177,7 +221,7 @@ def run_product(args, rank, world, local):
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    clk = clocks.stop() if rank == 0 else None
+    clocks.mark_end()
     if use_graph:
         # a captured step holds launches_per_step kernels of this library; CUDA graphs cannot hold timing events, so the
         # per-kernel durations for the roofline come from the same steps run eagerly right after the timed region
@@ -207,13 +251,21 @@ def run_product(args, rank, world, local):
     for i in range(2):
         e2e_step(i)
     barrier()
+    if clocks.t1 is not None and clocks.t1 - clocks.t0 < 0.5:
+        clocks.t1 = None                    # short timed region: let the window run on through the end-to-end region
     e0.record()
     for i in range(args.steps):
         e2e_step(i)
     e1.record()
     barrier()
+    if clocks.t1 is None:
+        clocks.mark_end()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     h2d = sum(x.numel() * x.element_size() for x in host[0])
+    clk = None
+    if rank == 0:                           # samples inside the device-resident timed region; if that was too short for
+        clk = clocks.stop()                 # nvidia-smi's 100 ms period, stop() falls back to the last samples (e2e region)
+    render = render_arm(args, model, rank, world, dev, barrier, max_over_ranks) if not args.no_render else None
 
     if rank != 0:
         return
@@ -252,6 +304,8 @@ def run_product(args, rank, world, local):
             "e2e": {"value": world * RAYS_PER_GPU * args.steps / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_dw": roof_tn}
+    if render is not None:
+        line["render"] = render
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         t0 = time.perf_counter()
@@ -269,6 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-render", action="store_true", help="skip the full-image render arm (BASELINE configs[3])")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly (host reads of the sample counts) instead of as a CUDA graph")
     ap.add_argument("--precision", default="bf16_fused", choices=["bf16_fused", "bf16"], help="bf16_fused: fused tcgen05 MLP kernels (product); bf16: layer-by-layer")
     args = ap.parse_args()

@@ -178,71 +178,188 @@ __global__ void __launch_bounds__(256) accumulate_bwd_kernel(EonerfAccumBwdArgs 
 // Fused EO-NeRF compositing (eonerf.py:229-246)
 // comp row: 0:3 albedo, 3 depth, 4 beta(+beta_min), 5 transient_s, 6:9 ambient, 9 sum(w), 10:12 zero
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) composite_fwd_kernel(EonerfCompositeFwdArgs a) {
-  int lane = threadIdx.x & 31;
-  int64_t ray = warp_ray();
-  if (ray >= a.n_rays) return;
-  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
-  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // albedo3, depth, beta, ts, sumw
-  float carry = 0.f;
-  for (int64_t base = beg; base < end; base += 32) {
-    int64_t i = base + lane;
-    bool ok = i < end;
-    float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
-    float sg = ok ? __ldg(a.sigma + i) : 0.f;
-    float tau = sg * (te - ts), tot;
-    float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
-    carry += tot;
-    if (ok) {
-      SampleW s = sample_weight(ts, te, sg, pre);
-      if (a.albedo) {
-        acc[0] += s.w * __ldg(a.albedo + 3 * i);
-        acc[1] += s.w * __ldg(a.albedo + 3 * i + 1);
-        acc[2] += s.w * __ldg(a.albedo + 3 * i + 2);
-      }
-      acc[3] += s.w * __ldg(a.z_mid + i);
-      if (a.transient_beta) acc[4] += s.w * __ldg(a.transient_beta + i);
-      if (a.transient_s) acc[5] += s.w * __ldg(a.transient_s + i);
-      acc[6] += s.w;
-    }
-  }
+// Rays with at most 128 kept samples (every ray when n_samples <= 129, the reference's setting) take the register path:
+// a lane issues all of its (up to 4 x 9) loads back to back before the first dependent instruction, so a warp keeps ~4 KB
+// in flight instead of ~1 KB, and the backward needs no second sweep over memory.  Longer rays use the chunk loop.
+constexpr int kFastChunks = 4;
+
+struct CompIn {           // one lane's samples of a ray: chunk c holds sample beg + 32 c + lane
+  float ts[kFastChunks], te[kFastChunks], sg[kFastChunks], z[kFastChunks];
+  float a0[kFastChunks], a1[kFastChunks], a2[kFastChunks], tb[kFastChunks], tsc[kFastChunks];
+};
+
+template <class Args>
+__device__ __forceinline__ void comp_load(const Args& a, int64_t beg, int64_t end, int lane, CompIn& in) {
 #pragma unroll
-  for (int c = 0; c < 7; ++c) acc[c] = warp_sum(acc[c]);
-  if (lane == 0) {
-    float* o = a.comp + ray * EONERF_COMP_COLS;
-    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
-    o[4] = acc[4] + a.beta_min;
-    o[5] = acc[5];
-    // ambient is constant along the ray (sun direction is per ray): sum_i w_i*a = a*sum_i w_i
-    for (int c = 0; c < 3; ++c) o[6 + c] = a.ambient_ray ? acc[6] * __ldg(a.ambient_ray + 3 * ray + c) : 0.f;
-    o[9] = acc[6];
-    o[10] = 0.f; o[11] = 0.f;
+  for (int c = 0; c < kFastChunks; ++c) {
+    const int64_t i = beg + c * 32 + lane;
+    const bool ok = i < end;
+    in.ts[c] = ok ? __ldg(a.t_starts + i) : 0.f;
+    in.te[c] = ok ? __ldg(a.t_ends + i) : 0.f;
+    in.sg[c] = ok ? __ldg(a.sigma + i) : 0.f;
+    in.z[c] = ok ? __ldg(a.z_mid + i) : 0.f;
+    in.a0[c] = (ok && a.albedo) ? __ldg(a.albedo + 3 * i) : 0.f;
+    in.a1[c] = (ok && a.albedo) ? __ldg(a.albedo + 3 * i + 1) : 0.f;
+    in.a2[c] = (ok && a.albedo) ? __ldg(a.albedo + 3 * i + 2) : 0.f;
+    in.tb[c] = (ok && a.transient_beta) ? __ldg(a.transient_beta + i) : 0.f;
+    in.tsc[c] = (ok && a.transient_s) ? __ldg(a.transient_s + i) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) composite_fwd_kernel(EonerfCompositeFwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t ray = warp_ray(); ray < a.n_rays; ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // albedo3, depth, beta, ts, sumw
+    float carry = 0.f;
+    if (end - beg <= 32 * kFastChunks) {
+      CompIn in;
+      comp_load(a, beg, end, lane, in);
+#pragma unroll
+      for (int c = 0; c < kFastChunks; ++c) {
+        const bool ok = beg + c * 32 + lane < end;
+        float tot;
+        const float tau = in.sg[c] * (in.te[c] - in.ts[c]);
+        const float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+        carry += tot;
+        if (ok) {
+          const SampleW s = sample_weight(in.ts[c], in.te[c], in.sg[c], pre);
+          acc[0] += s.w * in.a0[c]; acc[1] += s.w * in.a1[c]; acc[2] += s.w * in.a2[c];
+          acc[3] += s.w * in.z[c];
+          acc[4] += s.w * in.tb[c];
+          acc[5] += s.w * in.tsc[c];
+          acc[6] += s.w;
+        }
+      }
+    } else {
+      for (int64_t base = beg; base < end; base += 32) {
+        int64_t i = base + lane;
+        bool ok = i < end;
+        float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
+        float sg = ok ? __ldg(a.sigma + i) : 0.f;
+        float tau = sg * (te - ts), tot;
+        float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+        carry += tot;
+        if (ok) {
+          SampleW s = sample_weight(ts, te, sg, pre);
+          if (a.albedo) {
+            acc[0] += s.w * __ldg(a.albedo + 3 * i);
+            acc[1] += s.w * __ldg(a.albedo + 3 * i + 1);
+            acc[2] += s.w * __ldg(a.albedo + 3 * i + 2);
+          }
+          acc[3] += s.w * __ldg(a.z_mid + i);
+          if (a.transient_beta) acc[4] += s.w * __ldg(a.transient_beta + i);
+          if (a.transient_s) acc[5] += s.w * __ldg(a.transient_s + i);
+          acc[6] += s.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) acc[c] = warp_sum(acc[c]);
+    if (lane == 0) {
+      float* o = a.comp + ray * EONERF_COMP_COLS;
+      // ambient is constant along the ray (sun direction is per ray): sum_i w_i*a = a*sum_i w_i
+      float am[3];
+      for (int c = 0; c < 3; ++c) am[c] = a.ambient_ray ? acc[6] * __ldg(a.ambient_ray + 3 * ray + c) : 0.f;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] + a.beta_min, acc[5], am[0], am[1]);
+      *reinterpret_cast<float4*>(o + 8) = make_float4(am[2], acc[6], 0.f, 0.f);
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) composite_bwd_kernel(EonerfCompositeBwdArgs a) {
-  int lane = threadIdx.x & 31;
-  int64_t ray = warp_ray();
-  if (ray >= a.n_rays) return;
-  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
-  const float* g = a.g_comp + ray * EONERF_COMP_COLS;
-  float ga0 = __ldg(g), ga1 = __ldg(g + 1), ga2 = __ldg(g + 2), gd = __ldg(g + 3), gb = __ldg(g + 4), gs = __ldg(g + 5);
-  // per-ray constant part of G_i: ambient and the sum-of-weights column
-  float gconst = __ldg(g + 9);
-  if (a.ambient_ray)
-    for (int c = 0; c < 3; ++c) gconst += __ldg(g + 6 + c) * __ldg(a.ambient_ray + 3 * ray + c);
+  const int lane = threadIdx.x & 31;
+  for (int64_t ray = warp_ray(); ray < a.n_rays; ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+    const float* g = a.g_comp + ray * EONERF_COMP_COLS;
+    const float4 g03 = __ldg(reinterpret_cast<const float4*>(g)), g47 = __ldg(reinterpret_cast<const float4*>(g + 4)),
+                 g8b = __ldg(reinterpret_cast<const float4*>(g + 8));
+    const float ga0 = g03.x, ga1 = g03.y, ga2 = g03.z, gd = g03.w, gb = g47.x, gs = g47.y;
+    const float gam[3] = {g47.z, g47.w, g8b.x};
+    // per-ray constant part of G_i: ambient and the sum-of-weights column
+    float gconst = g8b.y;
+    if (a.ambient_ray)
+      for (int c = 0; c < 3; ++c) gconst += gam[c] * __ldg(a.ambient_ray + 3 * ray + c);
 
-  auto G_of = [&](int64_t i) {
-    float G = gconst + gd * __ldg(a.z_mid + i);
-    if (a.albedo) G += ga0 * __ldg(a.albedo + 3 * i) + ga1 * __ldg(a.albedo + 3 * i + 1) + ga2 * __ldg(a.albedo + 3 * i + 2);
-    if (a.transient_beta) G += gb * __ldg(a.transient_beta + i);
-    if (a.transient_s) G += gs * __ldg(a.transient_s + i);
-    return G;
-  };
+    if (end - beg <= 32 * kFastChunks) {
+      CompIn in;
+      comp_load(a, beg, end, lane, in);
+      float w[kFastChunks], T1[kFastChunks], v[kFastChunks], G[kFastChunks];
+      float S = 0.f, sumw = 0.f, carry = 0.f;
+#pragma unroll
+      for (int c = 0; c < kFastChunks; ++c) {
+        const bool ok = beg + c * 32 + lane < end;
+        float tot;
+        const float tau = in.sg[c] * (in.te[c] - in.ts[c]);
+        const float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+        carry += tot;
+        const SampleW s = sample_weight(in.ts[c], in.te[c], in.sg[c], pre);
+        G[c] = gconst + gd * in.z[c] + ga0 * in.a0[c] + ga1 * in.a1[c] + ga2 * in.a2[c] + gb * in.tb[c] + gs * in.tsc[c];
+        w[c] = ok ? s.w : 0.f;
+        T1[c] = s.T * expf(-s.tau);                       // T_{j+1} = T_j * exp(-tau_j)
+        v[c] = ok ? G[c] * s.w : 0.f;
+        S += v[c];
+        sumw += w[c];
+      }
+      S = warp_sum(S);
+      sumw = warp_sum(sumw);
+      if (lane == 0 && a.g_ambient_ray)
+        for (int c = 0; c < 3; ++c) a.g_ambient_ray[3 * ray + c] = gam[c] * sumw;
+      float run = 0.f;
+#pragma unroll
+      for (int c = 0; c < kFastChunks; ++c) {
+        const int64_t i = beg + c * 32 + lane;
+        const float inc = warp_inclusive_sum(v[c], lane);
+        const float suffix = (i == end - 1) ? 0.f : S - (run + inc);   // exact 0 for the 1e10-long last interval (see weights_bwd)
+        run += __shfl_sync(kFull, inc, 31);
+        if (i < end) {
+          a.g_sigma[i] = (in.te[c] - in.ts[c]) * (G[c] * T1[c] - suffix);
+          if (a.g_albedo) {
+            a.g_albedo[3 * i] = w[c] * ga0;
+            a.g_albedo[3 * i + 1] = w[c] * ga1;
+            a.g_albedo[3 * i + 2] = w[c] * ga2;
+          }
+          if (a.g_transient_beta) a.g_transient_beta[i] = w[c] * gb;
+          if (a.g_transient_s) a.g_transient_s[i] = w[c] * gs;
+        }
+      }
+      continue;
+    }
 
-  float S = 0.f, sumw = 0.f;
-  {
-    float carry = 0.f;
+    auto G_of = [&](int64_t i) {
+      float G = gconst + gd * __ldg(a.z_mid + i);
+      if (a.albedo) G += ga0 * __ldg(a.albedo + 3 * i) + ga1 * __ldg(a.albedo + 3 * i + 1) + ga2 * __ldg(a.albedo + 3 * i + 2);
+      if (a.transient_beta) G += gb * __ldg(a.transient_beta + i);
+      if (a.transient_s) G += gs * __ldg(a.transient_s + i);
+      return G;
+    };
+
+    float S = 0.f, sumw = 0.f;
+    {
+      float carry = 0.f;
+      for (int64_t base = beg; base < end; base += 32) {
+        int64_t i = base + lane;
+        bool ok = i < end;
+        float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
+        float sg = ok ? __ldg(a.sigma + i) : 0.f;
+        float tau = sg * (te - ts), tot;
+        float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+        carry += tot;
+        float v = 0.f, w = 0.f;
+        if (ok) {
+          SampleW s = sample_weight(ts, te, sg, pre);
+          w = s.w;
+          v = G_of(i) * s.w;
+        }
+        S += warp_sum(v);
+        sumw += warp_sum(w);
+      }
+    }
+    if (lane == 0 && a.g_ambient_ray)
+      for (int c = 0; c < 3; ++c) a.g_ambient_ray[3 * ray + c] = gam[c] * sumw;
+
+    float carry = 0.f, run = 0.f;
     for (int64_t base = beg; base < end; base += 32) {
       int64_t i = base + lane;
       bool ok = i < end;
@@ -251,44 +368,23 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(EonerfCompositeBwdAr
       float tau = sg * (te - ts), tot;
       float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
       carry += tot;
-      float v = 0.f, w = 0.f;
+      SampleW s = sample_weight(ts, te, sg, pre);
+      float G = ok ? G_of(i) : 0.f;
+      float v = ok ? G * s.w : 0.f;
+      float inc = warp_inclusive_sum(v, lane);
+      float suffix = (i == end - 1) ? 0.f : S - (run + inc);   // exact 0 for the 1e10-long last interval (see weights_bwd)
+      run += __shfl_sync(kFull, inc, 31);
       if (ok) {
-        SampleW s = sample_weight(ts, te, sg, pre);
-        w = s.w;
-        v = G_of(i) * s.w;
+        // T_{j+1} = T_j * exp(-tau_j)
+        a.g_sigma[i] = (te - ts) * (G * s.T * expf(-s.tau) - suffix);
+        if (a.g_albedo) {
+          a.g_albedo[3 * i] = s.w * ga0;
+          a.g_albedo[3 * i + 1] = s.w * ga1;
+          a.g_albedo[3 * i + 2] = s.w * ga2;
+        }
+        if (a.g_transient_beta) a.g_transient_beta[i] = s.w * gb;
+        if (a.g_transient_s) a.g_transient_s[i] = s.w * gs;
       }
-      S += warp_sum(v);
-      sumw += warp_sum(w);
-    }
-  }
-  if (lane == 0 && a.g_ambient_ray)
-    for (int c = 0; c < 3; ++c) a.g_ambient_ray[3 * ray + c] = __ldg(g + 6 + c) * sumw;
-
-  float carry = 0.f, run = 0.f;
-  for (int64_t base = beg; base < end; base += 32) {
-    int64_t i = base + lane;
-    bool ok = i < end;
-    float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
-    float sg = ok ? __ldg(a.sigma + i) : 0.f;
-    float tau = sg * (te - ts), tot;
-    float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
-    carry += tot;
-    SampleW s = sample_weight(ts, te, sg, pre);
-    float G = ok ? G_of(i) : 0.f;
-    float v = ok ? G * s.w : 0.f;
-    float inc = warp_inclusive_sum(v, lane);
-    float suffix = (i == end - 1) ? 0.f : S - (run + inc);   // exact 0 for the 1e10-long last interval (see weights_bwd)
-    run += __shfl_sync(kFull, inc, 31);
-    if (ok) {
-      // T_{j+1} = T_j * exp(-tau_j)
-      a.g_sigma[i] = (te - ts) * (G * s.T * expf(-s.tau) - suffix);
-      if (a.g_albedo) {
-        a.g_albedo[3 * i] = s.w * ga0;
-        a.g_albedo[3 * i + 1] = s.w * ga1;
-        a.g_albedo[3 * i + 2] = s.w * ga2;
-      }
-      if (a.g_transient_beta) a.g_transient_beta[i] = s.w * gb;
-      if (a.g_transient_s) a.g_transient_s[i] = s.w * gs;
     }
   }
 }
@@ -313,25 +409,50 @@ __global__ void sun_rays_kernel(EonerfSunRaysArgs a) {
 
 // geo_shadow[r] = transmittance in front of the LAST kept sample of sun ray r (:106-116), 1 if none
 __global__ void __launch_bounds__(256) shadow_fwd_kernel(EonerfShadowFwdArgs a) {
-  int lane = threadIdx.x & 31;
-  int64_t ray = warp_ray();
-  if (ray >= a.n_rays) return;
-  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
-  float acc = 0.f;
-  for (int64_t i = beg + lane; i < end - 1; i += 32)
-    acc += __ldg(a.sigma + i) * (__ldg(a.t_ends + i) - __ldg(a.t_starts + i));
-  acc = warp_sum(acc);
-  if (lane == 0) a.geo_shadow[ray] = (end > beg) ? expf(-acc) : 1.0f;
+  const int lane = threadIdx.x & 31;
+  for (int64_t ray = warp_ray(); ray < a.n_rays; ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+    float acc = 0.f;
+    int64_t i = beg + lane;
+    for (; i + 96 < end - 1; i += 128) {                  // 12 loads in flight per lane
+      float sg[4], te[4], ts[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { sg[c] = __ldg(a.sigma + i + 32 * c); te[c] = __ldg(a.t_ends + i + 32 * c); ts[c] = __ldg(a.t_starts + i + 32 * c); }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc += sg[c] * (te[c] - ts[c]);
+    }
+    {
+      float sg[4], te[4], ts[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool ok = i + 32 * c < end - 1;
+        sg[c] = ok ? __ldg(a.sigma + i + 32 * c) : 0.f; te[c] = ok ? __ldg(a.t_ends + i + 32 * c) : 0.f; ts[c] = ok ? __ldg(a.t_starts + i + 32 * c) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc += sg[c] * (te[c] - ts[c]);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) a.geo_shadow[ray] = (end > beg) ? expf(-acc) : 1.0f;
+  }
 }
 
 __global__ void __launch_bounds__(256) shadow_bwd_kernel(EonerfShadowBwdArgs a) {
-  int lane = threadIdx.x & 31;
-  int64_t ray = warp_ray();
-  if (ray >= a.n_rays) return;
-  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
-  float k = -__ldg(a.geo_shadow + ray) * __ldg(a.g_geo_shadow + ray);
-  for (int64_t i = beg + lane; i < end; i += 32)
-    a.g_sigma[i] = (i < end - 1) ? k * (__ldg(a.t_ends + i) - __ldg(a.t_starts + i)) : 0.f;
+  const int lane = threadIdx.x & 31;
+  for (int64_t ray = warp_ray(); ray < a.n_rays; ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+    const float k = -__ldg(a.geo_shadow + ray) * __ldg(a.g_geo_shadow + ray);
+    for (int64_t i = beg + lane; i < end; i += 128) {
+      float te[4], ts[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool ok = i + 32 * c < end;
+        te[c] = ok ? __ldg(a.t_ends + i + 32 * c) : 0.f; ts[c] = ok ? __ldg(a.t_starts + i + 32 * c) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (i + 32 * c < end) a.g_sigma[i + 32 * c] = (i + 32 * c < end - 1) ? k * (te[c] - ts[c]) : 0.f;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) sun_origin_bwd_kernel(EonerfSunOriginBwdArgs a) {
@@ -444,6 +565,18 @@ __global__ void epilogue_bwd_kernel(EonerfEpilogueBwdArgs a) {
 using namespace eonerf;
 
 #define RAY_BLOCKS(n) div_up((n), kWarpsPerBlock)
+// grid-stride kernels (compositing, shadows): at most 8 resident blocks per SM, each warp then walks several rays
+static inline int ray_blocks_capped(int64_t n_rays) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int64_t want = div_up(n_rays, kWarpsPerBlock), cap = (int64_t)sms * 8;
+  return (int)(want < cap ? want : cap);
+}
 
 extern "C" int eonerf_weights_fwd(const EonerfWeightsFwdArgs* a, eonerf_stream_t stream) {
   EO_REQUIRE(a && a->ray_offsets && a->n_rays >= 0, "weights_fwd: bad arguments");
@@ -487,7 +620,7 @@ extern "C" int eonerf_composite_fwd(const EonerfCompositeFwdArgs* a, eonerf_stre
   EO_REQUIRE(a && a->ray_offsets && a->comp && a->n_rays >= 0, "composite_fwd: bad arguments");
   if (a->n_rays == 0) return EONERF_OK;
   EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->z_mid && a->sigma), "composite_fwd: null input");
-  composite_fwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  composite_fwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -497,7 +630,7 @@ extern "C" int eonerf_composite_bwd(const EonerfCompositeBwdArgs* a, eonerf_stre
   if (a->n_rays == 0) return EONERF_OK;
   EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->z_mid && a->sigma && a->g_sigma),
              "composite_bwd: null pointer");
-  composite_bwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  composite_bwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -515,7 +648,7 @@ extern "C" int eonerf_shadow_fwd(const EonerfShadowFwdArgs* a, eonerf_stream_t s
   EO_REQUIRE(a && a->ray_offsets && a->geo_shadow && a->n_rays >= 0, "shadow_fwd: bad arguments");
   if (a->n_rays == 0) return EONERF_OK;
   EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->sigma), "shadow_fwd: null input");
-  shadow_fwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  shadow_fwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -524,7 +657,7 @@ extern "C" int eonerf_shadow_bwd(const EonerfShadowBwdArgs* a, eonerf_stream_t s
   EO_REQUIRE(a && a->ray_offsets && a->n_rays >= 0, "shadow_bwd: bad arguments");
   if (a->n_rays == 0 || a->n_pts == 0) return EONERF_OK;
   EO_REQUIRE(a->t_starts && a->t_ends && a->geo_shadow && a->g_geo_shadow && a->g_sigma, "shadow_bwd: null pointer");
-  shadow_bwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  shadow_bwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }

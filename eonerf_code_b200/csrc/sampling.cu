@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) sample_count_kernel(EonerfSampleArgs a) {
 
 // single CTA: in-place inclusive scan of ray_offsets[1..B]; ray_offsets[0] = 0; also emits the fp32
 // per-ray counts (count_number_of_pts_per_nerfacc_ray, sat_rendering.py:10-16) and the totals.
+constexpr int kScanItems = 8;     // rays per thread per sweep: 8192 rays per sweep of the single scan CTA
 __global__ void __launch_bounds__(1024) sample_scan_kernel(EonerfSampleArgs a) {
   __shared__ long long warp_tot[32];
   __shared__ long long carry_s;
@@ -89,14 +90,21 @@ __global__ void __launch_bounds__(1024) sample_scan_kernel(EonerfSampleArgs a) {
   if (tid == 0) { carry_s = 0; empty_s = 0; a.ray_offsets[0] = 0; }
   __syncthreads();
   int n_empty = 0;
-  for (int64_t base = 0; base < a.n_rays; base += 1024) {
-    int64_t i = base + tid;
-    long long c = (i < a.n_rays) ? a.ray_offsets[i + 1] : 0;
-    if (i < a.n_rays) {
-      if (!redraw) a.pts_per_ray[i] = (float)c;
-      n_empty += (c == 0);
+  for (int64_t base = 0; base < a.n_rays; base += 1024 * kScanItems) {
+    const int64_t i0 = base + (int64_t)tid * kScanItems;
+    long long c[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) c[k] = (i0 + k < a.n_rays) ? a.ray_offsets[i0 + k + 1] : 0;
+    long long v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (i0 + k < a.n_rays) {
+        if (!redraw) a.pts_per_ray[i0 + k] = (float)c[k];
+        n_empty += (c[k] == 0);
+      }
+      v += c[k];
+      c[k] = v;                                               // inclusive prefix inside the thread
     }
-    long long v = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       long long t = __shfl_up_sync(kFull, v, o);
@@ -114,10 +122,13 @@ __global__ void __launch_bounds__(1024) sample_scan_kernel(EonerfSampleArgs a) {
       warp_tot[lane] = w;
     }
     __syncthreads();
-    long long prefix = carry_s + (wid ? warp_tot[wid - 1] : 0) + v;
-    if (i < a.n_rays) a.ray_offsets[i + 1] = prefix;
+    // exclusive prefix of this thread = carry + previous warps + previous lanes
+    const long long before = carry_s + (wid ? warp_tot[wid - 1] : 0) + (v - c[kScanItems - 1]);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (i0 + k < a.n_rays) a.ray_offsets[i0 + k + 1] = before + c[k];
     __syncthreads();
-    if (tid == 1023) carry_s = prefix;
+    if (tid == 1023) carry_s = before + c[kScanItems - 1];
     __syncthreads();
   }
   n_empty = __reduce_add_sync(kFull, n_empty);

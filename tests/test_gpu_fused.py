@@ -154,7 +154,7 @@ def test_fused_backward_matches_layered(cuda, n, density_only):
     gs, g3 = torch.randn(n, generator=g).to(cuda), torch.randn(n, 3, generator=g).to(cuda)
     gts, gtb = torch.randn(n, generator=g).to(cuda), torch.randn(n, generator=g).to(cuda)
     res = {}
-    for mode in ("bf16", "bf16_fused"):
+    for mode in ("fp32", "bf16", "bf16_fused"):
         m = make_model(p, n_img, cuda, mode)
         e = m._engine()
         f = e.fwd(n, density_only, x=x, img_idx=None if density_only else img)
@@ -163,14 +163,17 @@ def test_fused_backward_matches_layered(cuda, n, density_only):
                    g_tb=None if density_only else gtb, grads_struct=gstruct, want_gx=density_only)
         torch.cuda.synchronize()
         res[mode] = (views, gx)
-    va, vb = res["bf16"][0], res["bf16_fused"][0]
+    v32, va, vb = res["fp32"][0], res["bf16"][0], res["bf16_fused"][0]
     for k in va:
         if float(va[k].abs().max()) == 0.0:
             assert float(vb[k].abs().max()) == 0.0, k
             continue
         assert torch.isfinite(vb[k]).all(), k
-        # both bf16 paths sit ~1e-1 (relative L2) from the fp32 gradient of these random upstream gradients (tools/diag_grad_noise.py: 0.17 vs
-        # 0.17 on transient_mlp.0 at n=100); their mutual distance is rounding-flip noise that shrinks with n
-        assert l2(vb[k], va[k]) <= (4e-2 if n <= 1000 else 2e-2), (k, l2(vb[k], va[k]))
+        # With these random upstream gradients both bf16 paths sit ~1e-1 (relative L2) from the fp32 kernels
+        # (tools/diag_grad_noise.py); their mutual distance is de-correlated rounding, a fraction of that.  The bar: the fused
+        # chain is as close to fp32 as the layer-by-layer chain is, and the two agree to within that noise.
+        d_layer, d_fused = l2(va[k], v32[k]), l2(vb[k], v32[k])
+        assert d_fused <= 1.25 * d_layer + 5e-3, (k, d_fused, d_layer)
+        assert l2(vb[k], va[k]) <= max(5e-2, 0.6 * d_layer), (k, l2(vb[k], va[k]), d_layer)
     if density_only:
         assert l2(res["bf16_fused"][1], res["bf16"][1]) <= 2e-2

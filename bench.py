@@ -136,6 +136,7 @@ def run_reference(args, rank, world):
 
 # --------------------------------------------------------------------------------------------------------------------
 RENDER_HW = 1024
+RENDER_CHUNK = 131072
 
 
 def render_arm(args, model, rank, world, dev, barrier, max_over_ranks):
@@ -156,7 +157,8 @@ def render_arm(args, model, rank, world, dev, barrier, max_over_ranks):
             barrier()
             e0.record()
             res, n_samples = sat_rendering.render_image(model, None, define_satrays_from_tensors(rays, ts), None, None,
-                                                        epoch_idx=EPOCH_IDX, chunk=65536, render_step_size=2.0 / N_SAMPLES, eval=True)
+                                                        epoch_idx=EPOCH_IDX, chunk=RENDER_CHUNK, render_step_size=2.0 / N_SAMPLES, eval=True,
+                                                        static=args.precision == "bf16_fused")   # sync-free: counts stay on the device
             out = torch.cat([res["rgb"], res["geo_shadows"], res["depth"]], dim=1).view(r1 - r0, RENDER_HW, 5)
             out = gather_rows(out, world)
             e1.record()
@@ -165,7 +167,7 @@ def render_arm(args, model, rank, world, dev, barrier, max_over_ranks):
     model.train()
     return {"metric": "render_rays_per_sec", "value": RENDER_HW * RENDER_HW / (ms * 1e-3), "unit": "rays/s", "ms_per_image": ms,
             "workload": f"BASELINE configs[3]: {RENDER_HW}x{RENDER_HW} eval render (rgb + geo_shadows + depth), n_samples={N_SAMPLES}, "
-                        f"65536-ray chunks, rows sharded over {world} GPU(s), gathered on rank 0",
+                        f"{RENDER_CHUNK}-ray chunks, rows sharded over {world} GPU(s), gathered on rank 0",
             "kept_camera_samples_rank0": int(n_samples)}
 
 

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeonerf_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 COMP_COLS = 12
 OUT_COLS = 21
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16_FUSED = 0, 1, 2, 3
@@ -140,6 +140,11 @@ class DwArgs(C.Structure):
                 ("dw", P), ("lddw", I64), ("db", P)]
 
 
+class AdamArgs(C.Structure):
+    _fields_ = [("param", P), ("grad", P), ("exp_avg", P), ("exp_avg_sq", P), ("n", I64), ("step", P),
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("grad_scale", F32)]
+
+
 # every symbol include/eonerf_b200.h declares: name -> (restype, argtypes)
 _ARGS = lambda T: [C.POINTER(T), P]
 SYMBOLS = {
@@ -174,6 +179,7 @@ SYMBOLS = {
     "eonerf_ambient_bwd": (C.c_int, _ARGS(AmbientBwdArgs)),
     "eonerf_linear_fwd": (C.c_int, _ARGS(LinearArgs)),
     "eonerf_linear_dw": (C.c_int, _ARGS(DwArgs)),
+    "eonerf_adam_step": (C.c_int, _ARGS(AdamArgs)),
 }
 
 _lib = None

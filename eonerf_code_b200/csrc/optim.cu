@@ -1,0 +1,71 @@
+// Adam step of the training loop (/root/reference/train_eonerf.py:57,158-160: torch.optim.Adam(lr=5e-4), default betas /
+// eps, no weight decay, no amsgrad) over ONE flat fp32 buffer: every parameter, its gradient and both moments are views of
+// four flat arrays, so the whole update is a single 128-bit-vectorised pass (680 k floats) instead of torch's per-tensor
+// multi-tensor launches.  The step counter lives on the device (a captured CUDA graph replays the same launch); the bias
+// corrections are computed from it in double precision, as torch.optim.Adam's default path does from Python floats.
+#include "common.cuh"
+
+namespace eonerf {
+
+// one thread: step += 1, then this step's scalars in DOUBLE precision as torch.optim.Adam's default (non-capturable) path
+// computes them from Python floats: step[1] = lr / (1 - beta1^t), step[2] = sqrt(1 - beta2^t)
+__global__ void adam_tick_kernel(EonerfAdamArgs a) {
+  const float t = a.step[0] + 1.0f;
+  a.step[0] = t;
+  a.step[1] = (float)(a.lr / (1.0 - pow(a.beta1, (double)t)));
+  a.step[2] = (float)sqrt(1.0 - pow(a.beta2, (double)t));
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(EonerfAdamArgs a) {
+  const float step_size = a.step[1], bc2_sqrt = a.step[2];
+  const int64_t n4 = a.n >> 2;
+  const float b2 = (float)a.beta2, omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2), gs = a.grad_scale, eps = (float)a.eps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p = reinterpret_cast<float4*>(a.param)[i];
+    const float4 g = reinterpret_cast<const float4*>(a.grad)[i];
+    float4 m = reinterpret_cast<float4*>(a.exp_avg)[i];
+    float4 v = reinterpret_cast<float4*>(a.exp_avg_sq)[i];
+#define EO_ADAM(c)                                                   \
+  {                                                                  \
+    const float gc = g.c * gs;                                       \
+    m.c = m.c + (gc - m.c) * omb1;                 /* lerp_ */        \
+    v.c = v.c * b2 + gc * gc * omb2;               /* mul_ + addcmul_ */ \
+    const float denom = sqrtf(v.c) / bc2_sqrt + eps;                 \
+    p.c = p.c - step_size * (m.c / denom);         /* addcdiv_ */     \
+  }
+    EO_ADAM(x) EO_ADAM(y) EO_ADAM(z) EO_ADAM(w)
+    reinterpret_cast<float4*>(a.param)[i] = p;
+    reinterpret_cast<float4*>(a.exp_avg)[i] = m;
+    reinterpret_cast<float4*>(a.exp_avg_sq)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {            // tail (n not a multiple of 4)
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float gc = a.grad[i] * gs;
+    const float m = a.exp_avg[i] + (gc - a.exp_avg[i]) * omb1;
+    const float v = a.exp_avg_sq[i] * b2 + gc * gc * omb2;
+    a.exp_avg[i] = m;
+    a.exp_avg_sq[i] = v;
+    a.param[i] -= step_size * (m / (sqrtf(v) / bc2_sqrt + eps));
+  }
+#undef EO_ADAM
+}
+
+}  // namespace eonerf
+
+using namespace eonerf;
+
+extern "C" int eonerf_adam_step(const EonerfAdamArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->n >= 0 && a->param && a->grad && a->exp_avg && a->exp_avg_sq && a->step, "adam_step: bad arguments");
+  EO_REQUIRE((((uintptr_t)a->param | (uintptr_t)a->grad | (uintptr_t)a->exp_avg | (uintptr_t)a->exp_avg_sq) & 15) == 0,
+             "adam_step: the flat buffers must be 16-byte aligned");
+  if (a->n == 0) return EONERF_OK;
+  cudaStream_t s = as_stream(stream);
+  int64_t blocks = div_up(a->n >> 2, 256);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_tick_kernel<<<1, 1, 0, s>>>(*a);
+  EO_LAUNCH_CHECK();
+  adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}

@@ -403,10 +403,12 @@ class _FieldFn(torch.autograd.Function):
     """EONerfMLP.forward / query_density / VanillaNeRFRadianceField.forward on explicit positions."""
 
     @staticmethod
-    def forward(ctx, engine, density_only, x, img_idx, cond_dirs, *params):
+    def forward(ctx, grad_on, engine, density_only, x, img_idx, cond_dirs, *params):
+        """grad_on: torch.is_grad_enabled() at the call site (inside forward() autograd always reports it off; under
+        torch.no_grad() nothing is stashed)."""
         _need_cuda(x)
         n = x.shape[0]
-        out = engine.fwd(n, density_only, x=x, img_idx=img_idx, cond_dirs=cond_dirs, keep=any(ctx.needs_input_grad))
+        out = engine.fwd(n, density_only, x=x, img_idx=img_idx, cond_dirs=cond_dirs, keep=grad_on and any(ctx.needs_input_grad))
         ctx.engine, ctx.density_only, ctx.n, ctx.out = engine, density_only, n, out
         ctx.x_needs_grad = x.requires_grad
         ctx.params = params
@@ -426,7 +428,7 @@ class _FieldFn(torch.autograd.Function):
                    grads_struct=gstruct, want_gx=ctx.x_needs_grad)
         if e.grad_sync is not None and not direct:
             e.grad_sync(flat)
-        return (None, None, gx, None, None) + _grads_tuple(e, views, ctx.params, direct)
+        return (None, None, None, gx, None, None) + _grads_tuple(e, views, ctx.params, direct)
 
 
 class _AmbientFn(torch.autograd.Function):
@@ -461,7 +463,7 @@ class _CameraPassFn(torch.autograd.Function):
     Output comp[B,12]: 0:3 albedo, 3 depth, 4 beta(+0.05), 5 transient_s, 6:9 ambient (not yet x0.2), 9 sum(w)."""
 
     @staticmethod
-    def forward(ctx, engine, only_depth, origins, viewdirs, sundirs, img_idx, ri, ts, te, offs, n_dev, *params):
+    def forward(ctx, grad_on, engine, only_depth, origins, viewdirs, sundirs, img_idx, ri, ts, te, offs, n_dev, *params):
         """n_dev: None, or int64[1] on the device = live sample count P (ri / ts / te then have their full capacity)."""
         _need_cuda(origins, viewdirs, ri, ts, te)
         for t in (ts, te):
@@ -470,7 +472,7 @@ class _CameraPassFn(torch.autograd.Function):
         B, P = origins.shape[0], ts.numel()
         ri = ri.contiguous()
         f = engine.fwd(P, density_only=only_depth, rays=(origins, viewdirs, ri, ts, te),
-                       img_idx=None if only_depth else _img_idx_2d(img_idx), want_z=True, keep=any(ctx.needs_input_grad),
+                       img_idx=None if only_depth else _img_idx_2d(img_idx), want_z=True, keep=grad_on and any(ctx.needs_input_grad),
                        n_dev=n_dev)
         set_last_t_end(te, offs)                                    # after z / positions were taken
         amb = amb_stash = None
@@ -506,7 +508,7 @@ class _CameraPassFn(torch.autograd.Function):
         ctx.keep = None
         if e.grad_sync is not None and not direct:
             e.grad_sync(flat)
-        return (None,) * 11 + _grads_tuple(e, views, ctx.params, direct)
+        return (None,) * 12 + _grads_tuple(e, views, ctx.params, direct)
 
 
 class _SunPassFn(torch.autograd.Function):
@@ -514,7 +516,7 @@ class _SunPassFn(torch.autograd.Function):
     query, transmittance in front of the last kept sample.  Differentiable in `depth` and the parameters."""
 
     @staticmethod
-    def forward(ctx, engine, origins, viewdirs, sundirs, depth, n_samples, u_sun, z_steps, info, static, *params):
+    def forward(ctx, grad_on, engine, origins, viewdirs, sundirs, depth, n_samples, u_sun, z_steps, info, static, *params):
         """static=True: no host read of the sun-sample count Q (buffers keep their capacity, kernels read Q on the device)."""
         _need_cuda(origins, viewdirs, sundirs, depth)
         B, dev = origins.shape[0], origins.device
@@ -530,7 +532,7 @@ class _SunPassFn(torch.autograd.Function):
         ri2, ts2, te2, sc_ppr, offs2, stats2 = sample_compact(sun[:, 0:3], sun[:, 3:6], None, u_sun, z_steps)
         n_dev = stats2[0:1] if static else None
         Q = ts2.numel() if static else int(stats2[0])               # eager: the one host sync of the sun pass
-        f2 = engine.fwd(Q, density_only=True, rays=(sun[:, 0:3], sun[:, 3:6], ri2, ts2, te2), keep=any(ctx.needs_input_grad),
+        f2 = engine.fwd(Q, density_only=True, rays=(sun[:, 0:3], sun[:, 3:6], ri2, ts2, te2), keep=grad_on and any(ctx.needs_input_grad),
                         n_dev=n_dev)
         geo = torch.empty(B, 1, dtype=torch.float32, device=dev)
         a = K.ShadowFwdArgs(_p(ts2), _p(te2), _p(f2["sigma"]), _p(offs2), B, Q, _p(geo))
@@ -558,7 +560,7 @@ class _SunPassFn(torch.autograd.Function):
         ctx.keep = None
         if e.grad_sync is not None and not direct:
             e.grad_sync(flat)
-        return (None, None, None, None, g_depth, None, None, None, None, None) + _grads_tuple(e, views, ctx.params, direct)
+        return (None, None, None, None, None, g_depth, None, None, None, None, None) + _grads_tuple(e, views, ctx.params, direct)
 
 
 class _EpilogueFn(torch.autograd.Function):

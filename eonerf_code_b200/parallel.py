@@ -28,27 +28,33 @@ def shard_bounds(n, rank, world):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def flat_offsets(params, align=4):
+    """Element offsets of the parameters inside a flat buffer; every tensor starts on a 16-byte boundary (align=4 floats),
+    as separately allocated tensors do (the kernels use 128-bit accesses on rows of some of them).  -> (offsets, total)."""
+    offs, off = [], 0
+    for p in params:
+        offs.append(off)
+        off += (p.numel() + align - 1) // align * align
+    return offs, off
+
+
 class FlatGrads:
     """Makes every parameter's .grad a view of ONE flat fp32 buffer, so the gradient all-reduce is a single collective
     and optimizer.zero_grad(set_to_none=False) is a single memset."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+        self.offsets, total = flat_offsets(self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
 
     def zero(self):
         self.flat.zero_()
-        off = 0
-        for p in self.params:          # autograd may have replaced a .grad: re-point it at the flat buffer
+        for p, off in zip(self.params, self.offsets):   # autograd may have replaced a .grad: re-point it at the flat buffer
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
 
     def all_reduce_mean(self, world, group=None):
         if world > 1:

@@ -46,7 +46,7 @@ class EONerfMLP(nn.Module, _EngineMixin):
     # --- point-wise API (eonerf.py:141-170) ---------------------------------------------------
     def query_density(self, x):
         e = self._engine()
-        return ops._FieldFn.apply(e, True, x, None, None, *e.tensors())
+        return ops._FieldFn.apply(torch.is_grad_enabled(), e, True, x, None, None, *e.tensors())
 
     def query_opacity(self, x, step_size):
         return self.query_density(x) * step_size
@@ -54,7 +54,7 @@ class EONerfMLP(nn.Module, _EngineMixin):
     def forward(self, x, sun_dirs=None, img_indices=None):
         e = self._engine()
         p = e.tensors()
-        sigma, albedo, ts, tb = ops._FieldFn.apply(e, False, x, img_indices.reshape(-1, 1), None, *p)
+        sigma, albedo, ts, tb = ops._FieldFn.apply(torch.is_grad_enabled(), e, False, x, img_indices.reshape(-1, 1), None, *p)
         ambient = ops._AmbientFn.apply(e, sun_dirs, *p)
         return sigma, albedo, ambient, ts, tb
 
@@ -63,7 +63,7 @@ class EONerfMLP(nn.Module, _EngineMixin):
         e = self._engine()
         n_rays = chunk_rays.origins.shape[0]
         offs = ops.pack_info(ray_indices, n_rays)
-        return ops._CameraPassFn.apply(e, only_depth, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs,
+        return ops._CameraPassFn.apply(torch.is_grad_enabled(), e, only_depth, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs,
                                        chunk_rays.img_idx, ray_indices, t_starts, t_ends, offs, None, *e.tensors())
 
     def render_depth(self, chunk_rays, t_starts, t_ends, ray_indices):

@@ -88,7 +88,7 @@ class VanillaNeRFRadianceField(nn.Module, _EngineMixin):
 
     def query_density(self, x):
         e = self._engine()
-        return ops._FieldFn.apply(e, True, x, None, None, *e.tensors())
+        return ops._FieldFn.apply(torch.is_grad_enabled(), e, True, x, None, None, *e.tensors())
 
     def query_opacity(self, x, step_size):
         return self.query_density(x) * step_size
@@ -97,5 +97,5 @@ class VanillaNeRFRadianceField(nn.Module, _EngineMixin):
         if condition is None:
             raise ValueError("view directions are required (mlp.py:153-165)")
         e = self._engine()
-        sigma, rgb = ops._FieldFn.apply(e, False, x, None, condition, *e.tensors())
+        sigma, rgb = ops._FieldFn.apply(torch.is_grad_enabled(), e, False, x, None, condition, *e.tensors())
         return rgb, sigma

@@ -52,7 +52,7 @@ def compute_geometric_shadows(chunk_rays, depth, radiance_field, occupancy_grid,
     e = radiance_field._engine()
     n = n_samples_from_step(sampling_args["render_step_size"])
     info = {} if info is None else info
-    geo = ops._SunPassFn.apply(e, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs, depth, n, u, z_steps, info,
+    geo = ops._SunPassFn.apply(torch.is_grad_enabled(), e, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs, depth, n, u, z_steps, info,
                                False, *e.tensors())
     return geo, info["sc_pts_per_ray"]
 
@@ -113,7 +113,7 @@ def render_image(
             if n_empty:                                     # :260-262 re-draw with near=None
                 ri, ts, te, _, offs, _ = _sample(chunk_rays.origins, chunk_rays.viewdirs, n, None, us.get("u_cam2"), z_steps)
             n_rendering_samples += ts.numel()
-        comp = ops._CameraPassFn.apply(e, only_depth, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs,
+        comp = ops._CameraPassFn.apply(torch.is_grad_enabled(), e, only_depth, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs,
                                        chunk_rays.img_idx, ri, ts, te, offs, n_dev, *e.tensors())
         if only_depth:                                      # :227-249
             outs.append(comp[:, 3:4])
@@ -121,7 +121,7 @@ def render_image(
         geo = sc_ppr = None
         if epoch_idx >= 2:                                  # :269-276
             info = {}
-            geo = ops._SunPassFn.apply(e, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs, comp[:, 3:4], n,
+            geo = ops._SunPassFn.apply(torch.is_grad_enabled(), e, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs, comp[:, 3:4], n,
                                        us.get("u_sun"), z_steps, info, static, *e.tensors())
             sc_ppr = info["sc_pts_per_ray"]
         rad = radiance_field.radiometricT_enc.weight if radiance_field.radiometric_normalization else None

@@ -15,6 +15,7 @@ import torch
 from . import _capi as K
 from . import metrics, sat_rendering
 from .datasets.satellite import define_satrays_from_tensors
+from .optim import FlatAdam
 from .parallel import FlatGrads
 
 
@@ -29,8 +30,9 @@ class TrainStep:
         if graph and radiance_field.precision != "bf16_fused":
             raise RuntimeError("graph=True needs precision='bf16_fused' (device-side sample counts)")
         params = list(radiance_field.parameters())
-        self.optimizer = torch.optim.Adam(params, lr=lr, capturable=True, foreach=True) if graph else torch.optim.Adam(params, lr=lr)
         self.grads = FlatGrads(params)
+        # torch.optim.Adam's state layout, one kernel over flat buffers (device-side step counter: graph-capturable)
+        self.optimizer = FlatAdam(params, self.grads.flat, lr=lr)
         # backward kernels accumulate straight into the flat gradient buffer (no per-parameter autograd adds)
         radiance_field._engine().use_grad_sink({k: p.grad for k, p in radiance_field.named_parameters()})
         self._graphs = {}
@@ -58,9 +60,7 @@ class TrainStep:
         return loss.detach(), n_rendered
 
     def _update(self, averaged):
-        if self.world > 1 and not averaged:
-            self.grads.flat.div_(self.world)
-        self.optimizer.step()
+        self.optimizer.step(grad_scale=1.0 if (averaged or self.world == 1) else 1.0 / self.world)
 
     def eager(self, rays, ts, pixels, epoch_idx):
         """rays [B,11], ts [B,1] int64, pixels [B,3] on the device -> (loss tensor, n_rendering_samples int)."""

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 8
+#define EONERF_ABI_VERSION 9
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -362,6 +362,23 @@ typedef struct {
   float* db;                        /* accumulated into, or NULL */
 } EonerfDwArgs;
 int eonerf_linear_dw(const EonerfDwArgs* a, eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser step of the training loop.  Replaces torch.optim.Adam(lr=5e-4).step() (train_eonerf.py:57,158-160; default
+ * betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad) for parameters, gradients and moments that are views of four
+ * flat fp32 buffers (16-byte aligned).  `step` points to 4 DEVICE floats: [0] the step counter (torch keeps Adam's step as
+ * an fp32 tensor), incremented by one per call; [1], [2] scratch for this step's lr/(1-beta1^t) and sqrt(1-beta2^t), which
+ * a one-thread kernel computes in double precision before the update kernel: the same two launches can be replayed from a
+ * CUDA graph.  grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  int64_t n;
+  float* step;
+  double lr; double beta1; double beta2; double eps;
+  float grad_scale;
+} EonerfAdamArgs;
+int eonerf_adam_step(const EonerfAdamArgs* a, eonerf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -120,3 +120,46 @@ def test_graph_train_step_matches_eager_steps(cuda):
         d = (p_g[k] - p_e[k]).abs()                      # atomic-order round-off decides the sign, so compare in bulk
         assert float(d.max()) <= 2 * lr * steps + 1e-7, k
         assert float((d > 0.5 * lr).float().mean()) < 0.05, (k, float((d > 0.5 * lr).float().mean()))
+
+
+def test_flat_adam_matches_torch_adam(cuda):
+    """csrc/optim.cu vs torch.optim.Adam (the reference's optimiser, train_eonerf.py:57): same parameters and moments after
+    several steps on the same gradients, and a state_dict torch.optim.Adam can load."""
+    from eonerf_code_b200.optim import FlatAdam
+    from eonerf_code_b200.parallel import FlatGrads
+    torch.manual_seed(0)
+    shapes = [(19, 4), (19, 9), (256, 63), (256,), (1, 256), (1,), (3, 128), (128, 260)]
+    pa = [torch.nn.Parameter(torch.randn(*s, device=cuda)) for s in shapes]
+    pb = [torch.nn.Parameter(t.detach().clone()) for t in pa]
+    fg = FlatGrads(pa)
+    opt_a = FlatAdam(pa, fg.flat, lr=5e-4)
+    opt_b = torch.optim.Adam(pb, lr=5e-4)
+    for it in range(7):
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(b) * (10.0 ** (it - 3))
+            a.grad.copy_(g)
+            b.grad = g.clone()
+        opt_a.step()
+        opt_b.step()
+    for a, b in zip(pa, pb):
+        close(a, b, 2e-6, 1e-7)
+        for key in ("exp_avg", "exp_avg_sq"):           # fma contraction may differ from torch's kernels: fp32 round-off only
+            ref = opt_b.state[b][key]
+            close(opt_a.state[a][key], ref, 1e-5, 1e-6 * float(ref.abs().max()))
+        assert float(opt_a.state[a]["step"]) == 7.0
+    # checkpoint round trip in both directions (train_eonerf.py:185-191 saves optimizer.state_dict())
+    opt_c = torch.optim.Adam([torch.nn.Parameter(t.detach().clone()) for t in pa], lr=5e-4)
+    opt_c.load_state_dict(opt_a.state_dict())
+    opt_a.load_state_dict(opt_b.state_dict())
+    for a, b in zip(pa, pb):
+        close(opt_a.state[a]["exp_avg_sq"], opt_b.state[b]["exp_avg_sq"], 0.0, 0.0)
+        assert opt_a.state[a]["exp_avg"].data_ptr() >= opt_a.flat_exp_avg.data_ptr()     # still views of the flat buffer
+    # gradient scaling (data-parallel mean after a sum all-reduce)
+    for a, b in zip(pa, pb):
+        g = torch.randn_like(b)
+        a.grad.copy_(2.0 * g)
+        b.grad = g.clone()
+    opt_a.step(grad_scale=0.5)
+    opt_b.step()
+    for a, b in zip(pa, pb):
+        close(a, b, 2e-6, 1e-7)

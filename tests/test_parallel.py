@@ -42,8 +42,9 @@ def _worker(rank, world, port, out):
     loss.backward()
     flat.all_reduce_mean(world)
     rows = parallel.gather_rows(out_l.detach()[:, :4].contiguous(), world)
-    if rank == 0:
-        torch.save({"grad": flat.flat.clone(), "rows": rows, "bounds": (b, e)}, out)
+    if rank == 0:       # per-parameter views (the flat buffer pads every tensor to a 16-byte boundary)
+        torch.save({"grad": torch.cat([q.grad.reshape(-1) for q in params]), "rows": rows, "bounds": (b, e),
+                    "flat_numel": flat.flat.numel(), "offsets": flat.offsets}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -70,6 +71,7 @@ def test_sharded_gradients_match_single_process(tmp_path):
     ref = torch.cat([(torch.zeros_like(q) if gq is None else gq).reshape(-1) for q, gq in zip(params, grads)])
     scale = float(ref.abs().max())
     assert float((got["grad"] - ref).abs().max()) <= 2e-5 * scale
+    assert all(o % 4 == 0 for o in got["offsets"]) and got["flat_numel"] >= ref.numel()
     assert torch.allclose(got["rows"], out_full.detach()[:, :4], rtol=1e-6, atol=1e-7)
 
 

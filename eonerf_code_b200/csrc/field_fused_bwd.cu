@@ -460,19 +460,31 @@ __global__ void __launch_bounds__(256) class_grad_blocked_kernel(const uint8_t* 
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   int cur = -1;
-  for (int64_t m = m_begin + rsub; m < m_end; m += 16) {
-    const int c = __ldg(cls + m);
-    if (c != cur) {
-      if (cur >= 0) {
+  for (int64_t m0 = m_begin + rsub; m0 < m_end; m0 += 64) {   // four rows in flight per thread
+    int cc[4];
+    uint4 gv[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { atomicAdd(dst + (int64_t)cur * kHid + sub * 8 + e, acc[e]); acc[e] = 0.f; }
-      }
-      cur = c;
+    for (int u = 0; u < 4; ++u) {
+      const int64_t m = m0 + 16 * u;
+      const bool ok = m < m_end;
+      cc[u] = ok ? __ldg(cls + m) : -1;
+      gv[u] = ok ? __ldg(blk_chunk(G, 4, m, 16 + sub)) : make_uint4(0, 0, 0, 0);
     }
-    float v[8];
-    unpack8(__ldg(blk_chunk(G, 4, m, 16 + sub)), v);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    for (int u = 0; u < 4; ++u) {
+      if (cc[u] < 0) continue;
+      if (cc[u] != cur) {
+        if (cur >= 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { atomicAdd(dst + (int64_t)cur * kHid + sub * 8 + e, acc[e]); acc[e] = 0.f; }
+        }
+        cur = cc[u];
+      }
+      float v[8];
+      unpack8(gv[u], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
   }
   if (cur >= 0) {
 #pragma unroll

@@ -6,9 +6,11 @@ tail -3 gpurun_out/pytest_gpu.log
 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -4 gpurun_out/smoke.log
 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.log
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; cat gpurun_out/bench_ref.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
+python tools/bench_render.py > gpurun_out/bench_render.log 2>&1; head -8 gpurun_out/bench_render.log
+# launch list of the default (CUDA graph) bench: kernels inside graph replays are profiled node by node
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-render > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
 ncu --set full --clock-control none --import-source on -k regex:'fused_fwd_kernel|fused_bwd_kernel|gemm_tn_blocked_kernel' -s 12 -c 6 \
-    -o gpurun_out/fused_full -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
-ncu --set full --clock-control none --import-source on -k regex:'composite_fwd_kernel|composite_bwd_kernel|shadow_fwd_kernel|shadow_bwd_kernel|sample_scatter_kernel|heads_dw_blocked_kernel|class_grad_blocked_kernel' -s 14 -c 10 \
-    -o gpurun_out/render_full -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_render.log 2>&1; echo "ncu render exit $?"
+    -o gpurun_out/fused_full -f python bench.py --steps 1 --warmup 3 --no-cpu --no-render --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
+ncu --set full --clock-control none --import-source on -k regex:'composite_fwd_kernel|composite_bwd_kernel|shadow_fwd_kernel|shadow_bwd_kernel|sample_scatter_kernel' -c 70 \
+    -o gpurun_out/render_full -f python tools/bench_render.py > gpurun_out/ncu_render.log 2>&1; echo "ncu render exit $?"

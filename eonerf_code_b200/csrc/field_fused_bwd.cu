@@ -71,8 +71,11 @@ static_assert(4096 + 2 * 128 * 16 <= kConstBytes, "row scalars do not fit");
 
 // keep[j] of a packed bf16 pair: sign-bit layout written by the forward (column 2j -> bit 15-j, column 2j+1 -> bit 31-j)
 __device__ __forceinline__ uint32_t apply_mask(uint32_t pk, uint32_t m, int j) {
-  const uint32_t sel = ((m << j) & 0x80008000u) >> 15;       // 0x00010001 pattern of the kept halves
-  return pk & (sel * 0xFFFFu);
+  // bits 15 and 31 of (m << j) are the keep flags of the pair: PRMT in sign-replicate mode (selector nibble | 8) spreads the
+  // top bit of bytes 1 and 3 over the low and the high half -> 0xFFFF per kept half, one instruction
+  uint32_t sel;
+  asm("prmt.b32 %0, %1, %2, 0xBB99;" : "=r"(sel) : "r"(m << j), "r"(0u));
+  return pk & sel;
 }
 
 template <int kCG, int kMC>
@@ -234,8 +237,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           mbar_wait(&acc_full[slot], (cph >> slot) & 1u);
           cph ^= 1u << slot;
           tc_fence_after();
-          if (e == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, kEpiThreads);
           const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + col0;
           if (d.kind == 4) {
             // ---- final stage: g_enc = acc[0:64] + G_ENC5, positional-encoding backward (half 0 owns the 64 columns) ----
@@ -274,27 +275,22 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
             }
             tc_fence_before();
             named_bar_sync(1, kEpiThreads);
-            if (e == 0) tma_store_commit();                  // keep one bulk group per (stage, slot)
             continue;
           }
           const bool write_out = !(d.kind == 3 && half == 1);   // encoding part: only 64 real columns
-#pragma unroll 1
-          for (int c = 0; c < cpt / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c * 32, v);
+          // one 32-column chunk: accumulator (+ sigma rank-1 term) -> bf16 -> ReLU mask -> next A operand in shared memory
+          auto chunk = [&](uint32_t (&v)[32], const int c) {
             const uint32_t m = c == 0 ? mw.x : (c == 1 ? mw.y : (c == 2 ? mw.z : mw.w));
-            float w[32];
+            uint32_t pk[16];
             if (d.kind == 2) {
               const uint32_t sw = s_hw + (uint32_t)(col0 + c * 32) * 4u;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) lds_f4(sw + j * 16, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-            }
-            tmem_ld_wait();
-            uint32_t pk[16];
-            if (d.kind == 2) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                pk[j] = apply_mask(pack_bf16(fmaf(dsig, w[2 * j], __uint_as_float(v[2 * j])), fmaf(dsig, w[2 * j + 1], __uint_as_float(v[2 * j + 1]))), m, j);
+              for (int j = 0; j < 8; ++j) {
+                float w0, w1, w2, w3;
+                lds_f4(sw + j * 16, w0, w1, w2, w3);
+                pk[2 * j] = apply_mask(pack_bf16(fmaf(dsig, w0, __uint_as_float(v[4 * j])), fmaf(dsig, w1, __uint_as_float(v[4 * j + 1]))), m, 2 * j);
+                pk[2 * j + 1] = apply_mask(pack_bf16(fmaf(dsig, w2, __uint_as_float(v[4 * j + 2])), fmaf(dsig, w3, __uint_as_float(v[4 * j + 3]))), m, 2 * j + 1);
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) pk[j] = apply_mask(pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), m, j);
@@ -305,6 +301,23 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
               const int ch0 = (colg & 63) >> 3;
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) sts_u4(blk + blk_off(r, ch0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+            }
+          };
+          {   // software pipeline: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+            uint32_t va[32], vb[32];
+            tmem_ld32(taddr, va);
+            tmem_ld_wait_dep(va);
+            tmem_ld32(taddr + 32, vb);
+            chunk(va, 0);
+            tmem_ld_wait_dep(vb);
+            if (cpt == 128) tmem_ld32(taddr + 64, va);
+            chunk(vb, 1);
+            if (cpt == 128) {
+              tmem_ld_wait_dep(va);
+              tmem_ld32(taddr + 96, vb);
+              chunk(va, 2);
+              tmem_ld_wait_dep(vb);
+              chunk(vb, 3);
             }
           }
           if (d.kind == 1) {
@@ -332,6 +345,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           }
           tc_fence_before();
           fence_proxy_async();
+          // the OTHER slot's latest G store (issued one epilogue ago) must have finished reading shared memory before the
+          // next epilogue overwrites that slot: checked here, so one named barrier per stage is enough
+          if (e == 0) tma_store_wait_read<0>();
           named_bar_sync(1, kEpiThreads);
           if (e == 0) {
             if (i + 1 < p.n_prog) signal_act_ready<kCG>(B, slot, rank);

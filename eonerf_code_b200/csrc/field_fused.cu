@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;                    // row of the tile
+    const int store_id = store_thread_id(e);        // 0..3: this thread owns the bulk stores of that output block; else -1
     const uint32_t s_cst = smem_u32(cst);
     const uint32_t s_part = smem_u32(part);
     uint32_t cph = 0;                               // bit `slot` = phase of acc_full[slot]
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
     for (int64_t it = it0; it < n_items; it += it_stride) {
       uint32_t cls_pack = 0;                        // image index of this row in slot 0 (low 16 bits) / slot 1
       // ---- positional encoding of both tiles ----
-      if (e == 0) tma_store_wait_read<0>();
+      if (store_id >= 0) tma_store_wait_read<0>();
       named_bar_sync(1, kEpiThreads);
       for (int slot = 0; slot < 2; ++slot) {
         const int64_t tile = 2 * kCl * it + 2 * rank + slot;
@@ -164,17 +165,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
       tc_fence_before();
       fence_proxy_async();
       named_bar_sync(1, kEpiThreads);
-      if (e == 0) {
+      // after-barrier duties are split over two threads of different warps (neither in a warp that writes head outputs), so
+      // no single warp arrives late at the next barrier: one signals the MMA issuer, the other owns the stash stores
+      if (e == kSignalThread) {
         signal_act_ready<kCG>(B, 0, rank);
         signal_act_ready<kCG>(B, 1, rank);
-        if (kTrain) {
-          for (int slot = 0; slot < 2; ++slot) {
-            const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-            if (tile < n_tiles)
-              bulk_store(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
-          }
-          tma_store_commit();
+      }
+      if (kTrain && store_id >= 0) {
+        for (int slot = store_id; slot < 2; slot += kStoreThreads) {
+          const int64_t tile = 2 * kCl * it + 2 * rank + slot;
+          if (tile < n_tiles) bulk_store(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
         }
+        tma_store_commit();
       }
 
       // ---- the layers ----
@@ -326,19 +328,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           // the OTHER slot's latest stash store (issued one epilogue ago) must have finished reading shared memory before the
           // next epilogue overwrites that slot
           EO_TN(td);
-          if (kTrain && e == 0) tma_store_wait_read<0>();
+          if (kTrain && store_id >= 0) tma_store_wait_read<0>();
           EO_TN(te);
           { EO_T0(); named_bar_sync(1, kEpiThreads); if (e == 32) EO_T1(5); }
           EO_TN(tf);
-          if (e == 0) {
-            if (s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
-            if (kTrain && tile < n_tiles && !(p.training & 2)) {
-              const int nb = d.halves * 2;
-              for (int bb = 0; bb < nb; ++bb)
-                bulk_store(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes,
-                           kBlkBytes);
-              tma_store_commit();
-            }
+          if (e == kSignalThread && s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
+          if (kTrain && store_id >= 0 && tile < n_tiles && !(p.training & 2)) {
+            const int nb = d.halves * 2;                     // 16 KB blocks store_id, store_id + kStoreThreads, ... of the layer's output
+            for (int bb = store_id; bb < nb; bb += kStoreThreads)
+              bulk_store(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes, kBlkBytes);
+            tma_store_commit();
           }
           if (valid && half == 0 && d.kind != 0) {
             float p0 = 0.f, p1 = 0.f;
@@ -359,7 +358,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         }
       }
     }
-    if (e == 0) tma_store_wait_all();
+    if (store_id >= 0) tma_store_wait_all();
   }
   fused_teardown<kCG, kMC>(tmem_base);
 }

@@ -109,12 +109,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
+    const int store_id = store_thread_id(e);
     const uint32_t s_hw = smem_u32(hw);
     uint32_t cph = 0;
     uint64_t* const acc_full = B.acc_full;
     for (int64_t it = it0; it < n_items; it += it_stride) {
       // ---- head gradients -> first G of the chain ----
-      if (e == 0) tma_store_wait_read<0>();
+      if (store_id >= 0) tma_store_wait_read<0>();
       named_bar_sync(1, kEpiThreads);
       for (int slot = 0; slot < 2; ++slot) {
         const int64_t tile = 2 * kCl * it + 2 * rank + slot;
@@ -194,17 +195,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
       }
       fence_proxy_async();
       named_bar_sync(1, kEpiThreads);
-      if (e == 0) {
+      if (e == kSignalThread) {
         signal_act_ready<kCG>(B, 0, rank);
         signal_act_ready<kCG>(B, 1, rank);
+      }
+      if (store_id >= 0) {                                   // block `store_id` of both slots' first G
         const int ga = p.density_only ? 7 : 12;
         const int nb = p.density_only ? 4 : 2;
-        for (int slot = 0; slot < 2; ++slot) {
-          const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-          if (tile < n_tiles)
-            for (int bb = 0; bb < nb; ++bb)
+        for (int bb = store_id; bb < nb; bb += kStoreThreads)
+          for (int slot = 0; slot < 2; ++slot) {
+            const int64_t tile = 2 * kCl * it + 2 * rank + slot;
+            if (tile < n_tiles)
               bulk_store(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
-        }
+          }
         tma_store_commit();
       }
 
@@ -347,23 +350,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           fence_proxy_async();
           // the OTHER slot's latest G store (issued one epilogue ago) must have finished reading shared memory before the
           // next epilogue overwrites that slot: checked here, so one named barrier per stage is enough
-          if (e == 0) tma_store_wait_read<0>();
+          if (store_id >= 0) tma_store_wait_read<0>();
           named_bar_sync(1, kEpiThreads);
-          if (e == 0) {
-            if (i + 1 < p.n_prog) signal_act_ready<kCG>(B, slot, rank);
-            if (d.garr >= 0 && tile < n_tiles) {
-              const int nb = d.kind == 1 ? 4 : d.halves * 2;
-              const int b0 = d.kind == 1 ? 0 : d.out_blk;
-              for (int bb = 0; bb < nb; ++bb)
-                bulk_store(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (b0 + bb) * kBlkBytes,
-                           kBlkBytes);
-            }
+          if (e == kSignalThread && i + 1 < p.n_prog) signal_act_ready<kCG>(B, slot, rank);
+          if (store_id >= 0 && d.garr >= 0 && tile < n_tiles) {
+            const int nb = d.kind == 1 ? 4 : d.halves * 2;
+            const int b0 = d.kind == 1 ? 0 : d.out_blk;
+            for (int bb = store_id; bb < nb; bb += kStoreThreads)    // 16 KB blocks store_id, store_id + kStoreThreads, ... of this G
+              bulk_store(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (b0 + bb) * kBlkBytes, kBlkBytes);
             tma_store_commit();
           }
         }
       }
     }
-    if (e == 0) tma_store_wait_all();
+    if (store_id >= 0) tma_store_wait_all();
   }
   fused_teardown<kCG, kMC>(tmem_base);
 }

@@ -20,6 +20,19 @@ constexpr int kOffBar = kOffPart + 2048;
 constexpr int kSmemFused = kOffBar + 128 + 1024;           // + alignment slack
 constexpr int kFusedThreads = 320;
 constexpr int kEpiThreads = 256;
+constexpr int kSignalThread = 128;    // epilogue thread (warp 6) that signals act_ready after the end-of-layer barrier
+// The bulk stash stores of an epilogue (up to four 16 KB blocks) are issued by kStoreThreads threads of different warps, each
+// tracking and waiting for its own bulk groups.  What matters is that the store thread is not the signalling thread and that
+// neither sits in a warp with other after-barrier work: 1, 2 and 4 store threads measure the same (A/B on one box).
+#ifndef EONERF_STORE_THREADS
+#define EONERF_STORE_THREADS 1
+#endif
+constexpr int kStoreThreads = EONERF_STORE_THREADS;        // 1 (thread 160 stores every block), 2 or 4
+__host__ __device__ constexpr int store_thread_id(int e) {
+  return kStoreThreads == 4 ? ((e & 63) == 32 ? (e >> 6) : -1)           // e = 32, 96, 160, 224
+         : kStoreThreads == 2 ? (e == 160 ? 0 : (e == 224 ? 1 : -1))
+                              : (e == 160 ? 0 : -1);
+}
 
 static_assert(kCFloats * 4 <= kConstBytes, "constants do not fit");
 static_assert(kSmemFused <= 232448, "shared memory budget");

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeonerf_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 COMP_COLS = 12
 OUT_COLS = 21
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16_FUSED = 0, 1, 2, 3
@@ -145,6 +145,11 @@ class AdamArgs(C.Structure):
                 ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("grad_scale", F32)]
 
 
+class GatherBatchArgs(C.Structure):
+    _fields_ = [("all_rays", P), ("rays_stride", I64), ("all_rgbs", P), ("rgbs_stride", I64), ("all_ts", P), ("perm", P),
+                ("n_rows", I64), ("first", I64), ("batch", I64), ("rays_out", P), ("rgbs_out", P), ("ts_out", P), ("idx_out", P)]
+
+
 # every symbol include/eonerf_b200.h declares: name -> (restype, argtypes)
 _ARGS = lambda T: [C.POINTER(T), P]
 SYMBOLS = {
@@ -180,6 +185,7 @@ SYMBOLS = {
     "eonerf_linear_fwd": (C.c_int, _ARGS(LinearArgs)),
     "eonerf_linear_dw": (C.c_int, _ARGS(DwArgs)),
     "eonerf_adam_step": (C.c_int, _ARGS(AdamArgs)),
+    "eonerf_gather_batch": (C.c_int, _ARGS(GatherBatchArgs)),
 }
 
 _lib = None

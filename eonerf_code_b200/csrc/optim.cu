@@ -69,3 +69,33 @@ extern "C" int eonerf_adam_step(const EonerfAdamArgs* a, eonerf_stream_t stream)
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident ray table: one training batch = rows perm[first .. first + B) of the dataset's all_rays / all_rgbs /
+// all_ids_img (/root/reference/datasets/satellite.py:799-807 `__getitem__` + the DataLoader's collate,
+// train_eonerf.py:70,99-109), gathered by one kernel instead of B Python `__getitem__` calls, worker IPC and a pageable
+// host -> device copy.  One thread per (row, 16-byte-or-less piece): rows are 44 + 12 + 8 bytes.
+// ------------------------------------------------------------------------------------------------
+namespace eonerf {
+__global__ void __launch_bounds__(256) gather_batch_kernel(EonerfGatherBatchArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = t >> 4;
+  const int c = (int)(t & 15);
+  if (row >= a.batch) return;
+  int64_t src = __ldg(a.perm + a.first + row);
+  if (src < 0 || src >= a.n_rows) src = 0;                 // a corrupt index must not read out of bounds
+  if (c < 11) a.rays_out[row * 11 + c] = __ldg(a.all_rays + src * a.rays_stride + c);
+  else if (c < 14) a.rgbs_out[row * 3 + (c - 11)] = __ldg(a.all_rgbs + src * a.rgbs_stride + (c - 11));
+  else if (c == 14) a.ts_out[row] = __ldg(a.all_ts + src);
+  else if (a.idx_out) a.idx_out[row] = src;
+}
+}  // namespace eonerf
+
+extern "C" int eonerf_gather_batch(const EonerfGatherBatchArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->batch >= 0 && a->n_rows > 0 && a->first >= 0, "gather_batch: bad arguments");
+  if (a->batch == 0) return EONERF_OK;
+  EO_REQUIRE(a->all_rays && a->all_rgbs && a->all_ts && a->perm && a->rays_out && a->rgbs_out && a->ts_out, "gather_batch: null pointer");
+  gather_batch_kernel<<<(unsigned)div_up(a->batch * 16, 256), 256, 0, as_stream(stream)>>>(*a);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}

@@ -50,24 +50,35 @@ __device__ __forceinline__ SampleW sample_weight(float ts, float te, float sigma
 // render_weight_from_density / render_transmittance_from_density
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) weights_fwd_kernel(EonerfWeightsFwdArgs a) {
-  int lane = threadIdx.x & 31;
-  int64_t ray = warp_ray();
-  if (ray >= a.n_rays) return;
-  int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
-  float carry = 0.f;
-  for (int64_t base = beg; base < end; base += 32) {
-    int64_t i = base + lane;
-    bool ok = i < end;
-    float ts = ok ? __ldg(a.t_starts + i) : 0.f, te = ok ? __ldg(a.t_ends + i) : 0.f;
-    float sg = ok ? __ldg(a.sigmas + i) : 0.f;
-    float tau = sg * (te - ts), tot;
-    float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
-    carry += tot;
-    if (ok) {
-      SampleW s = sample_weight(ts, te, sg, pre);
-      if (a.weights) a.weights[i] = s.w;
-      if (a.trans) a.trans[i] = s.T;
-      if (a.alphas) a.alphas[i] = s.alpha;
+  const int lane = threadIdx.x & 31;
+  for (int64_t ray = warp_ray(); ray < a.n_rays; ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+    float carry = 0.f;
+    for (int64_t base = beg; base < end; base += 128) {       // 4 x 32 samples: all 12 loads of a lane issued up front
+      float ts[4], te[4], sg[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int64_t i = base + c * 32 + lane;
+        const bool ok = i < end;
+        ts[c] = ok ? __ldg(a.t_starts + i) : 0.f;
+        te[c] = ok ? __ldg(a.t_ends + i) : 0.f;
+        sg[c] = ok ? __ldg(a.sigmas + i) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int64_t i = base + c * 32 + lane;
+        const bool ok = i < end;
+        float tot;
+        const float tau = sg[c] * (te[c] - ts[c]);
+        const float pre = carry + warp_exclusive_sum(ok ? tau : 0.f, lane, tot);
+        carry += tot;
+        if (ok) {
+          const SampleW s = sample_weight(ts[c], te[c], sg[c], pre);
+          if (a.weights) a.weights[i] = s.w;
+          if (a.trans) a.trans[i] = s.T;
+          if (a.alphas) a.alphas[i] = s.alpha;
+        }
+      }
     }
   }
 }
@@ -133,13 +144,22 @@ __global__ void __launch_bounds__(256) accumulate_fwd_kernel(EonerfAccumFwdArgs 
   if (ray >= a.n_rays) return;
   int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
   int C = a.n_channels;
-  if (C <= 4) {  // lanes over samples
+  if (C <= 4) {  // lanes over samples, four chunks of loads in flight
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t i = beg + lane; i < end; i += 32) {
-      float w = __ldg(a.weights + i);
+    for (int64_t base = beg + lane; base < end; base += 128) {
+      float w[4], v[4][4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < C) acc[c] += w * (a.values ? __ldg(a.values + i * C + c) : 1.0f);
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = base + 32 * u;
+        const bool ok = i < end;
+        w[u] = ok ? __ldg(a.weights + i) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[u][c] = (c < C) ? ((ok && a.values) ? __ldg(a.values + i * C + c) : 1.0f) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] += w[u] * v[u][c];
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -582,7 +602,7 @@ extern "C" int eonerf_weights_fwd(const EonerfWeightsFwdArgs* a, eonerf_stream_t
   EO_REQUIRE(a && a->ray_offsets && a->n_rays >= 0, "weights_fwd: bad arguments");
   if (a->n_rays == 0) return EONERF_OK;
   EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->sigmas), "weights_fwd: null input");
-  weights_fwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  weights_fwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 9
+#define EONERF_ABI_VERSION 10
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -379,6 +379,25 @@ typedef struct {
   float grad_scale;
 } EonerfAdamArgs;
 int eonerf_adam_step(const EonerfAdamArgs* a, eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident ray table.  Replaces the per-ray SatelliteDataset.__getitem__ + DataLoader
+ * collate + host->device copies of the training loop (datasets/satellite.py:799-807, train_eonerf.py:70,99-109): a batch
+ * is rows perm[first .. first+batch) of all_rays[N,11] / all_rgbs[N,3] / all_ids_img[N] (int64), all resident in HBM.
+ * perm is a device-side permutation of 0..N-1 (the DataLoader's shuffle=True epoch order).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* all_rays; int64_t rays_stride;     /* [N,11], row stride in floats */
+  const float* all_rgbs; int64_t rgbs_stride;     /* [N,3] */
+  const int64_t* all_ts;                          /* [N] image index per ray */
+  const int64_t* perm;                            /* [>= first+batch] row indices */
+  int64_t n_rows; int64_t first; int64_t batch;
+  float* rays_out;                                /* [batch,11] */
+  float* rgbs_out;                                /* [batch,3] */
+  int64_t* ts_out;                                /* [batch] (viewed as [batch,1]) */
+  int64_t* idx_out;                               /* [batch] source rows ("idx" of the reference's sample dict), or NULL */
+} EonerfGatherBatchArgs;
+int eonerf_gather_batch(const EonerfGatherBatchArgs* a, eonerf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -163,3 +163,32 @@ def test_flat_adam_matches_torch_adam(cuda):
     opt_b.step()
     for a, b in zip(pa, pb):
         close(a, b, 2e-6, 1e-7)
+
+
+def test_device_ray_loader_is_a_shuffled_epoch(cuda):
+    """DeviceRayLoader == DataLoader(shuffle=True) over the reference's training dataset (satellite.py:799-807): every row
+    exactly once per epoch, same dict keys / shapes / dtypes, rows bit-identical to indexing the table, short last batch."""
+    from eonerf_code_b200.datasets.device_loader import DeviceRayLoader
+    from eonerf_code_b200.datasets.synthetic import make_rays
+    n, B = 10_007, 1024
+    rays, ts, rgbs = make_rays(n, 7, seed=31)
+    gen = torch.Generator(device=cuda).manual_seed(5)
+    loader = DeviceRayLoader(rays, rgbs, ts, B, device=cuda, generator=gen)
+    assert len(loader) == (n + B - 1) // B
+    seen = []
+    for k, batch in enumerate(loader):
+        b = batch["rays"].shape[0]
+        assert b == (B if k < len(loader) - 1 else n - B * (len(loader) - 1))
+        assert batch["rays"].shape == (b, 11) and batch["rgbs"].shape == (b, 3) and batch["ts"].shape == (b, 1)
+        assert batch["ts"].dtype == torch.int64 and batch["idx"].dtype == torch.int64 and batch["rays"].is_cuda
+        idx = batch["idx"].cpu()
+        assert torch.equal(batch["rays"].cpu(), rays[idx]) and torch.equal(batch["rgbs"].cpu(), rgbs[idx])
+        assert torch.equal(batch["ts"].cpu(), ts[idx])
+        seen.append(idx)
+    seen = torch.cat(seen)
+    assert torch.equal(torch.sort(seen)[0], torch.arange(n))              # a permutation: without replacement
+    assert not torch.equal(seen, torch.arange(n))                          # ... and shuffled
+    second = torch.cat([b["idx"].cpu() for b in loader])
+    assert not torch.equal(second, seen)                                   # a new permutation every epoch
+    fixed = DeviceRayLoader(rays, rgbs, ts, B, shuffle=False, device=cuda)
+    assert torch.equal(torch.cat([b["idx"].cpu() for b in fixed]), torch.arange(n))

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeonerf_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 COMP_COLS = 12
 OUT_COLS = 21
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16_FUSED = 0, 1, 2, 3
@@ -150,6 +150,10 @@ class GatherBatchArgs(C.Structure):
                 ("n_rows", I64), ("first", I64), ("batch", I64), ("rays_out", P), ("rgbs_out", P), ("ts_out", P), ("idx_out", P)]
 
 
+class LossArgs(C.Structure):
+    _fields_ = [("out", P), ("gt_rgb", P), ("n_rays", I64), ("mode", I32), ("loss", P), ("g_out", P), ("partials", P)]
+
+
 # every symbol include/eonerf_b200.h declares: name -> (restype, argtypes)
 _ARGS = lambda T: [C.POINTER(T), P]
 SYMBOLS = {
@@ -186,6 +190,8 @@ SYMBOLS = {
     "eonerf_linear_dw": (C.c_int, _ARGS(DwArgs)),
     "eonerf_adam_step": (C.c_int, _ARGS(AdamArgs)),
     "eonerf_gather_batch": (C.c_int, _ARGS(GatherBatchArgs)),
+    "eonerf_loss_partials": (I64, [I64]),
+    "eonerf_loss_fwd_bwd": (C.c_int, _ARGS(LossArgs)),
 }
 
 _lib = None

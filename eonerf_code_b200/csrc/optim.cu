@@ -99,3 +99,87 @@ extern "C" int eonerf_gather_batch(const EonerfGatherBatchArgs* a, eonerf_stream
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Training losses on the packed per-ray outputs (out[B,21]: rgb = columns 0:3, beta = column 12), value AND gradient in
+// one pass: metrics.mse (train_eonerf.py:139-140, epoch < 2) and metrics.uncertainty_aware_loss (metrics.py:17-22)
+//     color = mean_{r,c} (rgb - gt)^2 / (2 beta^2),   logbeta = (3 + mean_r log beta) / 2,   loss = color + logbeta.
+// Replaces ~25 element-wise / reduction / slice-backward launches of the autograd graph.  Deterministic: per-block
+// partial sums, then one block adds them in a fixed order.
+// ------------------------------------------------------------------------------------------------
+namespace eonerf {
+__global__ void __launch_bounds__(256) loss_rows_kernel(EonerfLossArgs a) {
+  __shared__ float red[2][8];
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float color = 0.f, lb = 0.f;
+  if (r < a.n_rays) {
+    const float* o = a.out + r * EONERF_OUT_COLS;
+    float* g = a.g_out + r * EONERF_OUT_COLS;
+    const float inv3b = 1.0f / (3.0f * (float)a.n_rays);
+    float d[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[c] = o[c] - __ldg(a.gt_rgb + r * 3 + c);
+    const float sq = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+#pragma unroll
+    for (int c = 0; c < EONERF_OUT_COLS; ++c) g[c] = 0.f;
+    if (a.mode == 0) {                                        // mse
+      color = sq;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g[c] = 2.0f * d[c] * inv3b;
+    } else {
+      const float beta = o[12];
+      const float ib2 = 1.0f / (beta * beta);
+      color = sq * 0.5f * ib2;
+      lb = logf(beta);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g[c] = d[c] * ib2 * inv3b;
+      g[12] = -sq * ib2 / beta * inv3b + 0.5f / ((float)a.n_rays * beta);
+    }
+  }
+  color = warp_sum(color);
+  lb = warp_sum(lb);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = color; red[1][warp] = lb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float c = 0.f, l = 0.f;
+    for (int w = 0; w < 8; ++w) { c += red[0][w]; l += red[1][w]; }
+    a.partials[2 * blockIdx.x] = c;
+    a.partials[2 * blockIdx.x + 1] = l;
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_finish_kernel(EonerfLossArgs a, int n_blocks) {
+  __shared__ float red[2][8];
+  float c = 0.f, l = 0.f;
+  for (int i = threadIdx.x; i < n_blocks; i += 256) { c += a.partials[2 * i]; l += a.partials[2 * i + 1]; }
+  c = warp_sum(c);
+  l = warp_sum(l);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = c; red[1][warp] = l; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    c = 0.f; l = 0.f;
+    for (int w = 0; w < 8; ++w) { c += red[0][w]; l += red[1][w]; }
+    const float color = c / (3.0f * (float)a.n_rays);
+    const float logbeta = a.mode == 0 ? 0.f : (3.0f + l / (float)a.n_rays) * 0.5f;
+    a.loss[0] = color + logbeta;
+    a.loss[1] = color;
+    a.loss[2] = logbeta;
+  }
+}
+}  // namespace eonerf
+
+extern "C" int64_t eonerf_loss_partials(int64_t n_rays) { return 2 * div_up(n_rays > 0 ? n_rays : 1, 256); }
+
+extern "C" int eonerf_loss_fwd_bwd(const EonerfLossArgs* a, eonerf_stream_t stream) {
+  EO_REQUIRE(a && a->n_rays > 0 && (a->mode == 0 || a->mode == 1), "loss_fwd_bwd: bad arguments");
+  EO_REQUIRE(a->out && a->gt_rgb && a->g_out && a->loss && a->partials, "loss_fwd_bwd: null pointer");
+  cudaStream_t s = as_stream(stream);
+  const int blocks = (int)div_up(a->n_rays, 256);
+  loss_rows_kernel<<<blocks, 256, 0, s>>>(*a);
+  EO_LAUNCH_CHECK();
+  loss_finish_kernel<<<1, 256, 0, s>>>(*a, blocks);
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
+}

@@ -57,7 +57,7 @@ def compute_geometric_shadows(chunk_rays, depth, radiance_field, occupancy_grid,
     return geo, info["sc_pts_per_ray"]
 
 
-def render_image(
+def render_packed(
     radiance_field: torch.nn.Module,
     occupancy_grid,
     rays: SatRays,
@@ -79,12 +79,8 @@ def render_image(
     z_steps=None,
     static=False,
 ):
-    """sat_rendering.py:176-335 -> (dict of 12 [..., C] tensors (or {"depth"}), n_rendering_samples).
-    `uniforms`: optional list with one dict per chunk {u_cam, u_sun, u_cam2} replacing the device RNG.
-    `static=True` (fused precision only): the sync-free form used under CUDA-graph capture.  Sample counts never reach
-    the host: packed arrays keep their B*(n-1) capacity and the kernels read P / Q on the device, the reference's
-    "some ray kept no sample -> draw again" branch becomes a device-side condition (its uniforms are always drawn), and
-    n_rendering_samples comes back as a 0-d int64 device tensor."""
+    """The body of render_image: -> (packed [B,21] per-ray outputs in the column order of OUT_SLICES (or depth [B,1] when
+    only_depth), n_rendering_samples, rays_shape).  training.TrainStep evaluates its fused loss on the packed tensor."""
     rays_shape = rays.origins.shape
     if len(rays_shape) == 3:
         num_rays = rays_shape[0] * rays_shape[1]
@@ -128,6 +124,42 @@ def render_image(
         rad_sink = e.grad_sink.get("radiometricT_enc.weight") if (rad is not None and e.grad_sink is not None) else None
         outs.append(ops._EpilogueFn.apply(comp, geo, ppr, sc_ppr, chunk_rays.img_idx, eval, rad, e.n_images, rad_sink))
     out = torch.cat(outs, dim=0) if len(outs) != 1 else outs[0]
+    return out, n_rendering_samples, rays_shape
+
+
+def render_image(
+    radiance_field: torch.nn.Module,
+    occupancy_grid,
+    rays: SatRays,
+    scene_aabb: torch.Tensor,
+    args,
+    epoch_idx: Optional[int] = None,
+    chunk: int = 5120,
+    near_plane: Optional[float] = None,
+    far_plane: Optional[float] = None,
+    render_step_size: float = 1e-3,
+    render_bkgd: Optional[torch.Tensor] = None,
+    cone_angle: float = 0.0,
+    alpha_thre: float = 0.0,
+    early_stop_eps: float = 0.0,
+    timestamps: Optional[torch.Tensor] = None,
+    only_depth: bool = False,
+    eval: bool = False,
+    uniforms=None,
+    z_steps=None,
+    static=False,
+):
+    """sat_rendering.py:176-335 -> (dict of 12 [..., C] tensors (or {"depth"}), n_rendering_samples).
+    `uniforms`: optional list with one dict per chunk {u_cam, u_sun, u_cam2} replacing the device RNG.
+    `static=True` (fused precision only): the sync-free form used under CUDA-graph capture.  Sample counts never reach
+    the host: packed arrays keep their B*(n-1) capacity and the kernels read P / Q on the device, the reference's
+    "some ray kept no sample -> draw again" branch becomes a device-side condition (its uniforms are always drawn), and
+    n_rendering_samples comes back as a 0-d int64 device tensor."""
+    out, n_rendering_samples, rays_shape = render_packed(
+        radiance_field, occupancy_grid, rays, scene_aabb, args, epoch_idx=epoch_idx, chunk=chunk, near_plane=near_plane,
+        far_plane=far_plane, render_step_size=render_step_size, render_bkgd=render_bkgd, cone_angle=cone_angle, alpha_thre=alpha_thre,
+        early_stop_eps=early_stop_eps, timestamps=timestamps, only_depth=only_depth, eval=eval, uniforms=uniforms, z_steps=z_steps,
+        static=static)
     if only_depth:
         return {"depth": out.view((*rays_shape[:-1], -1))}, n_rendering_samples
     return {k: out[:, a:b].view((*rays_shape[:-1], -1)) for k, a, b in OUT_SLICES}, n_rendering_samples

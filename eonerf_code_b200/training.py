@@ -47,15 +47,12 @@ class TrainStep:
         if static or self.graph:               # graph replays update the parameters behind Python's back
             self.field._engine().refresh_prepared()
         self.grads.zero()
-        res, n_rendered = sat_rendering.render_image(self.field, None, sat, None, None, epoch_idx=epoch_idx,
-                                                     chunk=self.chunk or rays.shape[0], render_step_size=self.render_step_size,
-                                                     static=static)
+        out, n_rendered, _ = sat_rendering.render_packed(self.field, None, sat, None, None, epoch_idx=epoch_idx,
+                                                         chunk=self.chunk or rays.shape[0], render_step_size=self.render_step_size,
+                                                         static=static)
         if not static and n_rendered == 0:                                   # train_eonerf.py:135-136
             return None, 0
-        if epoch_idx < 2:
-            loss = metrics.mse(pixels, res["rgb"])
-        else:
-            loss, _ = metrics.uncertainty_aware_loss(pixels, res["rgb"], res["beta"])
+        loss, _ = metrics.packed_loss(out, pixels, epoch_idx)               # MSE (epoch < 2) / uncertainty-aware loss, value + gradient
         loss.backward()
         return loss.detach(), n_rendered
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 10
+#define EONERF_ABI_VERSION 11
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -398,6 +398,24 @@ typedef struct {
   int64_t* idx_out;                               /* [batch] source rows ("idx" of the reference's sample dict), or NULL */
 } EonerfGatherBatchArgs;
 int eonerf_gather_batch(const EonerfGatherBatchArgs* a, eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training losses on the packed per-ray outputs of eonerf_epilogue_fwd (out[B,21]), value and gradient in one pass.
+ * Replaces metrics.uncertainty_aware_loss (metrics.py:17-22; mode 1) / the epoch<2 MSE (train_eonerf.py:139-140; mode 0)
+ * and their autograd backward.  loss[0] = total, loss[1] = colour term, loss[2] = log-beta term (the reference's loss_dict).
+ * g_out[B,21] receives d loss / d out (zero outside the rgb columns 0:3 and the beta column 12).  Deterministic.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* out;            /* [B,21] */
+  const float* gt_rgb;         /* [B,3] */
+  int64_t n_rays;
+  int32_t mode;                /* 0 mse, 1 uncertainty-aware */
+  float* loss;                 /* [3] */
+  float* g_out;                /* [B,21] */
+  float* partials;             /* scratch, eonerf_loss_partials(B) floats */
+} EonerfLossArgs;
+int64_t eonerf_loss_partials(int64_t n_rays);
+int eonerf_loss_fwd_bwd(const EonerfLossArgs* a, eonerf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -192,3 +192,29 @@ def test_device_ray_loader_is_a_shuffled_epoch(cuda):
     assert not torch.equal(second, seen)                                   # a new permutation every epoch
     fixed = DeviceRayLoader(rays, rgbs, ts, B, shuffle=False, device=cuda)
     assert torch.equal(torch.cat([b["idx"].cpu() for b in fixed]), torch.arange(n))
+
+
+@pytest.mark.parametrize("epoch", [0, 2])
+def test_packed_loss_matches_reference_losses(cuda, epoch):
+    """eonerf_loss_fwd_bwd vs metrics.uncertainty_aware_loss / mse (metrics.py:17-22, train_eonerf.py:139-143): value, the two
+    terms of the loss_dict and the gradient wrt the packed renderer output."""
+    from eonerf_code_b200 import metrics
+    torch.manual_seed(3 + epoch)
+    B = 5000
+    out = torch.rand(B, 21, device=cuda)
+    out[:, 12] = out[:, 12] * 2 + 0.05                      # beta >= beta_min
+    gt = torch.rand(B, 3, device=cuda)
+    a = out.clone().requires_grad_(True)
+    b = out.clone().requires_grad_(True)
+    loss_a, terms = metrics.packed_loss(a, gt, epoch)
+    if epoch < 2:
+        loss_b = metrics.mse(gt, b[:, 0:3])
+    else:
+        loss_b, ref_terms = metrics.uncertainty_aware_loss(gt, b[:, 0:3], b[:, 12:13])
+        close(terms["coarse_color"], ref_terms["coarse_color"], 2e-6)
+        close(terms["coarse_logbeta"], ref_terms["coarse_logbeta"], 2e-6)
+    close(loss_a, loss_b, 2e-6)
+    (3.0 * loss_a).backward()
+    (3.0 * loss_b).backward()
+    close(a.grad, b.grad, 1e-5, 2e-6 * float(b.grad.abs().max()))    # the two terms of d/d beta cancel: absolute floor
+    assert float(a.grad[:, 3:12].abs().max()) == 0.0 and float(a.grad[:, 13:].abs().max()) == 0.0

@@ -26,26 +26,49 @@ namespace eonerf {
 // ------------------------------------------------------------------------------------------------
 // prepare: W fp32 [rows, k] (ld = ldw) -> dst [rows, kp] (zero padded) and dst_t [kp, rows]
 // ------------------------------------------------------------------------------------------------
+// All weight matrices of a prepare call go through ONE launch: a table of jobs, each thread finds its job from the prefix of
+// element counts (14 launches -> 1 per optimiser step).
+struct ConvertJob { const float* w; int64_t ldw; int rows, k, kp; void* dst; int dst_row0; void* dst_t; int ld_t; int first; };
+constexpr int kMaxConvertJobs = 16;
+struct ConvertJobs { ConvertJob j[kMaxConvertJobs]; int n; int total; };
+
 template <class T>
-__global__ void convert_weight_kernel(const float* __restrict__ w, int64_t ldw, int rows, int k, int kp,
-                                      T* __restrict__ dst, int dst_row0, T* __restrict__ dst_t, int ld_t) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * kp) return;
-  int r = idx / kp, c = idx % kp;
-  float v = c < k ? __ldg(w + (int64_t)r * ldw + c) : 0.f;
-  dst[(int64_t)(dst_row0 + r) * kp + c] = from_f32<T>(v);
-  dst_t[(int64_t)c * ld_t + dst_row0 + r] = from_f32<T>(v);
+__global__ void __launch_bounds__(256) convert_weights_kernel(const __grid_constant__ ConvertJobs jobs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= jobs.total) return;
+  int ji = 0;
+#pragma unroll 1
+  while (ji + 1 < jobs.n && idx >= jobs.j[ji + 1].first) ++ji;
+  const ConvertJob& q = jobs.j[ji];
+  const int e = idx - q.first;
+  const int r = e / q.kp, c = e % q.kp;
+  const float v = c < q.k ? __ldg(q.w + (int64_t)r * q.ldw + c) : 0.f;
+  static_cast<T*>(q.dst)[(int64_t)(q.dst_row0 + r) * q.kp + c] = from_f32<T>(v);
+  static_cast<T*>(q.dst_t)[(int64_t)c * q.ld_t + q.dst_row0 + r] = from_f32<T>(v);
+}
+
+static thread_local ConvertJobs t_jobs;          // filled by convert_weight(), launched by convert_flush()
+
+static int convert_flush(int precision, cudaStream_t s) {
+  if (t_jobs.n == 0) return EONERF_OK;
+  const int blocks = div_up(t_jobs.total, 256);
+  if (precision == EONERF_PREC_FP32) convert_weights_kernel<float><<<blocks, 256, 0, s>>>(t_jobs);
+  else convert_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(t_jobs);
+  t_jobs.n = 0;
+  t_jobs.total = 0;
+  EO_LAUNCH_CHECK();
+  return EONERF_OK;
 }
 
 static int convert_weight(int precision, const float* w, int64_t ldw, int rows, int k, int kp, void* dst, int dst_row0,
                           void* dst_t, int ld_t, cudaStream_t s) {
-  int n = rows * kp;
-  if (precision == EONERF_PREC_FP32)
-    convert_weight_kernel<float><<<div_up(n, 256), 256, 0, s>>>(w, ldw, rows, k, kp, (float*)dst, dst_row0, (float*)dst_t, ld_t);
-  else
-    convert_weight_kernel<__nv_bfloat16><<<div_up(n, 256), 256, 0, s>>>(w, ldw, rows, k, kp, (__nv_bfloat16*)dst, dst_row0,
-                                                                       (__nv_bfloat16*)dst_t, ld_t);
-  EO_LAUNCH_CHECK();
+  if (t_jobs.n == kMaxConvertJobs) {
+    int rc = convert_flush(precision, s);
+    if (rc != EONERF_OK) return rc;
+  }
+  t_jobs.j[t_jobs.n] = ConvertJob{w, ldw, rows, k, kp, dst, dst_row0, dst_t, ld_t, t_jobs.total};
+  t_jobs.n += 1;
+  t_jobs.total += rows * kp;
   return EONERF_OK;
 }
 
@@ -532,7 +555,7 @@ static int field_prepare_impl(int field, int precision, const EonerfFieldParams*
   } else {
     EO_TRY(convert_weight(precision, p->head0_w, 283, kHid, 283, kW + kDirEnc, at(prepared, L.hd0), 0, at(prepared, L.hd0_t), kHid, s));
   }
-  return EONERF_OK;
+  return convert_flush(precision, s);
 }
 
 static int field_fwd_impl(const EonerfFieldFwdArgs* a, cudaStream_t s) {

@@ -16,3 +16,18 @@ def define_satrays_from_tensors(rays, ts):
 def namedtuple_map(fn, tup):
     """datasets/utils.py:9-11"""
     return type(tup)(*(None if x is None else fn(x) for x in tup))
+
+
+def get_utmalt_from_nerf_prediction(rays, depth, scene_scale, scene_offset, double=True):
+    """satellite.py:502-531 (the `utm_sampling` branch): the evaluation epilogue that turns a rendered depth map into a
+    point cloud, x = (o + d * depth) * scene_scale + scene_offset, in fp64 as the reference does to keep metre-level UTM
+    coordinates exact.  rays [N,11], depth [N,1] or [N]; scene_scale / scene_offset [3].  -> (easts, norths, alts), each [N].
+    O(N) element-wise work on the per-ray outputs, device-agnostic torch (the ECEF / lon-lat branch needs the reference's
+    un-vendored geodesy helpers and stays out of scope)."""
+    import torch
+    if double:
+        rays, depth = rays.double(), depth.double()
+    scale = torch.as_tensor(scene_scale, dtype=rays.dtype, device=rays.device)
+    offset = torch.as_tensor(scene_offset, dtype=rays.dtype, device=rays.device)
+    xyz = (rays[:, 0:3] + rays[:, 3:6] * depth.reshape(-1, 1)) * scale + offset
+    return xyz[:, 0], xyz[:, 1], xyz[:, 2]

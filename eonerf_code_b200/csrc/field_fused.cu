@@ -86,13 +86,51 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
     if (lane == 0) fused_producer<kCG, kMC>(p.prog, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
     if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC, true>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);      // whole warp, converged
+  } else if (kDutyWarp && warp == kDutyWarpId) {
+    // ===== duty warp: mirrors the epilogue warps' named barriers; after each one, lane 0 hands the slot to the MMA issuer and
+    // starts the stash store of what the epilogue wrote; before the next one it waits until that store has read shared memory =====
+    for (int64_t it = it0; it < n_items; it += it_stride) {
+      if (kTrain && kDutyStores && lane == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, kBarThreads);                       // start of the item: the slots may be overwritten
+      named_bar_sync(1, kBarThreads);                       // positional encoding + layer-0 bias written
+      if (lane == 0) {
+        signal_act_ready<kCG>(B, 0, rank);
+        signal_act_ready<kCG>(B, 1, rank);
+        if (kTrain && kDutyStores) {
+          for (int slot = 0; slot < 2; ++slot) {
+            const int64_t tile = 2 * kCl * it + 2 * rank + slot;
+            if (tile < n_tiles) bulk_store(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
+          }
+          tma_store_commit();
+        }
+      }
+      __syncwarp();
+      for (int s = 0; s < p.n_stages; ++s)
+        for (int slot = 0; slot < 2; ++slot) {
+          if (kTrain && kDutyStores && lane == 0) tma_store_wait_read<0>();
+          named_bar_sync(1, kBarThreads);
+          if (lane == 0) {
+            if (s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
+            const int64_t tile = 2 * kCl * it + 2 * rank + slot;
+            if (kTrain && kDutyStores && tile < n_tiles && !(p.training & 2)) {
+              const FStage d = c_fstage[s];
+              const int nb = d.halves * 2;
+              for (int bb = 0; bb < nb; ++bb)
+                bulk_store(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes, kBlkBytes);
+              tma_store_commit();
+            }
+          }
+          __syncwarp();
+        }
+    }
+    if (kTrain && kDutyStores && lane == 0) tma_store_wait_all();
   } else {
     // ===== epilogue warps =====
     const int e = threadIdx.x - 64;
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;                    // row of the tile
-    const int store_id = store_thread_id(e);        // 0..3: this thread owns the bulk stores of that output block; else -1
+    const int store_id = kDutyStores ? -1 : store_thread_id(e);   // >= 0: this epilogue thread owns bulk stash stores
     const uint32_t s_cst = smem_u32(cst);
     const uint32_t s_part = smem_u32(part);
     uint32_t cph = 0;                               // bit `slot` = phase of acc_full[slot]
@@ -101,7 +139,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
       uint32_t cls_pack = 0;                        // image index of this row in slot 0 (low 16 bits) / slot 1
       // ---- positional encoding of both tiles ----
       if (store_id >= 0) tma_store_wait_read<0>();
-      named_bar_sync(1, kEpiThreads);
+      named_bar_sync(1, kBarThreads);
       for (int slot = 0; slot < 2; ++slot) {
         const int64_t tile = 2 * kCl * it + 2 * rank + slot;
         const int64_t pt = tile * kTileM + r;
@@ -164,10 +202,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
       }
       tc_fence_before();
       fence_proxy_async();
-      named_bar_sync(1, kEpiThreads);
+      named_bar_sync(1, kBarThreads);
       // after-barrier duties are split over two threads of different warps (neither in a warp that writes head outputs), so
       // no single warp arrives late at the next barrier: one signals the MMA issuer, the other owns the stash stores
-      if (e == kSignalThread) {
+      if (!kDutyWarp && e == kSignalThread) {
         signal_act_ready<kCG>(B, 0, rank);
         signal_act_ready<kCG>(B, 1, rank);
       }
@@ -330,9 +368,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           EO_TN(td);
           if (kTrain && store_id >= 0) tma_store_wait_read<0>();
           EO_TN(te);
-          { EO_T0(); named_bar_sync(1, kEpiThreads); if (e == 32) EO_T1(5); }
+          { EO_T0(); named_bar_sync(1, kBarThreads); if (e == 32) EO_T1(5); }
           EO_TN(tf);
-          if (e == kSignalThread && s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
+          if (!kDutyWarp && e == kSignalThread && s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
           if (kTrain && store_id >= 0 && tile < n_tiles && !(p.training & 2)) {
             const int nb = d.halves * 2;                     // 16 KB blocks store_id, store_id + kStoreThreads, ... of the layer's output
             for (int bb = store_id; bb < nb; bb += kStoreThreads)

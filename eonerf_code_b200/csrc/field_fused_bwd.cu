@@ -103,20 +103,66 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
     if (lane == 0) fused_producer<kCG, kMC>(p.mma, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
     if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC>(p.mma, smem, B, tmem_base, it0, n_items, it_stride);       // whole warp, converged
+  } else if (kDutyWarp && warp == kDutyWarpId) {
+    // ===== duty warp (see field_fused.cu): mirrors the epilogue warps' named barriers, signals the MMA issuer and owns the
+    // bulk stores of the G arrays =====
+    for (int64_t it = it0; it < n_items; it += it_stride) {
+      if (kDutyStores && lane == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, kBarThreads);                       // start of the item
+      named_bar_sync(1, kBarThreads);                       // head gradients -> first G written
+      if (lane == 0) {
+        signal_act_ready<kCG>(B, 0, rank);
+        signal_act_ready<kCG>(B, 1, rank);
+        const int ga = p.density_only ? 7 : 12;
+        const int nb = kDutyStores ? (p.density_only ? 4 : 2) : 0;
+        for (int slot = 0; slot < 2; ++slot) {
+          const int64_t tile = 2 * kCl * it + 2 * rank + slot;
+          if (tile < n_tiles)
+            for (int bb = 0; bb < nb; ++bb)
+              bulk_store(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
+        }
+        tma_store_commit();
+      }
+      __syncwarp();
+      for (int i = 0; i < p.n_prog; ++i) {
+        const BStage d = c_bstage[p.prog[i]];
+        for (int slot = 0; slot < 2; ++slot) {
+          if (d.kind == 4) {                                 // final stage: positions only, nothing to hand over or store
+            named_bar_sync(1, kBarThreads);
+            continue;
+          }
+          if (kDutyStores && lane == 0) tma_store_wait_read<0>();
+          named_bar_sync(1, kBarThreads);
+          if (lane == 0) {
+            if (i + 1 < p.n_prog) signal_act_ready<kCG>(B, slot, rank);
+            const int64_t tile = 2 * kCl * it + 2 * rank + slot;
+            if (kDutyStores && d.garr >= 0 && tile < n_tiles) {
+              const int nb = d.kind == 1 ? 4 : d.halves * 2;
+              const int b0 = d.kind == 1 ? 0 : d.out_blk;
+              for (int bb = 0; bb < nb; ++bb)
+                bulk_store(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (b0 + bb) * kBlkBytes, kBlkBytes);
+            }
+            tma_store_commit();
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (kDutyStores && lane == 0) tma_store_wait_all();
   } else {
     // ===== epilogue warps =====
     const int e = threadIdx.x - 64;
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    const int store_id = store_thread_id(e);
+    const int store_id = kDutyStores ? -1 : store_thread_id(e);
     const uint32_t s_hw = smem_u32(hw);
     uint32_t cph = 0;
     uint64_t* const acc_full = B.acc_full;
     for (int64_t it = it0; it < n_items; it += it_stride) {
       // ---- head gradients -> first G of the chain ----
       if (store_id >= 0) tma_store_wait_read<0>();
-      named_bar_sync(1, kEpiThreads);
+      named_bar_sync(1, kBarThreads);
       for (int slot = 0; slot < 2; ++slot) {
         const int64_t tile = 2 * kCl * it + 2 * rank + slot;
         const int64_t pt = tile * kTileM + r;
@@ -194,8 +240,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
         }
       }
       fence_proxy_async();
-      named_bar_sync(1, kEpiThreads);
-      if (e == kSignalThread) {
+      named_bar_sync(1, kBarThreads);
+      if (!kDutyWarp && e == kSignalThread) {
         signal_act_ready<kCG>(B, 0, rank);
         signal_act_ready<kCG>(B, 1, rank);
       }
@@ -277,7 +323,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
               }
             }
             tc_fence_before();
-            named_bar_sync(1, kEpiThreads);
+            named_bar_sync(1, kBarThreads);
             continue;
           }
           const bool write_out = !(d.kind == 3 && half == 1);   // encoding part: only 64 real columns
@@ -351,8 +397,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           // the OTHER slot's latest G store (issued one epilogue ago) must have finished reading shared memory before the
           // next epilogue overwrites that slot: checked here, so one named barrier per stage is enough
           if (store_id >= 0) tma_store_wait_read<0>();
-          named_bar_sync(1, kEpiThreads);
-          if (e == kSignalThread && i + 1 < p.n_prog) signal_act_ready<kCG>(B, slot, rank);
+          named_bar_sync(1, kBarThreads);
+          if (!kDutyWarp && e == kSignalThread && i + 1 < p.n_prog) signal_act_ready<kCG>(B, slot, rank);
           if (store_id >= 0 && d.garr >= 0 && tile < n_tiles) {
             const int nb = d.kind == 1 ? 4 : d.halves * 2;
             const int b0 = d.kind == 1 ? 0 : d.out_blk;

@@ -18,8 +18,21 @@ constexpr int kConstBytes = 15872;
 constexpr int kOffPart = kOffConst + kConstBytes;          // [2 slots][128][2] floats
 constexpr int kOffBar = kOffPart + 2048;
 constexpr int kSmemFused = kOffBar + 128 + 1024;           // + alignment slack
-constexpr int kFusedThreads = 320;
+// EONERF_DUTY_WARP = 1: an 11th warp joins every end-of-layer named barrier and does the after-barrier duties (signal the MMA
+// issuer, issue the bulk stash stores, wait for their shared-memory reads), so no epilogue warp has anything to do between
+// the barrier and the next accumulator.  0: two epilogue threads (kSignalThread, the store threads) do them.
+#ifndef EONERF_DUTY_WARP
+#define EONERF_DUTY_WARP 1
+#endif
+constexpr bool kDutyWarp = EONERF_DUTY_WARP != 0;
+constexpr int kDutyWarpId = 10;
+#ifndef EONERF_DUTY_STORES
+#define EONERF_DUTY_STORES 0
+#endif
+constexpr bool kDutyStores = kDutyWarp && EONERF_DUTY_STORES != 0;   // the duty warp also owns the bulk stores (measured slower)
+constexpr int kFusedThreads = kDutyWarp ? 352 : 320;
 constexpr int kEpiThreads = 256;
+constexpr int kBarThreads = kDutyWarp ? 288 : 256;      // participants of the end-of-layer named barrier
 constexpr int kSignalThread = 128;    // epilogue thread (warp 6) that signals act_ready after the end-of-layer barrier
 // The bulk stash stores of an epilogue (up to four 16 KB blocks) are issued by kStoreThreads threads of different warps, each
 // tracking and waiting for its own bulk groups.  What matters is that the store thread is not the signalling thread and that

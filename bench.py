@@ -313,9 +313,15 @@ def run_product(args, rank, world, local):
         fl, t_ms, n_l = prof[0].flops, prof[0].ms, prof[0].launches
         kname = "gemm_nt_tc_kernel (tcgen05 forward / input-gradient GEMMs)"
     ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+    traffic, traffic_dw, traffic_src = None, None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):              # per-launch DRAM bytes from the committed `ncu --set full` capture of the same command
+        tj = json.load(open(tpath))
+        traffic, traffic_dw, traffic_src = tj.get("fused_fwd_bwd_bytes_per_launch"), tj.get("dw_gemm_bytes_per_launch"), tj.get("source")
     roof = {"bound": "tensor", "kernel": kname, "achieved": ach,
             "peak": pk["tc_sustained"], "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-            "unit": "TFLOP/s", "frac": ach / pk["tc_sustained"], "traffic": None, "launches": int(n_l),
+            "unit": "TFLOP/s", "frac": ach / pk["tc_sustained"], "traffic": traffic if fused else None, "traffic_source": traffic_src,
+            "launches": int(n_l),
             "avg_launch_ms": t_ms / max(1, n_l), "share_of_step": t_ms / ms,
             "timed": ("CUDA events around every launch of the same steps replayed eagerly right after the timed region "
                       "(the timed region is a CUDA graph, which cannot hold timing events)") if use_graph else
@@ -327,6 +333,7 @@ def run_product(args, rank, world, local):
                "achieved_tflops": tn.flops / (tn.ms * 1e-3) / 1e12 if tn.ms > 0 else 0.0,
                "achieved": tn.bytes / (tn.ms * 1e-3) / 1e9 if tn.ms > 0 else 0.0, "peak": pk["hbm"], "unit": "GB/s",
                "frac": (tn.bytes / (tn.ms * 1e-3) / 1e9 / pk["hbm"]) if tn.ms > 0 else 0.0,
+               "traffic": traffic_dw, "algorithmic_bytes_per_launch": tn.bytes / max(1, tn.launches),
                "launches": int(tn.launches), "share_of_step": tn.ms / ms}
     line = {"metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -344,9 +351,9 @@ def run_product(args, rank, world, local):
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         t0 = time.perf_counter()
-        times = cpu_train_steps(1024, N_SAMPLES, 3, 1, threads)
+        times = cpu_train_steps(1024, N_SAMPLES, 12, 1, threads)
         line["cpu_baseline"] = {"value": 1024 * len(times) / sum(times), "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": f"3 steps of a 1024-ray slice of the same workload (n_samples=128, shadows on, fwd+bwd+Adam), "
+                                "sample": f"{len(times)} steps of a 1024-ray slice of the same workload (n_samples=128, shadows on, fwd+bwd+Adam), "
                                           f"oracle restatement of the reference PyTorch path, torch CPU; {time.perf_counter() - t0:.0f} s"}
     print(json.dumps(line), flush=True)
 

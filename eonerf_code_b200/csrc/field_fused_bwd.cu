@@ -429,6 +429,10 @@ __device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
 // dw_j[k] += sum_m dpre[m, col0+j] X[m, k];  db_j += sum_m dpre[m, col0+j]     (narrow heads, K = 128 or 256 features
 // starting at 16-byte chunk `chunk0` of the blocked array).  256 threads = (256/lpr) rows x lpr chunks per sweep.
 struct HeadGradsB { float* dw[3]; float* db[3]; };
+#ifndef EONERF_HEADS_UNROLL
+#define EONERF_HEADS_UNROLL 8
+#endif
+constexpr int kHeadsUnroll = EONERF_HEADS_UNROLL;      // 16-byte loads in flight per thread
 template <int J>
 __global__ void __launch_bounds__(256) heads_dw_blocked_kernel(const uint8_t* __restrict__ X, int nb, int chunk0, int K, int64_t M,
                                                                const float* __restrict__ dpre, int col0, HeadGradsB G,
@@ -447,11 +451,11 @@ __global__ void __launch_bounds__(256) heads_dw_blocked_kernel(const uint8_t* __
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
   }
-  for (int64_t m0 = m_begin + rsub; m0 < m_end; m0 += 4 * rows) {
-    uint4 xv[4];
-    float dv[4][J];
+  for (int64_t m0 = m_begin + rsub; m0 < m_end; m0 += kHeadsUnroll * rows) {
+    uint4 xv[kHeadsUnroll];
+    float dv[kHeadsUnroll][J];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kHeadsUnroll; ++u) {
       const int64_t m = m0 + (int64_t)u * rows;
       if (m < m_end) {
         xv[u] = __ldg(blk_chunk(X, nb, m, chunk0 + sub));
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(256) heads_dw_blocked_kernel(const uint8_t* __
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kHeadsUnroll; ++u) {
       float x[8];
       unpack8(xv[u], x);
 #pragma unroll

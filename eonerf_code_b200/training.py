@@ -20,8 +20,13 @@ from .parallel import FlatGrads
 
 
 class TrainStep:
-    def __init__(self, radiance_field, n_samples=128, chunk=None, lr=5e-4, world=1, graph=False):
+    def __init__(self, radiance_field, n_samples=128, chunk=None, lr=5e-4, world=1, graph=False, micro_batch=None):
+        """micro_batch: rays per forward+backward pass.  A batch larger than that is processed in slices whose gradients
+        accumulate in the flat buffer before ONE optimiser step (the losses are batch means, so the sum of the slice losses
+        weighted by slice size is the loss of the whole batch): BASELINE configs[4]'s 65 536-ray batch keeps ~170 GB of
+        activations alive if rendered in one piece; 16 384-ray slices need a quarter of that."""
         self.field = radiance_field
+        self.micro_batch = micro_batch
         self.n_samples = n_samples
         self.render_step_size = (torch.tensor(2.0) / n_samples).item()      # fp32 quotient (train_eonerf.py:50-53)
         self.chunk = chunk
@@ -41,27 +46,40 @@ class TrainStep:
         self.n_rendered_total = None            # graph mode: running sum of n_rendering_samples, on the device
 
     # ------------------------------------------------------------------------------------------------------------------
-    def _forward_backward(self, rays, ts, pixels, epoch_idx, static):
+    def _forward_backward(self, rays, ts, pixels, epoch_idx, static, uniforms=None):
+        """uniforms: optional {u_cam, u_sun, u_cam2} [B,n] tensors replacing the device RNG (parity tests)."""
         self.field.train()
-        sat = define_satrays_from_tensors(rays, ts)
         if static or self.graph:               # graph replays update the parameters behind Python's back
             self.field._engine().refresh_prepared()
         self.grads.zero()
-        out, n_rendered, _ = sat_rendering.render_packed(self.field, None, sat, None, None, epoch_idx=epoch_idx,
-                                                         chunk=self.chunk or rays.shape[0], render_step_size=self.render_step_size,
-                                                         static=static)
-        if not static and n_rendered == 0:                                   # train_eonerf.py:135-136
+        B = rays.shape[0]
+        mb = self.micro_batch or B
+        total_loss, total_rendered = None, 0
+        for b0 in range(0, B, mb):
+            sl = slice(b0, min(B, b0 + mb))
+            sat = define_satrays_from_tensors(rays[sl], ts[sl])
+            us = None if uniforms is None else [{k: v[sl] for k, v in uniforms.items()}]
+            out, n_rendered, _ = sat_rendering.render_packed(self.field, None, sat, None, None, epoch_idx=epoch_idx,
+                                                             chunk=self.chunk or (sl.stop - sl.start), render_step_size=self.render_step_size,
+                                                             static=static, uniforms=us)
+            if not static and n_rendered == 0:                               # train_eonerf.py:135-136
+                continue
+            loss, _ = metrics.packed_loss(out, pixels[sl], epoch_idx)       # MSE (epoch < 2) / uncertainty-aware loss, value + gradient
+            if mb < B:
+                loss = loss * ((sl.stop - sl.start) / B)
+            loss.backward()
+            total_loss = loss.detach() if total_loss is None else total_loss + loss.detach()
+            total_rendered = total_rendered + n_rendered
+        if total_loss is None:
             return None, 0
-        loss, _ = metrics.packed_loss(out, pixels, epoch_idx)               # MSE (epoch < 2) / uncertainty-aware loss, value + gradient
-        loss.backward()
-        return loss.detach(), n_rendered
+        return total_loss, total_rendered
 
     def _update(self, averaged):
         self.optimizer.step(grad_scale=1.0 if (averaged or self.world == 1) else 1.0 / self.world)
 
-    def eager(self, rays, ts, pixels, epoch_idx):
+    def eager(self, rays, ts, pixels, epoch_idx, uniforms=None):
         """rays [B,11], ts [B,1] int64, pixels [B,3] on the device -> (loss tensor, n_rendering_samples int)."""
-        loss, n_rendered = self._forward_backward(rays, ts, pixels, epoch_idx, static=False)
+        loss, n_rendered = self._forward_backward(rays, ts, pixels, epoch_idx, static=False, uniforms=uniforms)
         if loss is None:
             return None, 0
         self.grads.all_reduce_mean(self.world)

@@ -218,3 +218,22 @@ def test_packed_loss_matches_reference_losses(cuda, epoch):
     (3.0 * loss_b).backward()
     close(a.grad, b.grad, 1e-5, 2e-6 * float(b.grad.abs().max()))    # the two terms of d/d beta cancel: absolute floor
     assert float(a.grad[:, 3:12].abs().max()) == 0.0 and float(a.grad[:, 13:].abs().max()) == 0.0
+
+
+def test_micro_batches_accumulate_to_the_full_batch_gradient(cuda):
+    """TrainStep(micro_batch=b): slices of the batch rendered and back-propagated one after the other, gradients accumulated in
+    the flat buffer, one Adam step — same loss and gradient as the whole batch at once (the losses are batch means)."""
+    from eonerf_code_b200.training import TrainStep
+    B, n, n_img = 384, 64, 5
+    p = O.init_params(n_img, seed=12, bias_scale=0.05)
+    rays, ts, pixels, us = _inputs(B, n, n_img, cuda, seed=40)
+    res = {}
+    for mb in (None, 128, 100):
+        m = make_model(p, n_img, cuda, "bf16_fused")
+        step = TrainStep(m, n_samples=n, micro_batch=mb)
+        loss, nren = step._forward_backward(rays, ts, pixels, 2, static=False, uniforms=us[0])
+        res[mb] = (float(loss), nren, step.grads.flat.clone())
+    for mb in (128, 100):
+        assert res[mb][1] == res[None][1]
+        assert abs(res[mb][0] - res[None][0]) <= 2e-6 * abs(res[None][0])
+        assert rel_err(res[mb][2], res[None][2]) < 3e-4, mb

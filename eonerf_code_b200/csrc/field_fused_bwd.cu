@@ -430,7 +430,7 @@ __device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
 // starting at 16-byte chunk `chunk0` of the blocked array).  256 threads = (256/lpr) rows x lpr chunks per sweep.
 struct HeadGradsB { float* dw[3]; float* db[3]; };
 #ifndef EONERF_HEADS_UNROLL
-#define EONERF_HEADS_UNROLL 8
+#define EONERF_HEADS_UNROLL 4
 #endif
 constexpr int kHeadsUnroll = EONERF_HEADS_UNROLL;      // 16-byte loads in flight per thread
 template <int J>
@@ -438,7 +438,10 @@ __global__ void __launch_bounds__(256) heads_dw_blocked_kernel(const uint8_t* __
                                                                const float* __restrict__ dpre, int col0, HeadGradsB G,
                                                                int64_t rows_per_block, const int64_t* __restrict__ M_dev) {
   __shared__ float red[8][J][264];
-  if (M_dev) M = __ldg(M_dev);
+  if (M_dev) {                     // live count on the device: re-balance the rows over the grid (multiples of 64 rows)
+    M = __ldg(M_dev);
+    rows_per_block = ((M + gridDim.x - 1) / gridDim.x + 63) & ~(int64_t)63;
+  }
   if ((int64_t)blockIdx.x * rows_per_block >= M) return;
   const int lpr = K >> 3, rows = 256 / lpr;
   const int sub = threadIdx.x % lpr, rsub = threadIdx.x / lpr;
@@ -512,7 +515,10 @@ __global__ void __launch_bounds__(256) class_grad_blocked_kernel(const uint8_t* 
                                                                  int64_t n_images, float* __restrict__ dcb, int64_t rows_per_block,
                                                                  int use_smem, const int64_t* __restrict__ M_dev) {
   extern __shared__ float tab[];
-  if (M_dev) M = __ldg(M_dev);
+  if (M_dev) {
+    M = __ldg(M_dev);
+    rows_per_block = ((M + gridDim.x - 1) / gridDim.x + 63) & ~(int64_t)63;
+  }
   if ((int64_t)blockIdx.x * rows_per_block >= M) return;
   const int sub = threadIdx.x & 15, rsub = threadIdx.x >> 4;
   const int64_t m_begin = (int64_t)blockIdx.x * rows_per_block;
@@ -584,9 +590,11 @@ __global__ void emb_grad_fused_kernel(const float* __restrict__ dcb, const float
 template <int J>
 static int run_heads_dw_blocked(const uint8_t* X, int nb, int chunk0, int K, int64_t M, const float* dpre, int col0, const HeadGradsB& G,
                                 cudaStream_t s, const int64_t* M_dev) {
-  int64_t rows = 1024;
-  while (div_up(M, rows) > 4 * 148) rows *= 2;
-  heads_dw_blocked_kernel<J><<<div_up(M, rows), 256, 0, s>>>(X, nb, chunk0, K, M, dpre, col0, G, rows, M_dev);
+  // a whole number of blocks per SM (4 x 148) when there is enough work, rows per block a multiple of 64
+  int64_t blocks = 4 * 148;
+  if (blocks > div_up(M, 1024)) blocks = div_up(M, 1024);
+  const int64_t rows = (div_up(M, blocks) + 63) & ~(int64_t)63;
+  heads_dw_blocked_kernel<J><<<(unsigned)div_up(M, rows), 256, 0, s>>>(X, nb, chunk0, K, M, dpre, col0, G, rows, M_dev);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -704,9 +712,10 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
       EO_CUDA(cudaMemsetAsync(dcb, 0, prm->n_images * kHid * 4, s));
       const int64_t tab_bytes = prm->n_images * kHid * 4;
       const int use_smem = tab_bytes <= 40 * 1024;
-      int64_t rows = 2048;
-      while (div_up(N, rows) > 4 * 148) rows *= 2;
-      class_grad_blocked_kernel<<<div_up(N, rows), 256, use_smem ? tab_bytes : 0, s>>>(garr(9), (const int32_t*)(st + S.cls), N, prm->n_images,
+      int64_t blocks = 4 * 148;
+      if (blocks > div_up(N, 2048)) blocks = div_up(N, 2048);
+      const int64_t rows = (div_up(N, blocks) + 63) & ~(int64_t)63;
+      class_grad_blocked_kernel<<<(unsigned)div_up(N, rows), 256, use_smem ? tab_bytes : 0, s>>>(garr(9), (const int32_t*)(st + S.cls), N, prm->n_images,
                                                                                        dcb, rows, use_smem, a->n_pts_dev);
       EO_LAUNCH_CHECK();
       const int nthreads = (int)(prm->n_images * 4 > kHid * 4 ? prm->n_images * 4 : kHid * 4);

@@ -20,5 +20,5 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
 tot = sum(e.device_time_total for e in rows)
 print(f"total device time {tot / 3e3:.3f} ms per step over {sum(e.count for e in rows) // 3} kernels/memops")
-for e in rows[:40]:
+for e in rows[:int(os.environ.get("TOPN", "40"))]:
     print(f"{e.device_time_total / 3:9.1f} us/step {e.count // 3:4d}x  {e.key[:110]}")

@@ -59,3 +59,34 @@ def mse(gt_rgb, rgb):
 
 def psnr(gt_rgb, rgb):
     return -10.0 * torch.log10(mse(gt_rgb, rgb))
+
+
+# ---- optional prior terms of the training loss (train_eonerf.py:144-156); element-wise torch on per-ray tensors ----------
+def update_loss_with_aux_term(loss, loss_dict, aux_loss, aux_dict, epoch, start_epoch=0, end_epoch=float("inf")):
+    """metrics.py:9-15: the auxiliary term counts only while start_epoch <= epoch < end_epoch; its entries are always logged."""
+    if start_epoch <= epoch < end_epoch:
+        loss = loss + aux_loss
+    loss_dict.update(aux_dict)
+    return loss, loss_dict
+
+
+def depth_loss_L2(gt_depth, pred_depth, gt_conf=None, w=100):
+    """metrics.py:24-31: w * mean squared depth error over the rays that have a prior (gt_depth >= 0) and, when
+    confidences are given, a confidence of at least 4."""
+    keep = gt_depth >= 0
+    if gt_conf is not None:
+        keep = keep & (gt_conf >= 4)
+    term = w * torch.mean(torch.square(pred_depth[keep] - gt_depth[keep]))
+    return term, {"depth_l2": term, "depth_weight": w}
+
+
+def shadow_loss_L2(smask, geo_shadows, epoch=None):
+    """metrics.py:36-58: squared difference to the prior shadow mask on the pixels the prior marks as shadow (smask <= 0.5),
+    averaged over them and weighted by their share of the batch; also reports the fraction of pixels rendered lit
+    (> 0.2) that the prior calls shadow."""
+    in_shadow = smask <= 0.5
+    lit_but_shadow = (geo_shadows > 0.2) & (smask < 0.5)
+    frac_to_penalize = lit_but_shadow.sum(dim=0) / torch.ones_like(smask).sum(dim=0)
+    mean_sq = torch.sum(in_shadow * torch.square(geo_shadows - smask)) / (torch.sum(in_shadow) + 1e-6)
+    term = torch.sum(in_shadow) / torch.sum(smask >= 0) * mean_sq
+    return term, {"shadows_term1": term, "shadow_vals_to_penalize": frac_to_penalize}

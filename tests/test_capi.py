@@ -97,3 +97,25 @@ def test_utmalt_epilogue_matches_reference_formula():
     # fp32 would lose centimetres at UTM magnitudes: the reason for the reference's double=True
     e32, _, _ = get_utmalt_from_nerf_prediction(rays, depth, scale, offset, double=False)
     assert float((e32.double() - e).abs().max()) > 1e-3
+
+
+def test_prior_loss_terms_follow_the_reference_definitions():
+    """metrics.py:9-58 (depth / shadow prior terms and the epoch window of auxiliary terms)."""
+    from eonerf_code_b200 import metrics
+    g = torch.Generator().manual_seed(0)
+    gt = torch.rand(200, 1, generator=g) * 2 - 0.3          # some negative = no prior
+    pred = torch.rand(200, 1, generator=g)
+    conf = torch.randint(0, 8, (200, 1), generator=g).float()
+    t, d = metrics.depth_loss_L2(gt, pred, conf, w=100)
+    keep = (gt >= 0) & (conf >= 4)
+    assert torch.allclose(t, 100 * ((pred[keep] - gt[keep]) ** 2).mean()) and d["depth_weight"] == 100
+    sm = (torch.rand(200, 1, generator=g) > 0.4).float()
+    geo = torch.rand(200, 1, generator=g)
+    t2, d2 = metrics.shadow_loss_L2(sm, geo)
+    ref = ((sm <= 0.5).sum() / (sm >= 0).sum()) * (((sm <= 0.5) * (geo - sm) ** 2).sum() / ((sm <= 0.5).sum() + 1e-6))
+    assert torch.allclose(t2, ref)
+    assert torch.allclose(d2["shadow_vals_to_penalize"], (((geo > 0.2) & (sm < 0.5)).sum(0) / 200.0))
+    base, logs = torch.tensor(1.0), {}
+    l_in, logs = metrics.update_loss_with_aux_term(base, logs, t, d, epoch=3, start_epoch=2, end_epoch=5)
+    l_out, _ = metrics.update_loss_with_aux_term(base, {}, t, d, epoch=5, start_epoch=2, end_epoch=5)
+    assert torch.allclose(l_in, base + t) and torch.allclose(l_out, base) and "depth_l2" in logs

@@ -18,6 +18,16 @@
 
 #include "fused_common.cuh"
 
+// EONERF_STORE_HINT=1: bulk stash stores carry an L2 evict_first policy
+#ifndef EONERF_STORE_HINT
+#define EONERF_STORE_HINT 1
+#endif
+#if EONERF_STORE_HINT
+#define EO_BULK_STORE(dst, src, bytes) bulk_store_hint(dst, src, bytes, l2_policy_evict_first())
+#else
+#define EO_BULK_STORE(dst, src, bytes) bulk_store(dst, src, bytes)
+#endif
+
 namespace eonerf {
 
 namespace {
@@ -99,7 +109,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         if (kTrain && kDutyStores) {
           for (int slot = 0; slot < 2; ++slot) {
             const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-            if (tile < n_tiles) bulk_store(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
+            if (tile < n_tiles) EO_BULK_STORE(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
           }
           tma_store_commit();
         }
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
               const FStage d = c_fstage[s];
               const int nb = d.halves * 2;
               for (int bb = 0; bb < nb; ++bb)
-                bulk_store(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes, kBlkBytes);
+                EO_BULK_STORE(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes, kBlkBytes);
               tma_store_commit();
             }
           }
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
       if (kTrain && store_id >= 0) {
         for (int slot = store_id; slot < 2; slot += kStoreThreads) {
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-          if (tile < n_tiles) bulk_store(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
+          if (tile < n_tiles) EO_BULK_STORE(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
         }
         tma_store_commit();
       }
@@ -374,7 +384,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           if (kTrain && store_id >= 0 && tile < n_tiles && !(p.training & 2)) {
             const int nb = d.halves * 2;                     // 16 KB blocks store_id, store_id + kStoreThreads, ... of the layer's output
             for (int bb = store_id; bb < nb; bb += kStoreThreads)
-              bulk_store(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes, kBlkBytes);
+              EO_BULK_STORE(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes, kBlkBytes);
             tma_store_commit();
           }
           if (valid && half == 0 && d.kind != 0) {

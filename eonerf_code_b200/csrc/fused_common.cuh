@@ -20,6 +20,11 @@ constexpr int kSlotBytes = 5 * kBlkBytes;                  // ACT blocks 0..3 + 
 constexpr int kOffRing = 0;
 constexpr int kOffSlot = kRingStages * kBlkBytes;          // 49152
 constexpr int kOffConst = kOffSlot + 2 * kSlotBytes;       // 212992
+// Ring depth R: R weight blocks, then two activation slots of 5 blocks (R = 3: ACT 0..3 + ENC/DENC) or of 4 blocks (R = 5: the
+// backward chain without position gradients needs no DENC block, so its weight ring gets the 32 KB).  Same total either way.
+__host__ __device__ constexpr int off_slot(int ring) { return ring * kBlkBytes; }
+__host__ __device__ constexpr int slot_bytes(int ring) { return (ring > 3 ? 4 : 5) * kBlkBytes; }
+static_assert(off_slot(5) + 2 * slot_bytes(5) == kOffConst && off_slot(3) + 2 * slot_bytes(3) == kOffConst, "layouts must end at the constants");
 constexpr int kConstBytes = 15872;
 constexpr int kOffPart = kOffConst + kConstBytes;          // [2 slots][128][2] floats
 constexpr int kOffBar = kOffPart + 2048;
@@ -160,16 +165,17 @@ struct FusedBars { uint64_t* w_full; uint64_t* w_empty; uint64_t* acc_full; uint
 // the weight stream: each CTA loads 1/kMC of every weight block and multicasts it, so L2 is read once per cluster.  A ring
 // slot is refilled only when ALL CTAs of the cluster have consumed it (every CTA's tcgen05.commit arrives on every
 // CTA's w_empty), which keeps the rings in lockstep.
-template <int kCG, int kMC = 1>
+template <int kCG, int kMC = 1, int kRing = kRingStages>
 __device__ __forceinline__ void fused_setup(uint8_t* smem, FusedBars& B, uint32_t*& tmem_base_s, uint32_t rank) {
+  static_assert((2 * kRing + 4) * 8 + 4 <= 128, "barrier region");
   B.w_full = (uint64_t*)(smem + kOffBar);
-  B.w_empty = B.w_full + kRingStages;
-  B.acc_full = B.w_empty + kRingStages;
+  B.w_empty = B.w_full + kRing;
+  B.acc_full = B.w_empty + kRing;
   B.act_ready = B.acc_full + 2;
   tmem_base_s = (uint32_t*)(B.act_ready + 2);
   if (threadIdx.x == 0) {
     const uint32_t n_arr = (kCG == 2 && rank == 0) ? 2 : 1;   // leader of a pair: + the peer epilogue's remote arrival
-    for (int s = 0; s < kRingStages; ++s) { mbar_init(&B.w_full[s], 1); mbar_init(&B.w_empty[s], kMC); }
+    for (int s = 0; s < kRing; ++s) { mbar_init(&B.w_full[s], 1); mbar_init(&B.w_empty[s], kMC); }
     for (int s = 0; s < 2; ++s) { mbar_init(&B.acc_full[s], 1); mbar_init(&B.act_ready[s], n_arr); }
     fence_barrier_init();
   }
@@ -190,7 +196,7 @@ __device__ __forceinline__ void fused_teardown(uint32_t tmem_base) {
 }
 
 // one thread: stream this CTA's weight blocks through the ring
-template <int kCG, int kMC = 1>
+template <int kCG, int kMC = 1, int kRing = kRingStages>
 __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uint8_t* wblob, const CUtensorMap* wmap, uint8_t* smem,
                                                const FusedBars& B, int64_t it0, int64_t n_items, int64_t it_stride, uint32_t rank) {
   int rs = 0; uint32_t rph = 0;
@@ -220,7 +226,7 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
             tma_load_2d_2cta(dst, wmap, &B.w_full[rs], 0, row0);
             if (d.halves == 2) tma_load_2d_2cta(dst + kBlkBytes / 2, wmap, &B.w_full[rs], 0, row0 + 64);
 #endif
-            if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+            if (++rs == kRing) { rs = 0; rph ^= 1; }
             continue;
           }
           mbar_expect_tx(&B.w_full[rs], bytes);
@@ -234,14 +240,14 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
 #else
           bulk_load(smem + kOffRing + rs * kBlkBytes, src + base + (size_t)b * kBlkBytes, bytes, &B.w_full[rs]);
 #endif
-          if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+          if (++rs == kRing) { rs = 0; rph ^= 1; }
         }
     }
 }
 
 // the whole MMA warp (kCG = 2: of the leader CTA), converged: issue the MMAs of every stage for both slots
 // kAccInit: the epilogue warps have pre-loaded every accumulator (with the layer's bias): the first MMA of a stage accumulates too
-template <int kCG, int kMC = 1, bool kAccInit = false>
+template <int kCG, int kMC = 1, bool kAccInit = false, int kRing = kRingStages>
 __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t* smem, const FusedBars& B, uint32_t tmem_base, int64_t it0,
                                                  int64_t n_items, int64_t it_stride) {
   int rs = 0; uint32_t rph = 0;
@@ -260,7 +266,7 @@ __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t
         { EO_T0(); mbar_wait(&B.act_ready[slot], (aph >> slot) & 1u); EO_T1(0); }
         aph ^= 1u << slot;
         tc_fence_after();
-        const uint32_t slot0 = smem_u32(smem + kOffSlot + slot * kSlotBytes);
+        const uint32_t slot0 = smem_u32(smem + off_slot(kRing) + slot * slot_bytes(kRing));
         for (int h = 0; h < n_h; ++h) {
           const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
           for (int kb = 0; kb < d.nkb; ++kb) {
@@ -278,7 +284,7 @@ __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t
               else umma_commit(&B.w_empty[rs]);
             }
             __syncwarp();
-            if (++rs == kRingStages) { rs = 0; rph ^= 1; }
+            if (++rs == kRing) { rs = 0; rph ^= 1; }
           }
         }
         if (elected) {

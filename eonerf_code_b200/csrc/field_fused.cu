@@ -71,17 +71,18 @@ struct FusedFwdParams {
 
 template <bool kTrain, int kCG, int kMC>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __grid_constant__ FusedFwdParams p, const __grid_constant__ CUtensorMap wmap) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* cst = (float*)(smem + kOffConst);
-  float* part = (float*)(smem + kOffPart);
+  float* cst = (float*)(smem + kFOffConst);              // shared-memory copy of the constants (kFwdConstG: unused)
+  float* part = (float*)(smem + kFOffPart);
   constexpr int kCl = kCG * kMC;                              // CTAs per cluster
   const uint32_t rank = kCl > 1 ? cluster_ctarank() : 0;
   FusedBars B;
   uint32_t* tmem_base_s;
-  fused_setup<kCG, kMC>(smem, B, tmem_base_s, rank);
+  fused_setup<kCG, kMC, kFwdRing>(smem, B, tmem_base_s, rank, kFOffBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < kCFloats; i += kFusedThreads) cst[i] = __ldg(p.consts + i);
+  if (!kFwdConstG)
+    for (int i = threadIdx.x; i < kCFloats; i += kFusedThreads) cst[i] = __ldg(p.consts + i);
   tc_fence_before();
   if (kCl > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -93,9 +94,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
   const int64_t it0 = blockIdx.x / kCl, it_stride = gridDim.x / kCl;
 
   if (warp == 0) {
-    if (lane == 0) fused_producer<kCG, kMC>(p.prog, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
+    if (lane == 0) fused_producer<kCG, kMC, kFwdRing>(p.prog, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
-    if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC, true>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);      // whole warp, converged
+    if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC, true, kFwdRing, 5>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);      // whole warp, converged
   } else if (kDutyWarp && warp == kDutyWarpId) {
     // ===== duty warp: mirrors the epilogue warps' named barriers; after each one, lane 0 hands the slot to the MMA issuer and
     // starts the stash store of what the epilogue wrote; before the next one it waits until that store has read shared memory =====
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         if (kTrain && kDutyStores) {
           for (int slot = 0; slot < 2; ++slot) {
             const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-            if (tile < n_tiles) EO_BULK_STORE(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
+            if (tile < n_tiles) EO_BULK_STORE(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kFOffSlot + slot * kFSlotBytes + 4 * kBlkBytes, kBlkBytes);
           }
           tma_store_commit();
         }
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
               const FStage d = c_fstage[s];
               const int nb = d.halves * 2;
               for (int bb = 0; bb < nb; ++bb)
-                EO_BULK_STORE(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes, kBlkBytes);
+                EO_BULK_STORE(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kFOffSlot + slot * kFSlotBytes + (d.out_blk + bb) * kBlkBytes, kBlkBytes);
               tma_store_commit();
             }
           }
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
     const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;                    // row of the tile
     const int store_id = kDutyStores ? -1 : store_thread_id(e);   // >= 0: this epilogue thread owns bulk stash stores
-    const uint32_t s_cst = smem_u32(cst);
+    const uint32_t s_cst = kFwdConstG ? 0u : smem_u32(cst);     // base "address" of the constants for cf4()
+    auto cscal = [&](int i) { return kFwdConstG ? __ldg(p.consts + kCScalars + i) : cst[kCScalars + i]; };
     const uint32_t s_part = smem_u32(part);
     uint32_t cph = 0;                               // bit `slot` = phase of acc_full[slot]
     uint64_t* const acc_full = B.acc_full;
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
             if (p.cls) p.cls[pt] = (int32_t)((cls_pack >> (16 * slot)) & 0xFFFFu);
           }
         }
-        const uint32_t enc = smem_u32(smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes);
+        const uint32_t enc = smem_u32(smem + kFOffSlot + slot * kFSlotBytes + 4 * kBlkBytes);
         uint32_t w[16];
         if (half == 0) {
 #pragma unroll
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float b0, b1, b2, b3;
-            lds_f4(sb + j * 16, b0, b1, b2, b3);
+            cf4<kFwdConstG>(p.consts, sb + j * 16, b0, b1, b2, b3);
             b[4 * j] = __float_as_uint(b0); b[4 * j + 1] = __float_as_uint(b1); b[4 * j + 2] = __float_as_uint(b2); b[4 * j + 3] = __float_as_uint(b3);
           }
           tmem_st32(t0 + c * 32, b);
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
       if (kTrain && store_id >= 0) {
         for (int slot = store_id; slot < 2; slot += kStoreThreads) {
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-          if (tile < n_tiles) EO_BULK_STORE(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + 4 * kBlkBytes, kBlkBytes);
+          if (tile < n_tiles) EO_BULK_STORE(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kFOffSlot + slot * kFSlotBytes + 4 * kBlkBytes, kBlkBytes);
         }
         tma_store_commit();
       }
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
           const int64_t pt = tile * kTileM + r;
           const bool valid = pt < M;
-          const uint32_t act = smem_u32(smem + kOffSlot + slot * kSlotBytes);
+          const uint32_t act = smem_u32(smem + kFOffSlot + slot * kFSlotBytes);
           // per-image part of the HD0 bias (transient half only): W[:,256:260] . emb[img]
           const float* delta_next = (has_next && dn.kind == 2) ? p.class_delta + (size_t)((cls_pack >> (16 * slot)) & 0xFFFFu) * kHid : nullptr;
           EO_TN(ta); { EO_T0(); mbar_wait(&acc_full[slot], (cph >> slot) & 1u); if (e == 0) EO_T1(3); }
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float b0, b1, b2, b3;
-              lds_f4(sb + j * 16, b0, b1, b2, b3);
+              cf4<kFwdConstG>(p.consts, sb + j * 16, b0, b1, b2, b3);
               b[4 * j] = __float_as_uint(b0); b[4 * j + 1] = __float_as_uint(b1); b[4 * j + 2] = __float_as_uint(b2); b[4 * j + 3] = __float_as_uint(b3);
             }
             if (delta_next && colg >= kHid) {
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 float w0, w1, w2, w3;
-                lds_f4(sw + j * 16, w0, w1, w2, w3);
+                cf4<kFwdConstG>(p.consts, sw + j * 16, w0, w1, w2, w3);
                 h0 = fmaf(bf_lo(pk[2 * j]), w0, h0); h0 = fmaf(bf_hi(pk[2 * j]), w1, h0);
                 h0 = fmaf(bf_lo(pk[2 * j + 1]), w2, h0); h0 = fmaf(bf_hi(pk[2 * j + 1]), w3, h0);
               }
@@ -314,11 +316,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
                 for (int j = 0; j < 8; ++j) {
                   float w0, w1, w2, w3;
                   const float a0 = bf_lo(pk[2 * j]), a1 = bf_hi(pk[2 * j]), a2 = bf_lo(pk[2 * j + 1]), a3 = bf_hi(pk[2 * j + 1]);
-                  lds_f4(sw + j * 16, w0, w1, w2, w3);
+                  cf4<kFwdConstG>(p.consts, sw + j * 16, w0, w1, w2, w3);
                   h0 = fmaf(a0, w0, h0); h0 = fmaf(a1, w1, h0); h0 = fmaf(a2, w2, h0); h0 = fmaf(a3, w3, h0);
-                  lds_f4(sw + 512 + j * 16, w0, w1, w2, w3);
+                  cf4<kFwdConstG>(p.consts, sw + 512 + j * 16, w0, w1, w2, w3);
                   h1 = fmaf(a0, w0, h1); h1 = fmaf(a1, w1, h1); h1 = fmaf(a2, w2, h1); h1 = fmaf(a3, w3, h1);
-                  lds_f4(sw + 1024 + j * 16, w0, w1, w2, w3);
+                  cf4<kFwdConstG>(p.consts, sw + 1024 + j * 16, w0, w1, w2, w3);
                   h2 = fmaf(a0, w0, h2); h2 = fmaf(a1, w1, h2); h2 = fmaf(a2, w2, h2); h2 = fmaf(a3, w3, h2);
                 }
               }
@@ -328,9 +330,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
               for (int j = 0; j < 8; ++j) {
                 float w0, w1, w2, w3;
                 const float a0 = bf_lo(pk[2 * j]), a1 = bf_hi(pk[2 * j]), a2 = bf_lo(pk[2 * j + 1]), a3 = bf_hi(pk[2 * j + 1]);
-                lds_f4(sw + j * 16, w0, w1, w2, w3);
+                cf4<kFwdConstG>(p.consts, sw + j * 16, w0, w1, w2, w3);
                 h0 = fmaf(a0, w0, h0); h0 = fmaf(a1, w1, h0); h0 = fmaf(a2, w2, h0); h0 = fmaf(a3, w3, h0);
-                lds_f4(sw + (kCWTb - kCWTs) * 4 + j * 16, w0, w1, w2, w3);
+                cf4<kFwdConstG>(p.consts, sw + (kCWTb - kCWTs) * 4 + j * 16, w0, w1, w2, w3);
                 h1 = fmaf(a0, w0, h1); h1 = fmaf(a1, w1, h1); h1 = fmaf(a2, w2, h1); h1 = fmaf(a3, w3, h1);
               }
             }
@@ -384,21 +386,21 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           if (kTrain && store_id >= 0 && tile < n_tiles && !(p.training & 2)) {
             const int nb = d.halves * 2;                     // 16 KB blocks store_id, store_id + kStoreThreads, ... of the layer's output
             for (int bb = store_id; bb < nb; bb += kStoreThreads)
-              EO_BULK_STORE(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kOffSlot + slot * kSlotBytes + (d.out_blk + bb) * kBlkBytes, kBlkBytes);
+              EO_BULK_STORE(p.arr[s] + ((size_t)tile * nb + bb) * kBlkBytes, smem + kFOffSlot + slot * kFSlotBytes + (d.out_blk + bb) * kBlkBytes, kBlkBytes);
             tma_store_commit();
           }
           if (valid && half == 0 && d.kind != 0) {
             float p0 = 0.f, p1 = 0.f;
             if (d.kind != 2) lds_f2(s_part + slot * 1024 + r * 8, p0, p1);
             if (d.kind == 1) {
-              p.sigma[pt] = softplus_f(h0 + p0 + cst[kCScalars + 0]);                          // eonerf.py:106,145
+              p.sigma[pt] = softplus_f(h0 + p0 + cscal(0));                          // eonerf.py:106,145
             } else if (d.kind == 2) {
-              p.rgb[3 * pt + 0] = sigmoid_f(h0 + cst[kCScalars + 1]);
-              p.rgb[3 * pt + 1] = sigmoid_f(h1 + cst[kCScalars + 2]);
-              p.rgb[3 * pt + 2] = sigmoid_f(h2 + cst[kCScalars + 3]);
+              p.rgb[3 * pt + 0] = sigmoid_f(h0 + cscal(1));
+              p.rgb[3 * pt + 1] = sigmoid_f(h1 + cscal(2));
+              p.rgb[3 * pt + 2] = sigmoid_f(h2 + cscal(3));
             } else {
-              p.ts[pt] = sigmoid_f(h0 + p0 + cst[kCScalars + 4]);
-              p.tb[pt] = softplus_f(h1 + p1 + cst[kCScalars + 5]);
+              p.ts[pt] = sigmoid_f(h0 + p0 + cscal(4));
+              p.tb[pt] = softplus_f(h1 + p1 + cscal(5));
             }
           }
           EO_TN(tg);
@@ -604,12 +606,12 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   do {                                                                                                                          \
     static bool configured = false;                                                                                             \
     if (!configured) {                                                                                                          \
-      EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true, CG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));  \
-      EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false, CG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused)); \
+      EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true, CG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));  \
+      EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false, CG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd)); \
       configured = true;                                                                                                        \
     }                                                                                                                           \
     profile_begin(3, flops, 0.0, s);                                                                                            \
-    rc = train ? launch_fused(fused_fwd_kernel<true, CG, MC>, csz, n_ctas, p, wmap, s) : launch_fused(fused_fwd_kernel<false, CG, MC>, csz, n_ctas, p, wmap, s); \
+    rc = train ? launch_fused(fused_fwd_kernel<true, CG, MC>, csz, n_ctas, p, wmap, s, kSmemFwd) : launch_fused(fused_fwd_kernel<false, CG, MC>, csz, n_ctas, p, wmap, s, kSmemFwd); \
   } while (0)
   if (mode == 1) EO_LAUNCH_FWD(1, 1);
   else if (mode == 2) EO_LAUNCH_FWD(2, 1);

@@ -29,6 +29,21 @@ constexpr int kConstBytes = 15872;
 constexpr int kOffPart = kOffConst + kConstBytes;          // [2 slots][128][2] floats
 constexpr int kOffBar = kOffPart + 2048;
 constexpr int kSmemFused = kOffBar + 128 + 1024;           // + alignment slack
+// Forward kernel: EONERF_FWD_RING = 4 buys a fourth weight-ring stage with the 15 KB constants block (biases, head weights), which
+// is then read through L1 from global memory instead, and with the 1 KB alignment slack (the dynamic shared-memory array is
+// declared 1024-byte aligned).  3: the constants are staged in shared memory as in the backward kernel.
+#ifndef EONERF_FWD_RING
+#define EONERF_FWD_RING 3
+#endif
+constexpr int kFwdRing = EONERF_FWD_RING;
+constexpr bool kFwdConstG = kFwdRing > 3;                  // constants from global memory
+constexpr int kFOffSlot = kFwdRing * kBlkBytes;
+constexpr int kFSlotBytes = 5 * kBlkBytes;
+constexpr int kFOffConst = kFOffSlot + 2 * kFSlotBytes;
+constexpr int kFOffPart = kFOffConst + (kFwdConstG ? 0 : kConstBytes);
+constexpr int kFOffBar = kFOffPart + 2048;
+constexpr int kSmemFwd = kFOffBar + 128 + (kFwdConstG ? 896 : 1024);   // + alignment slack (896: all that is left under 227 KB)
+static_assert(kSmemFwd <= 232448, "forward shared memory budget");
 // EONERF_DUTY_WARP = 1: an 11th warp joins every end-of-layer named barrier and does the after-barrier duties (signal the MMA
 // issuer, issue the bulk stash stores, wait for their shared-memory reads), so no epilogue warp has anything to do between
 // the barrier and the next accumulator.  0: two epilogue threads (kSignalThread, the store threads) do them.
@@ -94,6 +109,18 @@ __device__ __forceinline__ void sts_f2(uint32_t a, float x, float y) {
 }
 __device__ __forceinline__ void sts_u4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+// four consecutive constants: from the shared-memory copy (addr = shared address) or, when the forward keeps no copy, through L1
+// from the prepared blob (addr = byte offset into it)
+template <bool kGlobal>
+__device__ __forceinline__ void cf4(const float* gbase, uint32_t addr, float& x, float& y, float& z, float& w) {
+  if (kGlobal) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(gbase) + addr));
+    x = t.x; y = t.y; z = t.z; w = t.w;
+  } else {
+    lds_f4(addr, x, y, z, w);
+  }
 }
 
 // sin(a) for |a| < ~1e3: two-term Cody-Waite reduction to [-pi, pi] then MUFU.SIN.  Absolute error < 6e-7, far below
@@ -166,9 +193,9 @@ struct FusedBars { uint64_t* w_full; uint64_t* w_empty; uint64_t* acc_full; uint
 // slot is refilled only when ALL CTAs of the cluster have consumed it (every CTA's tcgen05.commit arrives on every
 // CTA's w_empty), which keeps the rings in lockstep.
 template <int kCG, int kMC = 1, int kRing = kRingStages>
-__device__ __forceinline__ void fused_setup(uint8_t* smem, FusedBars& B, uint32_t*& tmem_base_s, uint32_t rank) {
+__device__ __forceinline__ void fused_setup(uint8_t* smem, FusedBars& B, uint32_t*& tmem_base_s, uint32_t rank, int off_bar = kOffBar) {
   static_assert((2 * kRing + 4) * 8 + 4 <= 128, "barrier region");
-  B.w_full = (uint64_t*)(smem + kOffBar);
+  B.w_full = (uint64_t*)(smem + off_bar);
   B.w_empty = B.w_full + kRing;
   B.acc_full = B.w_empty + kRing;
   B.act_ready = B.acc_full + 2;
@@ -247,7 +274,7 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
 
 // the whole MMA warp (kCG = 2: of the leader CTA), converged: issue the MMAs of every stage for both slots
 // kAccInit: the epilogue warps have pre-loaded every accumulator (with the layer's bias): the first MMA of a stage accumulates too
-template <int kCG, int kMC = 1, bool kAccInit = false, int kRing = kRingStages>
+template <int kCG, int kMC = 1, bool kAccInit = false, int kRing = kRingStages, int kSlotBlk = (kRing > 3 ? 4 : 5)>
 __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t* smem, const FusedBars& B, uint32_t tmem_base, int64_t it0,
                                                  int64_t n_items, int64_t it_stride) {
   int rs = 0; uint32_t rph = 0;
@@ -266,7 +293,7 @@ __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t
         { EO_T0(); mbar_wait(&B.act_ready[slot], (aph >> slot) & 1u); EO_T1(0); }
         aph ^= 1u << slot;
         tc_fence_after();
-        const uint32_t slot0 = smem_u32(smem + off_slot(kRing) + slot * slot_bytes(kRing));
+        const uint32_t slot0 = smem_u32(smem + off_slot(kRing) + slot * (kSlotBlk * kBlkBytes));
         for (int h = 0; h < n_h; ++h) {
           const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
           for (int kb = 0; kb < d.nkb; ++kb) {
@@ -306,11 +333,11 @@ __device__ __forceinline__ void signal_act_ready(const FusedBars& B, int slot, u
 }
 
 template <class Kernel, class Params>
-static int launch_fused(Kernel kernel, int cg, int n_ctas, const Params& p, const CUtensorMap& wmap, cudaStream_t s) {
+static int launch_fused(Kernel kernel, int cg, int n_ctas, const Params& p, const CUtensorMap& wmap, cudaStream_t s, int smem_bytes = kSmemFused) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)n_ctas);
   cfg.blockDim = dim3(kFusedThreads);
-  cfg.dynamicSmemBytes = kSmemFused;
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

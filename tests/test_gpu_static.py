@@ -257,3 +257,33 @@ def test_graph_train_step_variants(cuda, epoch, micro):
         assert int(nr) > B
     assert all(l == l for l in losses) and losses[-1] < losses[0], losses
     assert int(step.n_rendered_total) > steps * B
+
+
+def test_static_eval_render_equals_eager_and_keeps_no_activations(cuda):
+    """Evaluation (eval=True under torch.no_grad(), the bench's render arm): the sync-free form gives the eager form's
+    outputs, chunked, and neither keeps an activation stash (inference kernels: memory stays flat)."""
+    from eonerf_code_b200 import sat_rendering
+    from eonerf_code_b200.datasets.satellite import define_satrays_from_tensors
+    from eonerf_code_b200.datasets.synthetic import make_rays
+    B, n, n_img = 700, 64, 5
+    p = O.init_params(n_img, seed=2, bias_scale=0.05)
+    m = make_model(p, n_img, cuda, "bf16_fused").eval()
+    rays, ts, _ = make_rays(B, n_img, seed=3, eval_mode=True)
+    rays, ts = rays.to(cuda), ts.to(cuda)
+    g = torch.Generator().manual_seed(8)
+    us = [dict(u_cam=torch.rand(c, n, generator=g).to(cuda), u_sun=torch.rand(c, n, generator=g).to(cuda),
+               u_cam2=torch.rand(c, n, generator=g).to(cuda)) for c in (256, 256, 188)]
+    out = {}
+    with torch.no_grad():
+        for static in (False, True):
+            torch.cuda.reset_peak_memory_stats()
+            base = torch.cuda.memory_allocated()
+            res, nren = sat_rendering.render_image(m, None, define_satrays_from_tensors(rays, ts), None, None, epoch_idx=2, chunk=256,
+                                                   render_step_size=2.0 / n, eval=True, uniforms=us,
+                                                   z_steps=torch.linspace(0, 1, n).to(cuda), static=static)
+            out[static] = (res, int(nren), torch.cuda.max_memory_allocated() - base)
+    assert out[True][1] == out[False][1] > 0
+    for k in out[False][0]:
+        close(out[True][0][k], out[False][0][k], 1e-6, 1e-7)
+    # a training-mode stash for one 256-ray chunk would be ~100 MB (6.3 KB x 16 k samples); inference stays far below
+    assert out[True][2] < 40e6 and out[False][2] < 40e6, (out[True][2], out[False][2])

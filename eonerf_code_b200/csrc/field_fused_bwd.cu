@@ -619,6 +619,27 @@ static int run_heads_dw_blocked(const uint8_t* X, int nb, int chunk0, int K, int
     if (_r != EONERF_OK) return _r; \
   } while (0)
 
+// The narrow-head / per-image-bias gradient kernels only depend on the chain kernel and touch other gradient tensors than the
+// grouped dW GEMM: they run on a side stream, forked after the chain and joined after the GEMM, so they overlap it (all of them
+// are HBM readers that do not saturate the bus on their own).  Fork and join are event edges, which a stream capture turns into
+// graph dependencies.  One side stream + two events per device, created on first use; EONERF_SIDE_STREAM=0 keeps one stream.
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream* side_stream() {
+  static SideStream per_dev[16];
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("EONERF_SIDE_STREAM"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& S = per_dev[dev];
+  if (!S.stream) {
+    if (cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking) != cudaSuccess) { S.stream = nullptr; cudaGetLastError(); return nullptr; }
+    cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&S.join, cudaEventDisableTiming);
+  }
+  return &S;
+}
+
 int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   EO_REQUIRE(a->field == EONERF_FIELD_EONERF, "fused precision mode supports the EO-NeRF field only");
   const int64_t N = a->n_pts;
@@ -708,6 +729,13 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
     return (int)EONERF_OK;
   };
   const float* dpre = p.dpre;
+  SideStream* side = side_stream();
+  cudaStream_t hs = s;                                      // stream of the head / per-image gradient kernels
+  if (side) {
+    EO_CUDA(cudaEventRecord(side->fork, s));
+    EO_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    hs = side->stream;
+  }
   if (!a->density_only) {
     // transient_mlp.3 / .2 / .1 : G_T3^T T2, G_T2^T T1, G_T1^T HD0[:,128:256]
     EO_TRY(dW(garr(12), 2, 0, 1, sarr(11), 2, 0, 2, kHid, G->trans_w[3], kHid, G->trans_b[3], nullptr, 0, nullptr));
@@ -719,30 +747,30 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
     EO_TRY(dW(garr(8), 4, 0, 2, sarr(7), 4, 0, 4, kW, G->bott_w, kW, G->bott_b, G->bott_w + (int64_t)kHid * kW, kW, G->bott_b + kHid));
     {  // narrow heads
       HeadGradsB hg{{G->ts_w, G->tb_w, nullptr}, {G->ts_b, G->tb_b, nullptr}};
-      EO_TRY(run_heads_dw_blocked<2>(sarr(12), 2, 0, kHid, N, dpre, 4, hg, s, a->n_pts_dev));
+      EO_TRY(run_heads_dw_blocked<2>(sarr(12), 2, 0, kHid, N, dpre, 4, hg, hs, a->n_pts_dev));
       HeadGradsB ha{{G->head1_w, G->head1_w + kHid, G->head1_w + 2 * kHid}, {G->head1_b, G->head1_b + 1, G->head1_b + 2}};
-      EO_TRY(run_heads_dw_blocked<3>(sarr(9), 4, 0, kHid, N, dpre, 1, ha, s, a->n_pts_dev));
+      EO_TRY(run_heads_dw_blocked<3>(sarr(9), 4, 0, kHid, N, dpre, 1, ha, hs, a->n_pts_dev));
     }
     {  // transient embedding / W_t0[:,256:260] through the per-image bias rows
       float* dcb = (float*)(sc + C.dcb);
-      EO_CUDA(cudaMemsetAsync(dcb, 0, prm->n_images * kHid * 4, s));
+      EO_CUDA(cudaMemsetAsync(dcb, 0, prm->n_images * kHid * 4, hs));
       const int64_t tab_bytes = prm->n_images * kHid * 4;
       const int use_smem = tab_bytes <= 40 * 1024;
       int64_t blocks = 4 * 148;
       if (blocks > div_up(N, 2048)) blocks = div_up(N, 2048);
       const int64_t rows = (div_up(N, blocks) + 63) & ~(int64_t)63;
-      class_grad_blocked_kernel<<<(unsigned)div_up(N, rows), 256, use_smem ? tab_bytes : 0, s>>>(garr(9), (const int32_t*)(st + S.cls), N, prm->n_images,
+      class_grad_blocked_kernel<<<(unsigned)div_up(N, rows), 256, use_smem ? tab_bytes : 0, hs>>>(garr(9), (const int32_t*)(st + S.cls), N, prm->n_images,
                                                                                        dcb, rows, use_smem, a->n_pts_dev);
       EO_LAUNCH_CHECK();
       const int nthreads = (int)(prm->n_images * 4 > kHid * 4 ? prm->n_images * 4 : kHid * 4);
-      emb_grad_fused_kernel<<<div_up(nthreads, 128), 128, 0, s>>>(dcb, prm->trans_w[0], prm->transient_emb, prm->n_images, G->transient_emb,
+      emb_grad_fused_kernel<<<div_up(nthreads, 128), 128, 0, hs>>>(dcb, prm->trans_w[0], prm->transient_emb, prm->n_images, G->transient_emb,
                                                                    G->trans_w[0]);
       EO_LAUNCH_CHECK();
     }
   }
   {  // sigma head
-    HeadGradsB hs{{G->sigma_w, nullptr, nullptr}, {G->sigma_b, nullptr, nullptr}};
-    EO_TRY(run_heads_dw_blocked<1>(sarr(7), 4, 0, kW, N, dpre, 0, hs, s, a->n_pts_dev));
+    HeadGradsB hsig{{G->sigma_w, nullptr, nullptr}, {G->sigma_b, nullptr, nullptr}};
+    EO_TRY(run_heads_dw_blocked<1>(sarr(7), 4, 0, kW, N, dpre, 0, hsig, hs, a->n_pts_dev));
   }
   // trunk: layer i reads X = H_{i-1} (layer 5: [H4 | enc], layer 0: enc)
   for (int i = 7; i >= 1; --i) {
@@ -754,7 +782,12 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   }
   EO_TRY(dW(garr(0), 4, 0, 2, sarr(kArrEnc), 1, 0, 1, 63, G->trunk_w[0], 63, G->trunk_b[0], G->trunk_w[0] + (int64_t)kHid * 63, 63,
             G->trunk_b[0] + kHid));
-  return gemm_tn_blocked_group(gemms, n_gemms, s);
+  rc = gemm_tn_blocked_group(gemms, n_gemms, s);
+  if (side) {                                               // join: whatever follows on `s` also follows the head kernels
+    EO_CUDA(cudaEventRecord(side->join, side->stream));
+    EO_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+  }
+  return rc;
 }
 
 }  // namespace eonerf

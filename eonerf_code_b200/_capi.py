@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeonerf_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 COMP_COLS = 12
 OUT_COLS = 21
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16_FUSED = 0, 1, 2, 3
@@ -142,7 +142,7 @@ class DwArgs(C.Structure):
 
 class AdamArgs(C.Structure):
     _fields_ = [("param", P), ("grad", P), ("exp_avg", P), ("exp_avg_sq", P), ("n", I64), ("step", P),
-                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("grad_scale", F32)]
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("grad_scale", F32), ("lr_dev", P)]
 
 
 class GatherBatchArgs(C.Structure):
@@ -221,14 +221,18 @@ def check(rc, what=""):
         raise RuntimeError(f"eonerf_b200 {what} failed ({rc}): {msg}")
 
 
-_device_ok = False
+_device_ok = set()
 
 
-def require_device():
-    global _device_ok
-    if not _device_ok:
-        check(lib().eonerf_check_device(), "check_device")
-        _device_ok = True
+def require_device(index=None):
+    """Raises unless the CUDA device (default: the current one) is sm_100; checked once per device."""
+    import torch
+    if index is None:
+        index = torch.cuda.current_device()
+    if index not in _device_ok:
+        with torch.cuda.device(index):
+            check(lib().eonerf_check_device(), "check_device")
+        _device_ok.add(index)
 
 
 def call(name, args, stream):

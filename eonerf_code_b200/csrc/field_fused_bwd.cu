@@ -19,6 +19,7 @@
 //  8      H5            base_mlp.5[:,0:256]   mask H4                                          G_H4
 //  9..12  H4..H1        base_mlp.4 .. .1      mask H3..H0                                      G_H3..G_H0
 //  13     H0            base_mlp.0            + G_ENC5, positional-encoding backward           g_x (only if wanted)
+#include <vector>
 #include "fused_common.cuh"
 
 // EONERF_STORE_HINT=1: bulk stash stores carry an L2 evict_first policy
@@ -623,22 +624,56 @@ static int run_heads_dw_blocked(const uint8_t* X, int nb, int chunk0, int K, int
 // grouped dW GEMM: they run on a side stream, forked after the chain and joined after the GEMM, so they overlap it (all of them
 // are HBM readers that do not saturate the bus on their own).  Fork and join are event edges, which a stream capture turns into
 // graph dependencies.  One side stream + two events per device, created on first use; EONERF_SIDE_STREAM=0 keeps one stream.
-struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
-static SideStream* side_stream() {
-  static SideStream per_dev[16];
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("EONERF_SIDE_STREAM"); enabled = e ? atoi(e) : 1; }
+struct SideStream { int dev = -1; cudaStream_t owner = nullptr; cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+// One side stream + event pair per (host thread, device, caller stream): two host threads, or one thread driving two streams,
+// never share (and re-record) the same events.  thread_local => no locking; entries live as long as the thread.
+static SideStream* side_stream(cudaStream_t owner) {
+  static const int enabled = [] { const char* e = getenv("EONERF_SIDE_STREAM"); return e ? atoi(e) : 1; }();
   if (!enabled) return nullptr;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  SideStream& S = per_dev[dev];
-  if (!S.stream) {
-    if (cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking) != cudaSuccess) { S.stream = nullptr; cudaGetLastError(); return nullptr; }
-    cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&S.join, cudaEventDisableTiming);
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  thread_local std::vector<SideStream> table;
+  for (SideStream& S : table)
+    if (S.dev == dev && S.owner == owner) return &S;
+  if (table.size() >= 64) return nullptr;                   // a caller cycling through many streams: stay on one stream
+  SideStream S;
+  S.dev = dev; S.owner = owner;
+  if (cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&S.join, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    if (S.stream) cudaStreamDestroy(S.stream);
+    if (S.fork) cudaEventDestroy(S.fork);
+    return nullptr;
   }
-  return &S;
+  table.reserve(64);                                        // pointers handed out stay valid
+  table.push_back(S);
+  return &table.back();
 }
+
+// Fork / join of the side stream with the join guaranteed on every exit path: an early error return between fork and join
+// would otherwise leave the side stream's work unordered against whatever the caller launches next on `s` (and, under stream
+// capture, leave the capture with an unjoined branch).
+struct SideFork {
+  SideStream* side; cudaStream_t s; bool forked = false;
+  SideFork(SideStream* side_, cudaStream_t s_) : side(side_), s(s_) {}
+  int fork() {
+    if (!side) return EONERF_OK;
+    EO_CUDA(cudaEventRecord(side->fork, s));
+    EO_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    forked = true;
+    return EONERF_OK;
+  }
+  cudaStream_t stream() const { return forked ? side->stream : s; }
+  int join() {
+    if (!forked) return EONERF_OK;
+    forked = false;
+    EO_CUDA(cudaEventRecord(side->join, side->stream));
+    EO_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+    return EONERF_OK;
+  }
+  ~SideFork() { if (forked) { cudaEventRecord(side->join, side->stream); cudaStreamWaitEvent(s, side->join, 0); } }
+};
 
 int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   EO_REQUIRE(a->field == EONERF_FIELD_EONERF, "fused precision mode supports the EO-NeRF field only");
@@ -729,13 +764,9 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
     return (int)EONERF_OK;
   };
   const float* dpre = p.dpre;
-  SideStream* side = side_stream();
-  cudaStream_t hs = s;                                      // stream of the head / per-image gradient kernels
-  if (side) {
-    EO_CUDA(cudaEventRecord(side->fork, s));
-    EO_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-    hs = side->stream;
-  }
+  SideFork side(side_stream(s), s);
+  EO_TRY(side.fork());
+  cudaStream_t hs = side.stream();                          // stream of the head / per-image gradient kernels
   if (!a->density_only) {
     // transient_mlp.3 / .2 / .1 : G_T3^T T2, G_T2^T T1, G_T1^T HD0[:,128:256]
     EO_TRY(dW(garr(12), 2, 0, 1, sarr(11), 2, 0, 2, kHid, G->trans_w[3], kHid, G->trans_b[3], nullptr, 0, nullptr));
@@ -783,10 +814,7 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   EO_TRY(dW(garr(0), 4, 0, 2, sarr(kArrEnc), 1, 0, 1, 63, G->trunk_w[0], 63, G->trunk_b[0], G->trunk_w[0] + (int64_t)kHid * 63, 63,
             G->trunk_b[0] + kHid));
   rc = gemm_tn_blocked_group(gemms, n_gemms, s);
-  if (side) {                                               // join: whatever follows on `s` also follows the head kernels
-    EO_CUDA(cudaEventRecord(side->join, side->stream));
-    EO_CUDA(cudaStreamWaitEvent(s, side->join, 0));
-  }
+  EO_TRY(side.join());                                      // whatever follows on `s` also follows the head kernels
   return rc;
 }
 

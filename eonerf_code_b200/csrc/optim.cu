@@ -12,7 +12,8 @@ namespace eonerf {
 __global__ void adam_tick_kernel(EonerfAdamArgs a) {
   const float t = a.step[0] + 1.0f;
   a.step[0] = t;
-  a.step[1] = (float)(a.lr / (1.0 - pow(a.beta1, (double)t)));
+  const double lr = a.lr_dev ? *a.lr_dev : a.lr;
+  a.step[1] = (float)(lr / (1.0 - pow(a.beta1, (double)t)));
   a.step[2] = (float)sqrt(1.0 - pow(a.beta2, (double)t));
 }
 

@@ -52,7 +52,8 @@ class DeviceRayLoader:
         a = K.GatherBatchArgs(self.all_rays.data_ptr(), self.all_rays.stride(0), self.all_rgbs.data_ptr(), self.all_rgbs.stride(0),
                               self.all_ts.data_ptr(), perm.data_ptr(), self.n, first, batch, out["rays"].data_ptr(), out["rgbs"].data_ptr(),
                               out["ts"].data_ptr(), out["idx"].data_ptr())
-        K.call("gather_batch", a, torch.cuda.current_stream().cuda_stream)
+        with torch.cuda.device(dev):
+            K.call("gather_batch", a, torch.cuda.current_stream().cuda_stream)
         return out
 
     def __iter__(self):

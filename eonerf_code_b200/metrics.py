@@ -9,10 +9,12 @@ import ctypes as C
 import torch
 
 from . import _capi as K
+from .ops import on_tensor_device
 
 
 class _PackedLossFn(torch.autograd.Function):
     @staticmethod
+    @on_tensor_device
     def forward(ctx, out, gt_rgb, mode):
         if not out.is_cuda:
             raise RuntimeError("packed_loss runs on sm_100 GPUs only (there is no CPU fallback)")
@@ -31,6 +33,7 @@ class _PackedLossFn(torch.autograd.Function):
         return terms[0], terms
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, g_loss, _g_terms):
         (g_out,) = ctx.saved_tensors
         return g_out * g_loss, None, None

@@ -39,10 +39,60 @@ def _rows(t):
 
 
 def _need_cuda(*ts):
+    """Every tensor on ONE sm_100 device, and that device current (the kernels launch on its current stream)."""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("eonerf_code_b200 runs on sm_100 GPUs only: got a CPU tensor (there is no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"eonerf_code_b200: tensors on different devices ({dev} and {t.device})")
+    if dev is not None and dev.index != torch.cuda.current_device():
+        raise RuntimeError(f"eonerf_code_b200: tensors live on {dev} but the current device is cuda:{torch.cuda.current_device()} "
+                           "(internal error: the entry points switch to the tensors' device, see on_tensor_device)")
     K.require_device()
+
+
+def tensor_device(*objs):
+    """Device of the first CUDA tensor found in objs (namedtuples / lists / dicts are searched one level deep)."""
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            if o.is_cuda:
+                return o.device
+        elif isinstance(o, (tuple, list)):
+            for x in o:
+                if isinstance(x, torch.Tensor) and x.is_cuda:
+                    return x.device
+        elif isinstance(o, torch.nn.Module):
+            for x in o.parameters():
+                if x.is_cuda:
+                    return x.device
+                break
+        elif isinstance(o, FieldEngine):
+            for x in o.named.values():
+                if x.is_cuda:
+                    return x.device
+                break
+    return None
+
+
+def on_tensor_device(fn):
+    """Run fn with the CUDA device of its first CUDA tensor argument made current.  The reference picks its GPU with
+    `device=f"cuda:{args.gpu_id}"` and never calls set_device (train_eonerf.py:39-41): as a drop-in with gpu_id != 0 the
+    kernels must be launched on that device's stream, not on device 0's."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        dev = tensor_device(*a, *k.values())
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*a, **k)
+        with torch.cuda.device(dev):
+            return fn(*a, **k)
+    return wrapped
 
 
 _Z_STEPS = {}
@@ -59,6 +109,7 @@ def z_steps_for(n, device):
 # ------------------------------------------------------------------------------------------------
 # sampling
 # ------------------------------------------------------------------------------------------------
+@on_tensor_device
 def sample_compact(origins, viewdirs, near, u, z_steps=None, redraw_of=None):
     """Stratified samples + cube mask + compaction (sat_rendering.py:56-84, :10-16).
     Returns worst-case-sized buffers (ray_indices, t_starts, t_ends), pts_per_ray[B] fp32, ray_offsets[B+1], stats[2]
@@ -99,6 +150,7 @@ def sample_compact(origins, viewdirs, near, u, z_steps=None, redraw_of=None):
     return ri, ts, te, ppr, offs, stats
 
 
+@on_tensor_device
 def pack_info(ray_indices, n_rays):
     """ray_offsets[B+1] from sorted ray_indices (nerfacc pack_info)."""
     _need_cuda(ray_indices)
@@ -108,6 +160,7 @@ def pack_info(ray_indices, n_rays):
     return offs
 
 
+@on_tensor_device
 def set_last_t_end(t_ends, ray_offsets, value=1e10):
     """In place: t_ends[last sample of each ray] = 1e10 (eonerf.py:218-220)."""
     n_rays = ray_offsets.numel() - 1
@@ -119,6 +172,7 @@ def set_last_t_end(t_ends, ray_offsets, value=1e10):
 # ------------------------------------------------------------------------------------------------
 class _WeightsFn(torch.autograd.Function):
     @staticmethod
+    @on_tensor_device
     def forward(ctx, t_starts, t_ends, sigmas, ray_offsets):
         _need_cuda(t_starts, t_ends, sigmas)
         ts, te, sg = _f32(t_starts).contiguous(), _f32(t_ends).contiguous(), _f32(sigmas).contiguous()
@@ -130,6 +184,7 @@ class _WeightsFn(torch.autograd.Function):
         return w, T, al
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, gw, gT, ga):
         ts, te, sg, offs = ctx.saved_tensors
         c = lambda g: None if g is None else _f32(g).contiguous()
@@ -142,6 +197,7 @@ class _WeightsFn(torch.autograd.Function):
 
 class _AccumFn(torch.autograd.Function):
     @staticmethod
+    @on_tensor_device
     def forward(ctx, weights, values, ray_offsets):
         _need_cuda(weights)
         w = _f32(weights).contiguous()
@@ -156,6 +212,7 @@ class _AccumFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, g_out):
         w, v, offs = ctx.saved_tensors
         g_out = _f32(g_out).contiguous()
@@ -244,6 +301,7 @@ class FieldEngine:
         self._prepared_key = None
         return self.prepared()
 
+    @on_tensor_device
     def prepared(self):
         """Operand-layout weights, rebuilt when any parameter changed (optimizer steps bump ._version)."""
         key = (self.precision,) + tuple((t.data_ptr(), t._version) for t in self.named.values())
@@ -299,6 +357,7 @@ class FieldEngine:
     def scratch_bytes(self, n):
         return K.lib().eonerf_field_scratch_bytes(self.field, self.precision, n, self.n_images)
 
+    @on_tensor_device
     def fwd(self, n, density_only, x=None, rays=None, img_idx=None, cond_dirs=None, want_z=False, keep=True, n_dev=None):
         """rays = (origins, viewdirs, ray_indices, t_starts, t_ends).  Returns dict of outputs + stash.
         keep=False (inference): the fused mode keeps no activations at all; the layered modes still need the buffer.
@@ -350,6 +409,7 @@ class FieldEngine:
         K.call("field_fwd", a, _stream())
         return out
 
+    @on_tensor_device
     def bwd(self, n, density_only, fwd_out, g_sigma=None, g_rgb=None, g_ts=None, g_tb=None, grads_struct=None, want_gx=False,
             n_dev=None):
         dev = fwd_out["sigma"].device
@@ -370,6 +430,7 @@ class FieldEngine:
         return gx
 
     # --- per-ray ambient MLP (eonerf.py:163-164) --------------------------------------------
+    @on_tensor_device
     def ambient_fwd(self, sundirs):
         sd, ss_ = _rows(sundirs)
         B = sd.shape[0]
@@ -381,6 +442,7 @@ class FieldEngine:
         K.call("ambient_fwd", a, _stream())
         return amb, stash
 
+    @on_tensor_device
     def ambient_bwd(self, amb, stash, g_amb, grad_views):
         B = amb.shape[0]
         scratch = torch.empty(B * 136, dtype=torch.float32, device=amb.device)
@@ -403,6 +465,7 @@ class _FieldFn(torch.autograd.Function):
     """EONerfMLP.forward / query_density / VanillaNeRFRadianceField.forward on explicit positions."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, grad_on, engine, density_only, x, img_idx, cond_dirs, *params):
         """grad_on: torch.is_grad_enabled() at the call site (inside forward() autograd always reports it off; under
         torch.no_grad() nothing is stashed)."""
@@ -419,6 +482,7 @@ class _FieldFn(torch.autograd.Function):
         return out["sigma"][:, None], out["rgb"]
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, *gs):
         e = ctx.engine
         c = lambda g: None if g is None else _f32(g).contiguous()
@@ -433,6 +497,7 @@ class _FieldFn(torch.autograd.Function):
 
 class _AmbientFn(torch.autograd.Function):
     @staticmethod
+    @on_tensor_device
     def forward(ctx, engine, sundirs, *params):
         _need_cuda(sundirs)
         amb, stash = engine.ambient_fwd(sundirs)
@@ -440,6 +505,7 @@ class _AmbientFn(torch.autograd.Function):
         return amb
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, g):
         e = ctx.engine
         flat, views, _, direct = e.grads_for_backward()
@@ -463,6 +529,7 @@ class _CameraPassFn(torch.autograd.Function):
     Output comp[B,12]: 0:3 albedo, 3 depth, 4 beta(+0.05), 5 transient_s, 6:9 ambient (not yet x0.2), 9 sum(w)."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, grad_on, engine, only_depth, origins, viewdirs, sundirs, img_idx, ri, ts, te, offs, n_dev, *params):
         """n_dev: None, or int64[1] on the device = live sample count P (ri / ts / te then have their full capacity)."""
         _need_cuda(origins, viewdirs, ri, ts, te)
@@ -487,6 +554,7 @@ class _CameraPassFn(torch.autograd.Function):
         return comp
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, g_comp):
         e = ctx.engine
         B, P, ts, te, offs, f, amb, amb_stash, n_dev = ctx.keep
@@ -516,6 +584,7 @@ class _SunPassFn(torch.autograd.Function):
     query, transmittance in front of the last kept sample.  Differentiable in `depth` and the parameters."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, grad_on, engine, origins, viewdirs, sundirs, depth, n_samples, u_sun, z_steps, info, static, *params):
         """static=True: no host read of the sun-sample count Q (buffers keep their capacity, kernels read Q on the device)."""
         _need_cuda(origins, viewdirs, sundirs, depth)
@@ -544,6 +613,7 @@ class _SunPassFn(torch.autograd.Function):
         return geo
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, g_geo):
         e = ctx.engine
         B, Q, ts2, te2, offs2, f2, geo, dd, ds_, n_dev = ctx.keep
@@ -567,6 +637,7 @@ class _EpilogueFn(torch.autograd.Function):
     """Irradiance model + radiometric normalisation + 21-column packing (sat_rendering.py:265,269-276,288-312)."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, comp, geo, ppr, sc_ppr, img_idx, eval_mode, rad, n_images, rad_sink=None):
         """rad_sink: optional fp32 [n_img,9] tensor the radiometric-embedding gradient is accumulated into directly."""
         _need_cuda(comp)
@@ -582,6 +653,7 @@ class _EpilogueFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, g_out):
         comp, geo, ii, eval_mode, rad, n_images, rad_sink = ctx.keep
         B, dev = comp.shape[0], comp.device

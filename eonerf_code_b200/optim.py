@@ -28,6 +28,10 @@ class FlatAdam(torch.optim.Adam):
         self.flat_exp_avg_sq = torch.zeros_like(self.flat_param)
         self._step_buf = torch.zeros(4, dtype=torch.float32, device=ref.device)    # [step, lr/(1-b1^t), sqrt(1-b2^t), -]
         self.step_t = self._step_buf[0]                                            # torch keeps `step` as an fp32 tensor
+        # the learning rate lives on the device too: a captured step reads it there, so a scheduler / a manual
+        # param_groups[0]["lr"] change reaches graph replays through sync_hyper() (train_eonerf.py:64,304: StepLR)
+        self._lr_buf = torch.full((1,), float(lr), dtype=torch.float64, device=ref.device)
+        self._lr_synced = float(lr)
         for p, off in zip(params, self._offsets):
             n = p.numel()
             if p.dtype != torch.float32:
@@ -55,10 +59,30 @@ class FlatAdam(torch.optim.Adam):
             self.step_t.copy_(torch.as_tensor(st["step"], dtype=torch.float32))
         self._bind_state()
 
+    def state_dict(self):
+        """torch.optim.Adam's layout with an INDEPENDENT fp32 scalar `step` per parameter: inside this optimiser all
+        parameters share one device-side counter, and saving that aliasing would make a stock (non-capturable)
+        torch.optim.Adam increment the shared tensor once per parameter per iteration after load_state_dict."""
+        sd = super().state_dict()
+        for st in sd["state"].values():
+            if "step" in st:
+                st["step"] = st["step"].detach().clone()
+        return sd
+
+    def sync_hyper(self):
+        """Refresh the device-side learning rate from param_groups (no-op unless it changed).  `step()` calls it; a caller
+        that replays a captured step calls it before the replay."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_synced:
+            self._lr_buf.fill_(lr)
+            self._lr_synced = lr
+
     @torch.no_grad()
     def step(self, closure=None, grad_scale=1.0):
         if closure is not None:
             raise RuntimeError("FlatAdam.step does not take a closure")
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_hyper()
         first, last = self._params[0], self._params[-1]
         if (first.data_ptr() != self.flat_param.data_ptr()
                 or last.data_ptr() != self.flat_param.data_ptr() + 4 * self._offsets[-1]
@@ -67,7 +91,8 @@ class FlatAdam(torch.optim.Adam):
         g = self.param_groups[0]
         a = K.AdamArgs(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.flat_exp_avg.data_ptr(),
                        self.flat_exp_avg_sq.data_ptr(), self.flat_param.numel(), self._step_buf.data_ptr(),
-                       g["lr"], g["betas"][0], g["betas"][1], g["eps"], grad_scale)
-        K.call("adam_step", a, torch.cuda.current_stream().cuda_stream)
+                       g["lr"], g["betas"][0], g["betas"][1], g["eps"], grad_scale, self._lr_buf.data_ptr())
+        with torch.cuda.device(self.flat_param.device):
+            K.call("adam_step", a, torch.cuda.current_stream().cuda_stream)
         for p in self._params:                            # the kernel wrote behind autograd's back: bump the version counters
             torch.autograd.graph.increment_version(p)      # (ops.FieldEngine.prepared() keys its weight cache on them)

@@ -87,13 +87,14 @@ class TrainStep:
         return loss, n_rendered
 
     # ------------------------------------------------------------------------------------------------------------------
-    def _capture(self, rays, ts, pixels, epoch_idx):
-        g = {"rays": rays.clone(), "ts": ts.clone(), "pixels": pixels.clone()}
+    def _capture(self, rays, ts, pixels, epoch_idx, uniforms=None):
+        g = {"rays": rays.clone(), "ts": ts.clone(), "pixels": pixels.clone(),
+             "uniforms": None if uniforms is None else {k: v.clone() for k, v in uniforms.items()}}
         lib = K.lib()
         before = int(lib.eonerf_launch_count(0))
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1, capture_error_mode="thread_local"):
-            loss, n = self._forward_backward(g["rays"], g["ts"], g["pixels"], epoch_idx, static=True)
+            loss, n = self._forward_backward(g["rays"], g["ts"], g["pixels"], epoch_idx, static=True, uniforms=g["uniforms"])
             self.n_rendered_total += n
             if self.world == 1:
                 self._update(averaged=True)
@@ -106,30 +107,43 @@ class TrainStep:
         self.launches_per_step = int(lib.eonerf_launch_count(0)) - before
         return g
 
-    def __call__(self, rays, ts, pixels, epoch_idx):
+    def _params_changed(self):
+        """A graph replay ran Adam behind Python's back: bump the parameters' version counters so that every consumer keyed
+        on them (ops.FieldEngine.prepared(): the operand-layout weights an eval render_image uses) sees the new values."""
+        for p in self.optimizer._params:
+            torch.autograd.graph.increment_version(p)
+
+    def __call__(self, rays, ts, pixels, epoch_idx, uniforms=None):
         """Eager: as `eager`.  Graph mode: -> (loss, n_rendering_samples) as 0-d device tensors that the next call
-        overwrites; the very first call runs eagerly (it also initialises the optimiser state), the second captures."""
+        overwrites; the very first call runs eagerly (it also initialises the optimiser state), the second captures.
+        uniforms: optional {u_cam, u_sun, u_cam2} [B,n] replacing the device RNG (parity tests); in graph mode they are
+        copied into the captured step's own buffers like the batch."""
         if not self.graph:
-            return self.eager(rays, ts, pixels, epoch_idx)
+            return self.eager(rays, ts, pixels, epoch_idx, uniforms=uniforms)
         if self.n_rendered_total is None:
             self.n_rendered_total = torch.zeros((), dtype=torch.int64, device=rays.device)
         if not self._first_done:
             self._first_done = True
-            loss, n = self._forward_backward(rays, ts, pixels, epoch_idx, static=True)
+            loss, n = self._forward_backward(rays, ts, pixels, epoch_idx, static=True, uniforms=uniforms)
             self.n_rendered_total += n
             if self.world > 1:
                 torch.distributed.all_reduce(self.grads.flat)
             self._update(averaged=False)
             return loss, n
-        key = (epoch_idx >= 2, tuple(rays.shape), rays.device)
+        key = (epoch_idx >= 2, tuple(rays.shape), rays.device, uniforms is not None)
         g = self._graphs.get(key)
         if g is None:
-            g = self._graphs[key] = self._capture(rays, ts, pixels, epoch_idx)
+            g = self._graphs[key] = self._capture(rays, ts, pixels, epoch_idx, uniforms)
         g["rays"].copy_(rays, non_blocking=True)
         g["ts"].copy_(ts, non_blocking=True)
         g["pixels"].copy_(pixels, non_blocking=True)
+        if uniforms is not None:
+            for k, v in g["uniforms"].items():
+                v.copy_(uniforms[k], non_blocking=True)
+        self.optimizer.sync_hyper()            # the captured Adam reads lr on the device: follow schedulers between replays
         g["g1"].replay()
         if self.world > 1:
             torch.distributed.all_reduce(self.grads.flat)
             g["g2"].replay()
+        self._params_changed()
         return g["loss"], g["n"]

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 11
+#define EONERF_ABI_VERSION 12
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -370,6 +370,9 @@ int eonerf_linear_dw(const EonerfDwArgs* a, eonerf_stream_t stream);
  * an fp32 tensor), incremented by one per call; [1], [2] scratch for this step's lr/(1-beta1^t) and sqrt(1-beta2^t), which
  * a one-thread kernel computes in double precision before the update kernel: the same two launches can be replayed from a
  * CUDA graph.  grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).
+ * lr_dev (optional): one DEVICE double holding the learning rate; when set it overrides `lr`, so a captured step follows
+ * a scheduler (StepLR(gamma=0.9), train_eonerf.py:64,304) through a host->device refresh of that double instead of
+ * replaying the value frozen at capture time.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
@@ -377,6 +380,7 @@ typedef struct {
   float* step;
   double lr; double beta1; double beta2; double eps;
   float grad_scale;
+  const double* lr_dev;
 } EonerfAdamArgs;
 int eonerf_adam_step(const EonerfAdamArgs* a, eonerf_stream_t stream);
 

@@ -280,14 +280,14 @@ def _last_sample_index(ray_indices):
     return torch.cumsum(counts, 0) - 1
 
 
-def rendering(p, rays, t_starts, t_ends, ray_indices):
+def rendering(p, rays, t_starts, t_ends, ray_indices, emulate_bf16=False):
     """eonerf.py:196-248.  NOTE mutates t_ends in place like the reference (:220)."""
     n_rays = rays.origins.shape[0]
     z = ((t_starts + t_ends)[:, None] / 2.0).to(rays.origins.dtype)
     x = rays.origins[ray_indices] + rays.viewdirs[ray_indices] * z
     t_ends[_last_sample_index(ray_indices)] = 1e10
     t_starts, t_ends = t_starts.to(z.dtype), t_ends.to(z.dtype)
-    sigma, albedo, ambient, ts, tb = field_forward(p, x, rays.sundirs[ray_indices], rays.img_idx[ray_indices])
+    sigma, albedo, ambient, ts, tb = field_forward(p, x, rays.sundirs[ray_indices], rays.img_idx[ray_indices], emulate_bf16)
     w, trans, alphas = nv.render_weight_from_density(t_starts, t_ends, sigma.squeeze(-1),
                                                      ray_indices=ray_indices, n_rays=n_rays)
     acc = lambda v: nv.accumulate_along_rays(w, values=v, ray_indices=ray_indices, n_rays=n_rays)
@@ -309,7 +309,7 @@ def render_depth(p, rays, t_starts, t_ends, ray_indices):
     return nv.accumulate_along_rays(w, values=z, ray_indices=ray_indices, n_rays=n_rays)
 
 
-def geometric_shadows(p, rays, depth, n_samples, u_sun, z_steps=None):
+def geometric_shadows(p, rays, depth, n_samples, u_sun, z_steps=None, emulate_bf16=False):
     """sat_rendering.py:87-118: secondary rays from the rendered surface point towards the sun;
     shadow = transmittance *before* the last kept sample of each sun ray; 1 for rays with no samples."""
     n_rays = rays.origins.shape[0]
@@ -320,7 +320,7 @@ def geometric_shadows(p, rays, depth, n_samples, u_sun, z_steps=None):
     z = ((ts + te)[:, None] / 2.0).to(sc_o.dtype)
     ts, te = ts.to(sc_o.dtype), te.to(sc_o.dtype)
     x = sc_o[ri] + sc_d[ri] * z
-    sigma = query_density(p, x).squeeze(-1)
+    sigma = query_density(p, x, emulate_bf16).squeeze(-1)
     trans, _ = nv.render_transmittance_from_density(ts, te, sigma, ray_indices=ri, n_rays=n_rays)
     geo = torch.ones((n_rays, 1), dtype=sc_o.dtype)
     if ri.numel():
@@ -337,15 +337,20 @@ OUT_KEYS = OrderedDict([  # sat_rendering.py:322-334
 
 
 def render_chunk(p, rays, n_samples, epoch_idx, u_cam, u_sun=None, u_cam2=None, eval=False,
-                 radiometric=True, z_steps=None, return_extras=False):
-    """One iteration of the chunk loop of sat_rendering.py:252-313 → out [B, 21], n_samples_rendered."""
+                 radiometric=True, z_steps=None, return_extras=False, emulate_bf16=False, force_redraw=None,
+                 eval_img=None):
+    """One iteration of the chunk loop of sat_rendering.py:252-313 → out [B, 21], n_samples_rendered.
+    emulate_bf16: the MLPs round where the CUDA bf16 path rounds (see field_forward).
+    force_redraw / eval_img: for callers that evaluate a chunk of the reference in independent slices of rays
+    (render_chunk_sliced): the chunk-wide decisions of :259-262 ("any ray empty -> draw again") and :288-289
+    (eval: image index of the chunk's first ray) are then made by the caller over the whole chunk."""
     n_rays = rays.origins.shape[0]
     ri, ts, te, _ = satnerf_sampling(rays.origins, rays.viewdirs, n_samples, u_cam, near=rays.t_near, z_steps=z_steps)
     ppr = pts_per_ray(ri, n_rays)
-    if torch.sum(ppr == 0):                                                      # :260-262
+    if bool(torch.sum(ppr == 0)) if force_redraw is None else force_redraw:      # :260-262
         assert u_cam2 is not None, "a ray kept no samples: the reference re-draws, pass u_cam2"
         ri, ts, te, _ = satnerf_sampling(rays.origins, rays.viewdirs, n_samples, u_cam2, near=None, z_steps=z_steps)
-    albedo, depth, beta, tr_s, ambient, entropy, ex = rendering(p, rays, ts, te, ri)
+    albedo, depth, beta, tr_s, ambient, entropy, ex = rendering(p, rays, ts, te, ri, emulate_bf16)
     ambient = ambient * 0.2                                                       # :265
     sc_ex = None
     if epoch_idx < 2:                                                             # :269-272
@@ -353,9 +358,10 @@ def render_chunk(p, rays, n_samples, epoch_idx, u_cam, u_sun=None, u_cam2=None, 
         s = geo
         sc_ppr = torch.ones_like(ppr)
     else:
-        geo, sc_ppr, sc_ex = geometric_shadows(p, rays, depth, n_samples, u_sun, z_steps=z_steps)
+        geo, sc_ppr, sc_ex = geometric_shadows(p, rays, depth, n_samples, u_sun, z_steps=z_steps, emulate_bf16=emulate_bf16)
         s = geo * tr_s                                                            # :276
-    img = (torch.ones(n_rays, dtype=torch.long) * rays.img_idx[0]) if eval else rays.img_idx.reshape(-1)  # :288-291
+    first_img = rays.img_idx[0] if eval_img is None else eval_img
+    img = (torch.ones(n_rays, dtype=torch.long) * first_img) if eval else rays.img_idx.reshape(-1)  # :288-291
     rgb = albedo * s + (1 - s) * (ambient * albedo)                               # :294
     if radiometric:
         emb = p["radiometricT_enc.weight"][img]
@@ -404,8 +410,59 @@ def loss_from_out(out, pixels, epoch_idx):
     return uncertainty_aware_loss(pixels, out[:, 0:3], out[:, 12:13])
 
 
+def chunk_needs_redraw(rays, n_samples, u_cam, z_steps=None):
+    """sat_rendering.py:258-260: does any ray of the chunk keep no sample under the first draw?"""
+    ri, _, _, _ = satnerf_sampling(rays.origins, rays.viewdirs, n_samples, u_cam, near=rays.t_near, z_steps=z_steps)
+    return bool(torch.sum(pts_per_ray(ri, rays.origins.shape[0]) == 0))
+
+
+def _slices(n, k):
+    return [slice(i, min(n, i + k)) for i in range(0, n, k)]
+
+
+def _take(us, sl):
+    return None if us is None else us[sl]
+
+
+def render_chunk_sliced(p, rays, n_samples, epoch_idx, u_cam, u_sun=None, u_cam2=None, eval=False, radiometric=True,
+                        emulate_bf16=False, rays_per_slice=1024, z_steps=None):
+    """render_chunk on a chunk too large for one CPU pass: rays are independent, so the chunk is evaluated
+    in slices; the two chunk-wide decisions of the reference (re-draw, eval image index) are taken over the whole chunk
+    first.  Returns (out [B,21], n_rendering_samples) exactly as render_chunk would on the whole chunk."""
+    B = rays.origins.shape[0]
+    redraw = chunk_needs_redraw(rays, n_samples, u_cam, z_steps)
+    outs, total = [], 0
+    for sl in _slices(B, rays_per_slice):
+        o, k = render_chunk(p, SatRays(*[r[sl] for r in rays]), n_samples, epoch_idx, u_cam[sl], _take(u_sun, sl), _take(u_cam2, sl),
+                            eval=eval, radiometric=radiometric, z_steps=z_steps, emulate_bf16=emulate_bf16, force_redraw=redraw,
+                            eval_img=rays.img_idx[0])
+        outs.append(o)
+        total += k
+    return torch.cat(outs, 0), total
+
+
+def train_step_grads_sliced(p, rays, pixels, n_samples, epoch_idx, u_cam, u_sun=None, u_cam2=None, radiometric=True,
+                            emulate_bf16=False, rays_per_slice=1024):
+    """train_step_grads on a batch too large for one CPU autograd pass: the losses are batch means (metrics.py:17-22), so
+    the gradient of the batch is the size-weighted sum of the slices' gradients.  -> (loss, out, grads, n_rendered)."""
+    B = rays.origins.shape[0]
+    redraw = chunk_needs_redraw(rays, n_samples, u_cam)
+    q = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
+    outs, total, loss_sum = [], 0, 0.0
+    for sl in _slices(B, rays_per_slice):
+        o, k = render_chunk(q, SatRays(*[r[sl] for r in rays]), n_samples, epoch_idx, u_cam[sl], _take(u_sun, sl), _take(u_cam2, sl),
+                            radiometric=radiometric, emulate_bf16=emulate_bf16, force_redraw=redraw)
+        loss = loss_from_out(o, pixels[sl], epoch_idx) * ((sl.stop - sl.start) / B)
+        loss.backward()
+        outs.append(o.detach())
+        loss_sum += float(loss.detach())
+        total += k
+    grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v))) for k, v in q.items())
+    return torch.tensor(loss_sum), torch.cat(outs, 0), grads, total
+
+
 def train_step_grads(p, rays, pixels, n_samples, epoch_idx, u_cam, u_sun=None, u_cam2=None, radiometric=True,
-                     dtype=None):
+                     dtype=None, emulate_bf16=False):
     """forward + loss + backward; returns (loss, out, {name: grad}, n_rendering_samples).  dtype=torch.float64 runs
     everything but the sampler in double precision (conditioning reference for the gradient tests)."""
     if dtype is not None:
@@ -413,7 +470,8 @@ def train_step_grads(p, rays, pixels, n_samples, epoch_idx, u_cam, u_sun=None, u
         rays = SatRays(*[r if r.dtype == torch.int64 else r.to(dtype) for r in rays])
         pixels = pixels.to(dtype)
     q = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
-    out, n_rendered = render_chunk(q, rays, n_samples, epoch_idx, u_cam, u_sun, u_cam2, radiometric=radiometric)
+    out, n_rendered = render_chunk(q, rays, n_samples, epoch_idx, u_cam, u_sun, u_cam2, radiometric=radiometric,
+                                   emulate_bf16=emulate_bf16)
     loss = loss_from_out(out, pixels, epoch_idx)
     loss.backward()
     grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v))) for k, v in q.items())

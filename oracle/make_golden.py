@@ -170,12 +170,88 @@ def gen_volrend(ref):
     print("volrend: ok")
 
 
+def gen_redraw(ref):
+    """The zero-sample re-draw branch (sat_rendering.py:259-262): three rays start at t_near=3 (every first-draw sample is
+    below the cube) so the whole chunk is sampled again with near=None and a second set of uniforms; one ray never enters
+    the cube at all (still empty after the re-draw: zero weights, depth 0, beta = beta_min, geo_shadow = 1).  pts_per_ray
+    keeps the FIRST draw's counts (:258, :308)."""
+    B, n_arg, epoch, n_img = 48, 32, 2, 6
+    p = O.init_params(n_img, seed=21, bias_scale=0.05)
+    m = ref_model(ref, p, n_img)
+    rays, ts, pixels = make_rays(B, n_img, seed=9, variant="spread")
+    rays[[3, 17, 40], 6] = 3.0
+    rays[11, 0:3] = torch.tensor([3.0, 3.0, 1.0])
+    step = (torch.tensor(2.0) / n_arg).item()
+    n = int(2 / step)
+    g = torch.Generator().manual_seed(77)
+    u_cam, u_cam2, u_sun = (torch.rand(B, n, generator=g) for _ in range(3))
+    sr = ref.satellite.define_satrays_from_tensors(rays, ts)
+    m.train()
+    with ref_harness.FixedRand([u_cam, u_cam2, u_sun]) as fr:
+        res, nren = ref.sat_rendering.render_image(m, None, sr, None, None, epoch_idx=epoch, chunk=B, render_step_size=step)
+        assert not fr.queue, "the reference did not take the re-draw branch"
+    out_ref = torch.cat([res[k] for k in O.OUT_KEYS], 1)
+    loss, _ = ref.metrics.uncertainty_aware_loss(pixels, res["rgb"], res["beta"])
+    m.zero_grad()
+    loss.backward()
+    gref = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in m.named_parameters()}
+    loss_o, out_o, gora, nren_o = O.train_step_grads(p, O.satrays_from_table(rays, ts), pixels, n, epoch, u_cam, u_sun, u_cam2)
+    assert nren == nren_o
+    assert (out_ref[:, 14] == 0).sum() == 4 and float(out_ref[11, 3]) == 0.0
+    assert torch.allclose(out_ref.detach(), out_o, rtol=1e-5, atol=1e-6), (out_ref.detach() - out_o).abs().max()
+    assert torch.allclose(loss.detach(), loss_o, rtol=1e-5)
+    for k in gref:
+        assert torch.allclose(gref[k], gora[k], rtol=2e-4, atol=1e-7), k
+    np.savez_compressed(os.path.join(GOLD, "redraw.npz"), rays=rays.numpy(), ts=ts.numpy(), pixels=pixels.numpy(),
+                        u_cam=u_cam.numpy(), u_cam2=u_cam2.numpy(), u_sun=u_sun.numpy(), n=np.int64(n), epoch=np.int64(epoch),
+                        n_img=np.int64(n_img), out=out_ref.detach().numpy(), loss=loss.detach().numpy(),
+                        n_rendering_samples=np.int64(nren), fingerprint=param_fingerprint(p),
+                        grad_norms=np.array([float(gref[k].double().norm()) for k in gref]),
+                        grad_names=np.array(list(gref.keys())))
+    print(f"redraw: n={n} n_rendering_samples={nren} loss={float(loss):.6f} empty first-draw rays=4")
+
+
+def gen_vanilla(ref):
+    """VanillaNeRFRadianceField (mlp.py:211-250): forward(x, viewdirs) -> (rgb, sigma), query_density, and the parameter
+    gradients of a scalar loss, from the reference class itself."""
+    N = 300
+    p = O.init_vanilla_params(seed=51, bias_scale=0.1)
+    m = ref.mlp.VanillaNeRFRadianceField()
+    missing, unexpected = m.load_state_dict(p, strict=False)
+    assert not unexpected and all("scales" in k for k in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(52)
+    x = torch.rand(N, 3, generator=g) * 3 - 1.5
+    d = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=1)
+    rgb, sigma = m(x, d)
+    dens = m.query_density(x)
+    with torch.no_grad():
+        rgb_o, sigma_o = O.vanilla_forward(p, x, d)
+    assert torch.allclose(rgb.detach(), rgb_o, rtol=1e-6, atol=1e-6) and torch.allclose(sigma.detach(), sigma_o, rtol=1e-6, atol=1e-6)
+    assert torch.equal(dens, sigma)
+    w_rgb, w_sig = torch.rand(N, 3, generator=g), torch.rand(N, 1, generator=g)
+    ((rgb * w_rgb).sum() + (sigma * w_sig).sum()).backward()
+    gref = {k: v.grad for k, v in m.named_parameters()}
+    np.savez_compressed(os.path.join(GOLD, "vanilla.npz"), seed=51, bias_scale=0.1, fingerprint=param_fingerprint(p), x=x.numpy(),
+                        viewdirs=d.numpy(), rgb=rgb.detach().numpy(), sigma=sigma.detach().numpy(), w_rgb=w_rgb.numpy(),
+                        w_sigma=w_sig.numpy(), grad_names=np.array(list(gref.keys())),
+                        grad_norms=np.array([float(v.double().norm()) for v in gref.values()]),
+                        **{"grad__" + k: v.numpy() for k, v in gref.items() if v.numel() <= 768})
+    print("vanilla: ok", tuple(rgb.shape), tuple(sigma.shape), f"sigma>0: {(sigma > 0).float().mean():.2f}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_harness.load()
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:                       # python -m oracle.make_golden redraw vanilla
+        for name in only:
+            globals()["gen_" + name](ref)
+        sys.exit(0)
     gen_sampling(ref)
     gen_field(ref)
     gen_volrend(ref)
     gen_render(ref)
+    gen_redraw(ref)
+    gen_vanilla(ref)
     print("golden fixtures written to", GOLD)

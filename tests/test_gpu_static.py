@@ -287,3 +287,131 @@ def test_static_eval_render_equals_eager_and_keeps_no_activations(cuda):
         close(out[True][0][k], out[False][0][k], 1e-6, 1e-7)
     # a training-mode stash for one 256-ray chunk would be ~100 MB (6.3 KB x 16 k samples); inference stays far below
     assert out[True][2] < 40e6 and out[False][2] < 40e6, (out[True][2], out[False][2])
+
+
+def test_graph_step_follows_lr_changes(cuda):
+    """A scheduler (StepLR(gamma=0.9), train_eonerf.py:64,304) or a manual param_groups[0]['lr'] change must reach the
+    captured Adam: lr lives in a device double the captured kernel reads, refreshed before each replay."""
+    from eonerf_code_b200.training import TrainStep
+    B, n, n_img = 256, 32, 4
+    p = O.init_params(n_img, seed=14, bias_scale=0.05)
+    rays, ts, pixels, us = _inputs(B, n, n_img, cuda, seed=70)
+    lrs = [5e-4, 5e-4, 5e-4, 5e-5, 5e-5, 1e-3]
+    res = {}
+    for mode in ("graph", "eager"):
+        m = make_model(p, n_img, cuda, "bf16_fused")
+        step = TrainStep(m, n_samples=n, graph=(mode == "graph"))
+        sched_seen = []
+        for lr in lrs:
+            step.optimizer.param_groups[0]["lr"] = lr
+            if mode == "graph":
+                step(rays, ts, pixels, 2, uniforms=us[0])
+            else:
+                step._forward_backward(rays, ts, pixels, 2, static=True, uniforms=us[0])
+                step._update(averaged=True)
+            sched_seen.append(float(step.optimizer._lr_buf))
+        assert sched_seen == lrs
+        res[mode] = {k: v.detach().clone() for k, v in m.named_parameters()}
+    for k in res["eager"]:                               # same tolerance logic as test_graph_train_step_matches_eager_steps
+        d = (res["graph"][k] - res["eager"][k]).abs()
+        assert float(d.max()) <= 2 * sum(lrs) + 1e-7, k
+        assert float((d > 0.5 * 5e-4).float().mean()) < 0.05, (k, float((d > 0.5 * 5e-4).float().mean()))
+    # and the change is not a no-op: with lr frozen at capture (5e-4) the last three steps would move differently
+    m = make_model(p, n_img, cuda, "bf16_fused")
+    step = TrainStep(m, n_samples=n, graph=True)
+    for _ in lrs:
+        step(rays, ts, pixels, 2, uniforms=us[0])
+    k = "base_mlp.hidden_layers.3.weight"
+    frozen = dict(m.named_parameters())[k].detach()
+    assert float((frozen - res["graph"][k]).abs().max()) > 1e-4
+
+
+def test_eval_between_graph_steps_sees_current_weights(cuda):
+    """Graph replays run Adam behind Python's back; an eval render between replays must use the weights the optimiser just
+    wrote (the operand-layout cache is keyed on the parameters' versions, which TrainStep bumps after every replay)."""
+    from eonerf_code_b200 import sat_rendering
+    from eonerf_code_b200.datasets.satellite import define_satrays_from_tensors
+    from eonerf_code_b200.training import TrainStep
+    B, n, n_img = 256, 32, 4
+    p = O.init_params(n_img, seed=15, bias_scale=0.05)
+    rays, ts, pixels, us = _inputs(B, n, n_img, cuda, seed=71)
+    m = make_model(p, n_img, cuda, "bf16_fused")
+    step = TrainStep(m, n_samples=n, graph=True, lr=5e-3)
+
+    def evaluate(model):
+        with torch.no_grad():
+            res, _ = sat_rendering.render_image(model, None, define_satrays_from_tensors(rays, ts), None, None, epoch_idx=2, chunk=B,
+                                                render_step_size=2.0 / n, eval=True, uniforms=us,
+                                                z_steps=torch.linspace(0, 1, n).to(cuda))
+        return res["rgb"].clone()
+
+    for round_ in range(3):
+        for _ in range(3):
+            step(rays, ts, pixels, 2, uniforms=us[0])
+        got = evaluate(m)
+        fresh = make_model({k: v.detach().cpu() for k, v in m.state_dict().items() if "scales" not in k}, n_img, cuda, "bf16_fused")
+        want = evaluate(fresh)                           # a new module built from the current master weights
+        assert torch.equal(got, want), round_
+
+
+def test_flat_adam_state_dict_loads_into_stock_adam(cuda):
+    """FlatAdam.state_dict() must not leak its shared step counter: a stock torch.optim.Adam that loads it increments `step`
+    once per parameter per iteration (aliased tensors would be bumped 8x here)."""
+    from eonerf_code_b200.optim import FlatAdam
+    from eonerf_code_b200.parallel import FlatGrads
+    torch.manual_seed(1)
+    shapes = [(19, 4), (256, 63), (256,), (1, 256), (1,), (3, 128), (128, 260), (7,)]
+    pa = [torch.nn.Parameter(torch.randn(*s, device=cuda)) for s in shapes]
+    pb = [torch.nn.Parameter(t.detach().clone()) for t in pa]
+    pc = [torch.nn.Parameter(t.detach().clone()) for t in pa]
+    fg = FlatGrads(pa)
+    opt_a, opt_b = FlatAdam(pa, fg.flat, lr=5e-4), torch.optim.Adam(pb, lr=5e-4)
+    grads = [[torch.randn_like(b) for b in pb] for _ in range(5)]
+    for it in range(3):
+        for a, b, g in zip(pa, pb, grads[it]):
+            a.grad.copy_(g)
+            b.grad = g.clone()
+        opt_a.step()
+        opt_b.step()
+    sd = opt_a.state_dict()
+    steps = [st["step"] for st in sd["state"].values()]
+    assert len({s.data_ptr() for s in steps}) == len(steps) and all(float(s) == 3.0 for s in steps)
+    import io
+    buf = io.BytesIO()
+    torch.save(sd, buf)                                  # through a checkpoint file, as train_eonerf.py:185-191 does
+    buf.seek(0)
+    opt_c = torch.optim.Adam(pc, lr=5e-4)
+    for c, a in zip(pc, pa):
+        c.data.copy_(a.data)
+    opt_c.load_state_dict(torch.load(buf))
+    for it in (3, 4):
+        for b, c, g in zip(pb, pc, grads[it]):
+            b.grad = g.clone()
+            c.grad = g.clone()
+        opt_b.step()
+        opt_c.step()
+    for b, c in zip(pb, pc):
+        assert float(opt_c.state[c]["step"]) == 5.0
+        close(c, b, 2e-6, 1e-7)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_non_default_device(cuda):
+    """gpu_id != 0 as the reference selects it (device=f"cuda:{args.gpu_id}", no set_device): kernels must run on the tensors'
+    device and stream, and give the same numbers as on device 0."""
+    from eonerf_code_b200 import sat_rendering
+    from eonerf_code_b200.datasets.satellite import define_satrays_from_tensors
+    B, n, n_img = 128, 32, 4
+    p = O.init_params(n_img, seed=16, bias_scale=0.05)
+    rays, ts, pixels, us = _inputs(B, n, n_img, cuda, seed=72)
+    outs = []
+    for dev in (torch.device("cuda:0"), torch.device("cuda:1")):
+        m = make_model(p, n_img, dev, "bf16_fused")
+        u = [{k: v.to(dev) for k, v in us[0].items()}]
+        assert torch.cuda.current_device() == 0
+        res, _ = sat_rendering.render_image(m, None, define_satrays_from_tensors(rays.to(dev), ts.to(dev)), None, None, epoch_idx=2,
+                                            chunk=B, render_step_size=2.0 / n, uniforms=u, z_steps=torch.linspace(0, 1, n).to(dev))
+        res["rgb"].sum().backward()
+        outs.append((res["rgb"].detach().cpu(), m.base_mlp.hidden_layers[3].weight.grad.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel_err(outs[1][1], outs[0][1]) < 2e-4

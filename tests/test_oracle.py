@@ -114,3 +114,65 @@ def test_analytic_identities():
         out, _ = O.render_chunk(p, O.satrays_from_table(rays, ts), 32, 0, u)
     assert torch.equal(out[:, 0:3], torch.clip(out[:, 4:7], 0, 1))
     assert torch.all(out[:, 13] == 1) and torch.all(out[:, 15:18] == 1) and torch.all(out[:, 10] == 1)
+
+
+def test_redraw_branch_against_reference_outputs(golden):
+    """sat_rendering.py:259-262 (zero-sample re-draw) pinned by the reference's own outputs, tests/golden/redraw.npz."""
+    g = golden["redraw"]
+    n_img, n, epoch = int(g["n_img"]), int(g["n"]), int(g["epoch"])
+    p = O.init_params(n_img, seed=21, bias_scale=0.05)
+    np.testing.assert_allclose(fingerprint(p), g["fingerprint"], rtol=1e-12)
+    rays, ts, pixels = t(g["rays"]), t(g["ts"]), t(g["pixels"])
+    sr = O.satrays_from_table(rays, ts)
+    assert O.chunk_needs_redraw(sr, n, t(g["u_cam"]))
+    loss, out, grads, nren = O.train_step_grads(p, sr, pixels, n, epoch, t(g["u_cam"]), t(g["u_sun"]), t(g["u_cam2"]))
+    assert nren == int(g["n_rendering_samples"])
+    assert torch.allclose(out, t(g["out"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(loss, t(g["loss"]), rtol=1e-5)
+    assert int((out[:, 14] == 0).sum()) == 4            # pts_per_ray keeps the FIRST draw's counts
+    norms = np.array([float(grads[str(k)].double().norm()) for k in g["grad_names"]])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=1e-3, atol=1e-9)
+
+
+def test_vanilla_field_against_reference_outputs(golden):
+    """VanillaNeRFRadianceField (mlp.py:211-250) pinned by the reference class's own outputs and gradients."""
+    g = golden["vanilla"]
+    p = O.init_vanilla_params(seed=int(g["seed"]), bias_scale=float(g["bias_scale"]))
+    np.testing.assert_allclose(fingerprint(p), g["fingerprint"], rtol=1e-12)
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    rgb, sigma = O.vanilla_forward(q, t(g["x"]), t(g["viewdirs"]))
+    assert torch.allclose(rgb, t(g["rgb"]), rtol=1e-6, atol=1e-6) and torch.allclose(sigma, t(g["sigma"]), rtol=1e-6, atol=1e-6)
+    ((rgb * t(g["w_rgb"])).sum() + (sigma * t(g["w_sigma"])).sum()).backward()
+    names = [str(k) for k in g["grad_names"]]
+    assert names == list(p.keys())
+    np.testing.assert_allclose(np.array([float(q[k].grad.double().norm()) for k in names]), g["grad_norms"], rtol=1e-4)
+    for k in names:
+        if "grad__" + k in g.files:
+            assert torch.allclose(q[k].grad, t(g["grad__" + k]), rtol=1e-4, atol=1e-6), k
+
+
+def test_sliced_oracle_equals_whole_chunk():
+    """render_chunk_sliced / train_step_grads_sliced (what the at-size GPU tests use) == the one-pass forms, including the
+    chunk-wide re-draw decision and the eval image index."""
+    from eonerf_code_b200.datasets.synthetic import make_rays
+    B, n, n_img = 96, 24, 4
+    p = O.init_params(n_img, seed=3, bias_scale=0.05)
+    rays, ts, pixels = make_rays(B, n_img, seed=4)
+    rays[70, 6] = 3.0                                    # one empty ray in the LAST slice -> every slice must re-draw
+    g = torch.Generator().manual_seed(5)
+    u = [torch.rand(B, n, generator=g) for _ in range(3)]
+    sr = O.satrays_from_table(rays, ts)
+    for ev in (False, True):
+        with torch.no_grad():
+            a, na = O.render_chunk(p, sr, n, 2, u[0], u[1], u[2], eval=ev)
+            b, nb = O.render_chunk_sliced(p, sr, n, 2, u[0], u[1], u[2], eval=ev, rays_per_slice=32)
+        assert na == nb and torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+    for emu in (False, True):
+        la, _, ga, _ = O.train_step_grads(p, sr, pixels, n, 2, u[0], u[1], u[2], emulate_bf16=emu)
+        lb, _, gb, _ = O.train_step_grads_sliced(p, sr, pixels, n, 2, u[0], u[1], u[2], emulate_bf16=emu, rays_per_slice=32)
+        assert abs(float(la) - float(lb)) < 1e-5
+        for k in ga:
+            # bf16 emulation rounds the back-propagated gradients to bf16 at every layer: a slice weight that is not a power of
+            # two (32/96) moves the rounding points, so the two forms agree to bf16 round-off only (2^-9 per element)
+            d = float((ga[k] - gb[k]).norm() / max(float(ga[k].norm()), 1e-30))
+            assert d <= (1e-2 if emu else 1e-4), (k, d)

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeonerf_b200.so")
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 COMP_COLS = 12
 OUT_COLS = 21
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16_FUSED = 0, 1, 2, 3
@@ -154,6 +154,18 @@ class LossArgs(C.Structure):
     _fields_ = [("out", P), ("gt_rgb", P), ("n_rays", I64), ("mode", I32), ("loss", P), ("g_out", P), ("partials", P)]
 
 
+class UtmPointsArgs(C.Structure):
+    _fields_ = [("rays", P), ("rays_stride", I64), ("depth", P), ("depth_stride", I64), ("n_rays", I64),
+                ("scene_scale", C.c_double * 3), ("scene_offset", C.c_double * 3), ("easts", P), ("norths", P), ("alts", P),
+                ("alt_f32", P)]
+
+
+class DsmArgs(C.Structure):
+    _fields_ = [("easts", P), ("norths", P), ("alts", P), ("depth", P), ("depth_stride", I64), ("n_points", I64),
+                ("xoff", C.c_double), ("yoff", C.c_double), ("resolution", C.c_double), ("xsize", I32), ("ysize", I32),
+                ("radius", I32), ("sigma", C.c_double), ("negative_north_shift", C.c_double), ("acc", P), ("dsm", P)]
+
+
 # every symbol include/eonerf_b200.h declares: name -> (restype, argtypes)
 _ARGS = lambda T: [C.POINTER(T), P]
 SYMBOLS = {
@@ -192,6 +204,8 @@ SYMBOLS = {
     "eonerf_gather_batch": (C.c_int, _ARGS(GatherBatchArgs)),
     "eonerf_loss_partials": (I64, [I64]),
     "eonerf_loss_fwd_bwd": (C.c_int, _ARGS(LossArgs)),
+    "eonerf_utm_points": (C.c_int, _ARGS(UtmPointsArgs)),
+    "eonerf_dsm_rasterize": (C.c_int, _ARGS(DsmArgs)),
 }
 
 _lib = None

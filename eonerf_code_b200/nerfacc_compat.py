@@ -51,30 +51,72 @@ def pack_info(ray_indices, n_rays=None):
 
 
 class OccGridEstimator(torch.nn.Module):
-    """Checkpoint-compatible shim.  The reference constructs, updates and state_dict()s the grid but every
-    `.sampling` call site is commented out (sat_rendering.py:92,94,234,257), so its contents never reach the
-    renderer.  Buffers follow nerfacc v0.5.2 so `occ_grid_state_dict` round-trips (train_eonerf.py:187,
-    eval_eonerf.py:69-71).  `update_every_n_steps` is a no-op: the 2.1 M-point density pass it would run
-    produces a result nobody reads."""
+    """nerfacc v0.5.2 `OccGridEstimator` as far as the reference uses it: constructed (train_eonerf.py:74, eval_eonerf.py:69),
+    updated every 50 steps with `radiance_field.query_opacity` (train_eonerf.py:112-119), `state_dict()`ed into the checkpoint
+    (:187) and loaded back (eval_eonerf.py:70-71).  Every `.sampling` call site of the reference is commented out
+    (sat_rendering.py:92,94,234,257), so the grid never reaches the renderer; it is kept REAL here (same buffers, same
+    update rule, same random draws from the global generator of the grid's device) so that checkpoints carry the grid the
+    reference would have written and the device RNG stream stays aligned with the reference's.
+    The density pass of the update runs on the fused sm_100a density kernel through `occ_eval_fn`.
+
+    Restated from the published algorithm of nerfacc v0.5.2 (estimators/occ_grid.py); upstream is not vendored in the
+    reference: parity unpinned (oracle/nerfacc_v052.py holds the checker's restatement)."""
+
+    DIM = 3
 
     def __init__(self, roi_aabb, resolution=128, levels=1, **kwargs):
         super().__init__()
         if isinstance(resolution, int):
-            resolution = [resolution] * 3
+            resolution = [resolution] * self.DIM
         res = torch.tensor(resolution, dtype=torch.int32)
         aabb = torch.as_tensor(roi_aabb, dtype=torch.float32).flatten()
-        aabbs = torch.stack([torch.cat([(aabb[:3] + aabb[3:]) / 2 - (aabb[3:] - aabb[:3]) / 2 * 2 ** i,
-                                        (aabb[:3] + aabb[3:]) / 2 + (aabb[3:] - aabb[:3]) / 2 * 2 ** i]) for i in range(levels)])
+        center, half = (aabb[:3] + aabb[3:]) / 2, (aabb[3:] - aabb[:3]) / 2
+        aabbs = torch.stack([torch.cat([center - half * 2 ** i, center + half * 2 ** i]) for i in range(levels)])
         n_cells = int(res.prod())
         self.levels, self.cells_per_lvl = levels, n_cells
         self.register_buffer("resolution", res)
         self.register_buffer("aabbs", aabbs)
         self.register_buffer("occs", torch.zeros(levels * n_cells))
         self.register_buffer("binaries", torch.zeros([levels] + list(resolution), dtype=torch.bool))
+        # cell coordinates in flattening order (x slowest, z fastest), as upstream's meshgrid(indexing="ij")
+        coords = torch.stack(torch.meshgrid([torch.arange(r) for r in resolution], indexing="ij"), dim=-1).reshape(n_cells, self.DIM)
+        self.register_buffer("grid_coords", coords, persistent=False)
+        self.register_buffer("grid_indices", torch.arange(n_cells), persistent=False)
 
     @property
     def device(self):
         return self.aabbs.device
 
-    def update_every_n_steps(self, step, occ_eval_fn=None, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16):
-        return None
+    @torch.no_grad()
+    def _sample_uniform_and_occupied_cells(self, n):
+        out = []
+        for lvl in range(self.levels):
+            uniform = torch.randint(self.cells_per_lvl, (n,), device=self.device)
+            occupied = torch.nonzero(self.binaries[lvl].flatten())[:, 0]
+            if n < len(occupied):
+                occupied = occupied[torch.randint(len(occupied), (n,), device=self.device)]
+            out.append(torch.cat([uniform, occupied], dim=0))
+        return out
+
+    @torch.no_grad()
+    def _update(self, step, occ_eval_fn, occ_thre=0.01, ema_decay=0.95, warmup_steps=256):
+        if step < warmup_steps:
+            lvl_indices = [self.grid_indices] * self.levels
+        else:
+            lvl_indices = self._sample_uniform_and_occupied_cells(self.cells_per_lvl // 4)
+        for lvl, indices in enumerate(lvl_indices):
+            coords = self.grid_coords[indices]
+            x = (coords + torch.rand_like(coords, dtype=torch.float32)) / self.resolution
+            x = self.aabbs[lvl, :3] + x * (self.aabbs[lvl, 3:] - self.aabbs[lvl, :3])
+            occ = occ_eval_fn(x).squeeze(-1)
+            cell_ids = lvl * self.cells_per_lvl + indices
+            self.occs[cell_ids] = torch.maximum(self.occs[cell_ids] * ema_decay, occ)
+        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
+        self.binaries = (self.occs > thre).view(self.binaries.shape)
+
+    @torch.no_grad()
+    def update_every_n_steps(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16):
+        if not self.training:
+            raise RuntimeError("Please call estimator.train() before calling update_every_n_steps().")
+        if step % n == 0 and self.training:
+            self._update(step=step, occ_eval_fn=occ_eval_fn, occ_thre=occ_thre, ema_decay=ema_decay, warmup_steps=warmup_steps)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 12
+#define EONERF_ABI_VERSION 13
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -420,6 +420,43 @@ typedef struct {
 } EonerfLossArgs;
 int64_t eonerf_loss_partials(int64_t n_rays);
 int eonerf_loss_fwd_bwd(const EonerfLossArgs* a, eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation epilogue.
+ * eonerf_utm_points replaces SatelliteDataset.get_utmalt_from_nerf_prediction (datasets/satellite.py:502-531, the
+ * utm_sampling branch): x = (o + d * depth) * scene_scale + scene_offset with rays and depth promoted to fp64 first.
+ * Outputs are optional planes [N] (fp64 easts / norths / alts, fp32 altitude for the render arm's altitude column).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* rays; int64_t rays_stride;        /* [N,>=6] rows [o(3) d(3) ...], stride in floats */
+  const float* depth; int64_t depth_stride;      /* [N] rendered depth */
+  int64_t n_rays;
+  double scene_scale[3]; double scene_offset[3];
+  double* easts; double* norths; double* alts;   /* [N] each, or NULL */
+  float* alt_f32;                                /* [N] or NULL */
+} EonerfUtmPointsArgs;
+int eonerf_utm_points(const EonerfUtmPointsArgs* a, eonerf_stream_t stream);
+
+/* eonerf_dsm_rasterize replaces the plyflatten call of SatelliteDataset.get_dsm_from_nerf_prediction
+ * (datasets/satellite.py:548-587): plyflatten(cloud, xoff, yoff, resolution, xsize, ysize, radius, sigma) -> dsm[ysize,xsize]
+ * fp32, NaN where no point fell.  Cell of a point: i = floor((x - xoff)/res), j = floor((yoff - y)/res); cells within
+ * `radius` (k1^2 + k2^2 <= radius^2) receive its height with weight 1 (sigma = inf) or the Gaussian of the distance to the
+ * cell centre.  Points with depth < 0 are dropped (:561) and norths < 0 are shifted by negative_north_shift (:559, 10e6).
+ * `acc` = caller-provided scratch of 2 * xsize * ysize doubles (zeroed here).  plyflatten is an un-vendored dependency of
+ * the reference: semantics restated from its published source, parity unpinned.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const double* easts; const double* norths; const double* alts;   /* [N] */
+  const float* depth; int64_t depth_stride;                        /* [N] or NULL */
+  int64_t n_points;
+  double xoff; double yoff; double resolution;
+  int32_t xsize; int32_t ysize; int32_t radius;
+  double sigma;                                                    /* +inf: unweighted mean */
+  double negative_north_shift;
+  double* acc;                                                     /* scratch [ysize*xsize*2] */
+  float* dsm;                                                      /* [ysize,xsize] */
+} EonerfDsmArgs;
+int eonerf_dsm_rasterize(const EonerfDsmArgs* a, eonerf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -99,20 +99,57 @@ def accumulate_along_rays(weights, values=None, ray_indices=None, n_rays=None):
 
 
 class OccGridEstimator(torch.nn.Module):
-    """The reference only constructs / updates / state_dict()s the grid (train_eonerf.py:74,112-119,187);
-    every `.sampling` call site is commented out (sat_rendering.py:92,94,234,257)."""
+    """estimators/occ_grid.py of nerfacc v0.5.2, the part the reference exercises (train_eonerf.py:74,112-119,187;
+    eval_eonerf.py:66-71): buffers `resolution`, `aabbs`, `occs`, `binaries` (persistent) + `grid_coords`, `grid_indices`
+    (non-persistent); `update_every_n_steps` = every n-th step, EMA-max update of the cell occupancies from
+    `occ_eval_fn` at one jittered point per visited cell (all cells during warm-up, then cells_per_lvl/4 uniform + up to
+    as many currently-occupied ones), binary grid = occs > min(mean(occs), occ_thre).  Every `.sampling` call site of the
+    reference is commented out (sat_rendering.py:92,94,234,257).  Restated from memory of the published source: unpinned."""
 
     def __init__(self, roi_aabb=None, resolution=128, levels=1, **kw):
         super().__init__()
-        self.register_buffer("aabbs", torch.tensor([roi_aabb if roi_aabb is not None else [-1.] * 3 + [1.] * 3],
-                                                   dtype=torch.float32))
+        roi_aabb = [-1.] * 3 + [1.] * 3 if roi_aabb is None else roi_aabb
+        resolution = [resolution] * 3 if isinstance(resolution, int) else list(resolution)
+        aabb = torch.as_tensor(roi_aabb, dtype=torch.float32).flatten()
+        c, h = (aabb[:3] + aabb[3:]) / 2, (aabb[3:] - aabb[:3]) / 2
+        self.levels = levels
+        self.cells_per_lvl = int(torch.tensor(resolution).prod())
+        self.register_buffer("resolution", torch.tensor(resolution, dtype=torch.int32))
+        self.register_buffer("aabbs", torch.stack([torch.cat([c - h * 2 ** i, c + h * 2 ** i]) for i in range(levels)]))
+        self.register_buffer("occs", torch.zeros(levels * self.cells_per_lvl))
+        self.register_buffer("binaries", torch.zeros([levels] + resolution, dtype=torch.bool))
+        gc = torch.stack(torch.meshgrid([torch.arange(r) for r in resolution], indexing="ij"), -1).reshape(self.cells_per_lvl, 3)
+        self.register_buffer("grid_coords", gc, persistent=False)
+        self.register_buffer("grid_indices", torch.arange(self.cells_per_lvl), persistent=False)
 
     @property
     def device(self):
         return self.aabbs.device
 
-    def update_every_n_steps(self, *a, **kw):
-        return None
+    @torch.no_grad()
+    def update_every_n_steps(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16):
+        if not self.training:
+            raise RuntimeError("Please call estimator.train() before calling update_every_n_steps().")
+        if step % n != 0:
+            return
+        for lvl in range(self.levels):
+            if step < warmup_steps:
+                idx = self.grid_indices
+            else:
+                k = self.cells_per_lvl // 4
+                uni = torch.randint(self.cells_per_lvl, (k,), device=self.device)
+                occd = torch.nonzero(self.binaries[lvl].flatten())[:, 0]
+                if k < len(occd):
+                    occd = occd[torch.randint(len(occd), (k,), device=self.device)]
+                idx = torch.cat([uni, occd], 0)
+            gc = self.grid_coords[idx]
+            x = (gc + torch.rand_like(gc, dtype=torch.float32)) / self.resolution
+            x = self.aabbs[lvl, :3] + x * (self.aabbs[lvl, 3:] - self.aabbs[lvl, :3])
+            occ = occ_eval_fn(x).squeeze(-1)
+            cid = lvl * self.cells_per_lvl + idx
+            self.occs[cid] = torch.maximum(self.occs[cid] * ema_decay, occ)
+        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
+        self.binaries = (self.occs > thre).view(self.binaries.shape)
 
 
 def install_as_nerfacc():

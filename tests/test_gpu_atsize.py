@@ -8,8 +8,8 @@ pinned against the unmodified reference by tests/golden/) on the SAME rays, weig
   (the sun rays start at the rendered surface point, sat_rendering.py:90, so with a bf16 MLP the cube filter of a sun
   sample next to a face can flip: against the fp32 oracle's own depth the counts must still agree on >= 99 % of the rays
   and never differ by more than 2);
-* floating-point outputs vs the fp32 oracle: >= 90 % of the elements of every output within 1e-3 absolute (north_star's
-  bf16-MLP tolerance), all within MAX_ABS below;
+* floating-point outputs vs the fp32 oracle: >= 99 % of the elements of every output within 1e-3 absolute (north_star's
+  bf16-MLP tolerance; it asks for >= 90 %), all within MAX_ABS below;
 * gradients of one whole step vs the oracle's bf16-emulating autograd (same rounding points, fp32 accumulation):
   relative L2 distance per parameter tensor.
 
@@ -29,8 +29,11 @@ pytestmark = pytest.mark.gpu
 
 FLOAT_KEYS = ("rgb", "depth", "albedo_rgb", "ambient_rgb", "geo_shadows", "transient_s", "beta", "shadowless_rgb")
 # stated maxima of |product - fp32 oracle| per output (bf16 MLP, composited over <= 127 samples; depth is in ray units 0..2)
-MAX_ABS = {"rgb": 1.5e-2, "depth": 1.5e-2, "albedo_rgb": 1.5e-2, "ambient_rgb": 1e-3, "geo_shadows": 6e-2, "transient_s": 1.5e-2,
-           "beta": 1.5e-2, "shadowless_rgb": 1.5e-2}
+# (measured, profiles/r2a_parity_report.jsonl: rgb 2.3e-3, depth 3.4e-4, albedo 4.5e-4, geo_shadows 9.3e-3, beta 5.3e-4; the
+# bounds leave a factor ~3).  geo_shadows = exp(-sum sigma*delta) over <= 127 sun samples amplifies the bf16 density error.
+MAX_ABS = {"rgb": 6e-3, "depth": 1e-3, "albedo_rgb": 1.5e-3, "ambient_rgb": 1e-5, "geo_shadows": 3e-2, "transient_s": 1e-3,
+           "beta": 2e-3, "shadowless_rgb": 1.5e-3}
+MIN_WITHIN_1E3 = 0.99      # north_star asks for >= 0.90; measured >= 0.9966 on every output
 
 
 def _report(name, payload):
@@ -78,7 +81,7 @@ def _compare_outputs(name, res, out_o, rows=None, rays=None, us=None, n=None):
             d = (mine - ref).abs()
             stats[k] = {"within_1e-3": float((d <= 1e-3).float().mean()), "max_abs": float(d.max()), "mean_abs": float(d.mean())}
     _report(name, {"outputs": stats})
-    bad = {k: v for k, v in stats.items() if k in MAX_ABS and (v["within_1e-3"] < 0.90 or v["max_abs"] > MAX_ABS[k])}
+    bad = {k: v for k, v in stats.items() if k in MAX_ABS and (v["within_1e-3"] < MIN_WITHIN_1E3 or v["max_abs"] > MAX_ABS[k])}
     assert not bad, bad
     return stats
 
@@ -194,7 +197,8 @@ def _l2(a, b):
 # relative-L2 bars of the whole-step gradient vs the oracle's bf16-emulating autograd.  The per-image 9-vector rows and the
 # narrow heads see every ray of the batch (well averaged); the sun-pass position gradient feeds the trunk's first layers
 # through 2^k-weighted pos-enc terms, the worst conditioned part (see test_full_gradients_vs_oracle_fp32).
-GRAD_L2 = 3e-2
+GRAD_L2 = 3e-2          # mid-size eager test (measured 1.0e-2)
+GRAD_L2_CFG3 = 1e-2     # full-size captured step (measured 2.7e-3: more samples per parameter average the rounding)
 
 
 def test_cfg3_step_gradients_graph_vs_oracle_bf16(cuda):
@@ -223,7 +227,7 @@ def test_cfg3_step_gradients_graph_vs_oracle_bf16(cuda):
     zero = [k for k, v in m.named_parameters() if float(grads_o[k].abs().max()) == 0 and float(v.grad.abs().max()) != 0]
     _report("cfg3_step_gradients", {"loss": float(loss), "loss_oracle": float(loss_o), "rel_l2": dist})
     assert not zero, zero
-    bad = {k: e for k, e in dist.items() if e > GRAD_L2}
+    bad = {k: e for k, e in dist.items() if e > GRAD_L2_CFG3}
     assert not bad, bad
 
 

@@ -70,7 +70,7 @@ struct FusedFwdParams {
 };
 
 template <bool kTrain, int kCG, int kMC>
-__global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __grid_constant__ FusedFwdParams p, const __grid_constant__ CUtensorMap wmap) {
+__global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_constant__ FusedFwdParams p, const __grid_constant__ CUtensorMap wmap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* cst = (float*)(smem + kFOffConst);              // shared-memory copy of the constants (kFwdConstG: unused)
@@ -80,9 +80,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
   FusedBars B;
   uint32_t* tmem_base_s;
   fused_setup<kCG, kMC, kFwdRing>(smem, B, tmem_base_s, rank, kFOffBar);
+  // encoder handshake (see fused_mma_issuer): enc_full[slot] counts the encoder warp of every CTA whose rows the MMA covers
+  uint64_t* const enc_full = (uint64_t*)(smem + kFOffBar + 88);
+  uint64_t* const enc_free = enc_full + 2;
+  static_assert((2 * kFwdRing + 4) * 8 + 4 <= 88 && 88 + 4 * 8 <= 128, "barrier region");
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&enc_full[s], (kCG == 2 && rank == 0) ? 2 : 1); mbar_init(&enc_free[s], 1); }
+    fence_barrier_init();
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (!kFwdConstG)
-    for (int i = threadIdx.x; i < kCFloats; i += kFusedThreads) cst[i] = __ldg(p.consts + i);
+    for (int i = threadIdx.x; i < kCFloats; i += kFwdThreads) cst[i] = __ldg(p.consts + i);
   tc_fence_before();
   if (kCl > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -96,32 +104,85 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
   if (warp == 0) {
     if (lane == 0) fused_producer<kCG, kMC, kFwdRing>(p.prog, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
   } else if (warp == 1) {
-    if (kCG == 1 || rank == 0) fused_mma_issuer<kCG, kMC, true, kFwdRing, 5>(p.prog, smem, B, tmem_base, it0, n_items, it_stride);      // whole warp, converged
-  } else if (kDutyWarp && warp == kDutyWarpId) {
-    // ===== duty warp: mirrors the epilogue warps' named barriers; after each one, lane 0 hands the slot to the MMA issuer and
-    // starts the stash store of what the epilogue wrote; before the next one it waits until that store has read shared memory =====
-    for (int64_t it = it0; it < n_items; it += it_stride) {
-      if (kTrain && kDutyStores && lane == 0) tma_store_wait_read<0>();
-      named_bar_sync(1, kBarThreads);                       // start of the item: the slots may be overwritten
-      named_bar_sync(1, kBarThreads);                       // positional encoding + layer-0 bias written
-      if (lane == 0) {
-        signal_act_ready<kCG>(B, 0, rank);
-        signal_act_ready<kCG>(B, 1, rank);
-        if (kTrain && kDutyStores) {
-          for (int slot = 0; slot < 2; ++slot) {
-            const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-            if (tile < n_tiles) EO_BULK_STORE(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kFOffSlot + slot * kFSlotBytes + 4 * kBlkBytes, kBlkBytes);
+    if (kCG == 1 || rank == 0)      // whole warp, converged
+      fused_mma_issuer<kCG, kMC, true, kFwdRing, 5>(p.prog, smem, B, tmem_base, it0, n_items, it_stride, enc_full, enc_free);
+  } else if (warp == kEncWarpId) {
+    // ===== encoder warp: sample positions -> positional encoding of both tiles of every item, one item ahead of the layers.
+    // Lane l owns rows l, l+32, l+64, l+96 of each tile.  Also writes the per-sample side outputs (z_mid; training: xf, cls)
+    // and, in training, stores the ENC block to the stash. =====
+    uint32_t fph = 0;                                // bit `slot` = phase of enc_free[slot]
+    for (int64_t it = it0; it < n_items; it += it_stride)
+      for (int slot = 0; slot < 2; ++slot) {
+        const int64_t tile = 2 * kCl * it + 2 * rank + slot;
+        if (kTrain && lane == 0) tma_store_wait_read<0>();     // the previous ENC store has read the block
+        mbar_wait(&enc_free[slot], ((fph >> slot) & 1u) ^ 1u);  // ... and so have the MMAs of the previous item (passes at once the first time)
+        fph ^= 1u << slot;
+        __syncwarp();
+        const uint32_t enc = smem_u32(smem + kFOffSlot + slot * kFSlotBytes + 4 * kBlkBytes);
+#pragma unroll 1
+        for (int rr = 0; rr < 4; ++rr) {
+          const int r = rr * 32 + lane;
+          const int64_t pt = tile * kTileM + r;
+          float x[3] = {0.f, 0.f, 0.f};
+          if (pt < M) {
+            int64_t ray = -1;
+            if (p.x) {
+              x[0] = __ldg(p.x + 3 * pt); x[1] = __ldg(p.x + 3 * pt + 1); x[2] = __ldg(p.x + 3 * pt + 2);
+              if (p.ray_indices) ray = __ldg(p.ray_indices + pt);
+            } else {
+              ray = __ldg(p.ray_indices + pt);
+              const float ts = __ldg(p.t_starts + pt), te = __ldg(p.t_ends + pt);
+              const float zm = __fdiv_rn(__fadd_rn(ts, te), 2.0f);                              // eonerf.py:206
+              const float* o = p.origins + ray * p.o_stride;
+              const float* dd = p.viewdirs + ray * p.d_stride;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) x[k] = __fadd_rn(__ldg(o + k), __fmul_rn(__ldg(dd + k), zm));   // eonerf.py:207
+              if (p.z_mid) p.z_mid[pt] = zm;
+            }
+            if (kTrain) {
+              p.xf[3 * pt] = x[0]; p.xf[3 * pt + 1] = x[1]; p.xf[3 * pt + 2] = x[2];
+              if (p.cls && p.img_idx)
+                p.cls[pt] = (int32_t)(p.ray_indices ? __ldg(p.img_idx + ray * p.img_stride) : __ldg(p.img_idx + pt * p.img_stride));
+            }
           }
-          tma_store_commit();
+          uint32_t w[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) w[u] = pack_bf16(posenc_col<0>(x, 2 * u), posenc_col<0>(x, 2 * u + 1));
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) sts_u4(enc + blk_off(r, jj), w[4 * jj], w[4 * jj + 1], w[4 * jj + 2], w[4 * jj + 3]);
+#pragma unroll
+          for (int u = 0; u < 16; ++u) w[u] = pack_bf16(posenc_col<32>(x, 2 * u), posenc_col<32>(x, 2 * u + 1));
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) sts_u4(enc + blk_off(r, 4 + jj), w[4 * jj], w[4 * jj + 1], w[4 * jj + 2], w[4 * jj + 3]);
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCG == 2 && rank != 0) mbar_arrive_remote(&enc_full[slot], 0); else mbar_arrive(&enc_full[slot]);
+          if (kTrain) {
+            if (tile < n_tiles) EO_BULK_STORE(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kFOffSlot + slot * kFSlotBytes + 4 * kBlkBytes, kBlkBytes);
+            tma_store_commit();
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
+    if (kTrain && lane == 0) tma_store_wait_all();
+  } else if (kDutyWarp && warp == kDutyWarpId) {
+    // ===== duty warp: mirrors the epilogue warps' named barriers; after each one, lane 0 hands the slot to the MMA issuer =====
+    named_bar_sync(1, kBarThreads);                       // layer-0 bias of the first item written to both accumulators
+    if (lane == 0 && it0 < n_items) {
+      signal_act_ready<kCG>(B, 0, rank);
+      signal_act_ready<kCG>(B, 1, rank);
+    }
+    __syncwarp();
+    for (int64_t it = it0; it < n_items; it += it_stride) {
+      const bool next_item = it + it_stride < n_items;
       for (int s = 0; s < p.n_stages; ++s)
         for (int slot = 0; slot < 2; ++slot) {
           if (kTrain && kDutyStores && lane == 0) tma_store_wait_read<0>();
           named_bar_sync(1, kBarThreads);
           if (lane == 0) {
-            if (s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
+            if (s + 1 < p.n_stages || next_item) signal_act_ready<kCG>(B, slot, rank);
             const int64_t tile = 2 * kCl * it + 2 * rank + slot;
             if (kTrain && kDutyStores && tile < n_tiles && !(p.training & 2)) {
               const FStage d = c_fstage[s];
@@ -147,87 +208,45 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
     const uint32_t s_part = smem_u32(part);
     uint32_t cph = 0;                               // bit `slot` = phase of acc_full[slot]
     uint64_t* const acc_full = B.acc_full;
-    for (int64_t it = it0; it < n_items; it += it_stride) {
-      uint32_t cls_pack = 0;                        // image index of this row in slot 0 (low 16 bits) / slot 1
-      // ---- positional encoding of both tiles ----
-      if (store_id >= 0) tma_store_wait_read<0>();
-      named_bar_sync(1, kBarThreads);
-      for (int slot = 0; slot < 2; ++slot) {
-        const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-        const int64_t pt = tile * kTileM + r;
-        const bool valid = pt < M;
-        float x[3] = {0.f, 0.f, 0.f};
-        int64_t ray = -1;
-        if (valid) {
-          if (p.x) {
-            x[0] = __ldg(p.x + 3 * pt); x[1] = __ldg(p.x + 3 * pt + 1); x[2] = __ldg(p.x + 3 * pt + 2);
-            if (p.ray_indices) ray = __ldg(p.ray_indices + pt);
-          } else {
-            ray = __ldg(p.ray_indices + pt);
-            const float ts = __ldg(p.t_starts + pt), te = __ldg(p.t_ends + pt);
-            const float zm = __fdiv_rn(__fadd_rn(ts, te), 2.0f);                              // eonerf.py:206
-            const float* o = p.origins + ray * p.o_stride;
-            const float* dd = p.viewdirs + ray * p.d_stride;
+    // The accumulators start from the layer's bias: every epilogue writes the NEXT layer's bias over the columns it has just
+    // drained (tcgen05.st), so no bias add sits between the TMEM load and the bf16 pack.  Layer 0's goes in here for the
+    // first item (later items: the last stage of the previous item writes it).
+    {
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t b[32];
+        const uint32_t sb = s_cst + (uint32_t)(c_fstage[0].bias_off + half * 128 + c * 32) * 4u;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) x[k] = __fadd_rn(__ldg(o + k), __fmul_rn(__ldg(dd + k), zm));   // eonerf.py:207
-            if (half == 0 && p.z_mid) p.z_mid[pt] = zm;
-          }
-          if (p.img_idx) {
-            const int64_t img = p.ray_indices ? __ldg(p.img_idx + ray * p.img_stride) : __ldg(p.img_idx + pt * p.img_stride);
+        for (int j = 0; j < 8; ++j) {
+          float b0, b1, b2, b3;
+          cf4<kFwdConstG>(p.consts, sb + j * 16, b0, b1, b2, b3);
+          b[4 * j] = __float_as_uint(b0); b[4 * j + 1] = __float_as_uint(b1); b[4 * j + 2] = __float_as_uint(b2); b[4 * j + 3] = __float_as_uint(b3);
+        }
+        tmem_st32(t0 + c * 32, b);
+        tmem_st32(t0 + 256 + c * 32, b);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    named_bar_sync(1, kBarThreads);
+    if (!kDutyWarp && e == kSignalThread && it0 < n_items) {
+      signal_act_ready<kCG>(B, 0, rank);
+      signal_act_ready<kCG>(B, 1, rank);
+    }
+    for (int64_t it = it0; it < n_items; it += it_stride) {
+      const bool next_item = it + it_stride < n_items;
+      // image index of this row in slot 0 (low 16 bits) / slot 1: selects the per-image bias row of the HD0 stage (fetched now,
+      // used eight stages later)
+      uint32_t cls_pack = 0;
+      if (p.img_idx)
+        for (int slot = 0; slot < 2; ++slot) {
+          const int64_t pt = (2 * kCl * it + 2 * rank + slot) * kTileM + r;
+          if (pt < M) {
+            const int64_t img = p.ray_indices ? __ldg(p.img_idx + __ldg(p.ray_indices + pt) * p.img_stride) : __ldg(p.img_idx + pt * p.img_stride);
             cls_pack |= ((uint32_t)img & 0xFFFFu) << (16 * slot);
           }
-          if (kTrain && half == 0) {
-            p.xf[3 * pt] = x[0]; p.xf[3 * pt + 1] = x[1]; p.xf[3 * pt + 2] = x[2];
-            if (p.cls) p.cls[pt] = (int32_t)((cls_pack >> (16 * slot)) & 0xFFFFu);
-          }
         }
-        const uint32_t enc = smem_u32(smem + kFOffSlot + slot * kFSlotBytes + 4 * kBlkBytes);
-        uint32_t w[16];
-        if (half == 0) {
-#pragma unroll
-          for (int u = 0; u < 16; ++u) w[u] = pack_bf16(posenc_col<0>(x, 2 * u), posenc_col<0>(x, 2 * u + 1));
-        } else {
-#pragma unroll
-          for (int u = 0; u < 16; ++u) w[u] = pack_bf16(posenc_col<32>(x, 2 * u), posenc_col<32>(x, 2 * u + 1));
-        }
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) sts_u4(enc + blk_off(r, half * 4 + jj), w[4 * jj], w[4 * jj + 1], w[4 * jj + 2], w[4 * jj + 3]);
-      }
-      // The accumulators start from the layer's bias: every epilogue writes the NEXT layer's bias over the columns it has
-      // just drained (tcgen05.st), so no bias add sits between the TMEM load and the bf16 pack.  Layer 0's goes in here.
-      {
-        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t b[32];
-          const uint32_t sb = s_cst + (uint32_t)(c_fstage[0].bias_off + half * 128 + c * 32) * 4u;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float b0, b1, b2, b3;
-            cf4<kFwdConstG>(p.consts, sb + j * 16, b0, b1, b2, b3);
-            b[4 * j] = __float_as_uint(b0); b[4 * j + 1] = __float_as_uint(b1); b[4 * j + 2] = __float_as_uint(b2); b[4 * j + 3] = __float_as_uint(b3);
-          }
-          tmem_st32(t0 + c * 32, b);
-          tmem_st32(t0 + 256 + c * 32, b);
-        }
-        tmem_st_wait();
-      }
-      tc_fence_before();
-      fence_proxy_async();
-      named_bar_sync(1, kBarThreads);
-      // after-barrier duties are split over two threads of different warps (neither in a warp that writes head outputs), so
-      // no single warp arrives late at the next barrier: one signals the MMA issuer, the other owns the stash stores
-      if (!kDutyWarp && e == kSignalThread) {
-        signal_act_ready<kCG>(B, 0, rank);
-        signal_act_ready<kCG>(B, 1, rank);
-      }
-      if (kTrain && store_id >= 0) {
-        for (int slot = store_id; slot < 2; slot += kStoreThreads) {
-          const int64_t tile = 2 * kCl * it + 2 * rank + slot;
-          if (tile < n_tiles) EO_BULK_STORE(p.arr[kArrEnc] + (size_t)tile * kBlkBytes, smem + kFOffSlot + slot * kFSlotBytes + 4 * kBlkBytes, kBlkBytes);
-        }
-        tma_store_commit();
-      }
 
       // ---- the layers ----
       for (int s = 0; s < p.n_stages; ++s) {
@@ -235,8 +254,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
         const int cpt = d.halves == 2 ? 128 : 64;          // columns per thread
         const int col0 = half * cpt;
         const bool want_mask = kTrain && d.mask >= 0 && !(p.training & 4);
-        const bool has_next = s + 1 < p.n_stages;
-        const FStage dn = c_fstage[has_next ? s + 1 : s];
+        const bool last_stage = s + 1 == p.n_stages;
+        const bool has_next = !last_stage || next_item;     // another MMA stage follows on this slot (maybe the next item's stage 0)
+        const FStage dn = c_fstage[last_stage ? 0 : s + 1];
         const int next_cols = dn.halves * 128;              // accumulator columns the next layer uses
         for (int slot = 0; slot < 2; ++slot) {
           const int64_t tile = 2 * kCl * it + 2 * rank + slot;
@@ -255,8 +275,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           // one 32-column chunk: accumulator + bias -> (ReLU) -> bf16 -> next A operand in shared memory; returns the ReLU keep bits
           // (column 2j -> bit 15-j, column 2j+1 -> bit 31-j: the complement of the pre-activation sign bits, funnel-shifted in)
           // next layer's bias for the 32 accumulator columns of chunk c (per-image rows of the HD0 transient half included)
-          auto next_bias = [&](const int c) {
-            const int colg = col0 + c * 32;
+          auto next_bias_cols = [&](const int colg) {
             if (!has_next || colg >= next_cols) return;
             uint32_t b[32];
             const uint32_t sb = s_cst + (uint32_t)(dn.bias_off + colg) * 4u;
@@ -276,6 +295,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
             }
             tmem_st32(tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + colg, b);
           };
+          auto next_bias = [&](const int c) { next_bias_cols(col0 + c * 32); };
           auto chunk = [&](uint32_t (&v)[32], const int c) -> uint32_t {
             float x[32];
 #pragma unroll
@@ -365,6 +385,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
             next_bias(3);
             m3 = chunk(vb, 3);
           }
+          if (last_stage && cpt == 64) {
+            // a 128-wide last stage drains (and refills) accumulator columns 0..127 only; columns 128..255 have been idle since
+            // the HD0 stage: give them the next item's layer-0 bias too
+            next_bias_cols(128 + col0);
+            next_bias_cols(128 + col0 + 32);
+          }
           if (has_next) tmem_st_wait();
           EO_TN(tc);
           if (want_mask && valid) {
@@ -382,7 +408,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_fwd_kernel(const __gri
           EO_TN(te);
           { EO_T0(); named_bar_sync(1, kBarThreads); if (e == 32) EO_T1(5); }
           EO_TN(tf);
-          if (!kDutyWarp && e == kSignalThread && s + 1 < p.n_stages) signal_act_ready<kCG>(B, slot, rank);
+          if (!kDutyWarp && e == kSignalThread && has_next) signal_act_ready<kCG>(B, slot, rank);
           if (kTrain && store_id >= 0 && tile < n_tiles && !(p.training & 2)) {
             const int nb = d.halves * 2;                     // 16 KB blocks store_id, store_id + kStoreThreads, ... of the layer's output
             for (int bb = store_id; bb < nb; bb += kStoreThreads)
@@ -611,7 +637,8 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
       configured = true;                                                                                                        \
     }                                                                                                                           \
     profile_begin(3, flops, 0.0, s);                                                                                            \
-    rc = train ? launch_fused(fused_fwd_kernel<true, CG, MC>, csz, n_ctas, p, wmap, s, kSmemFwd) : launch_fused(fused_fwd_kernel<false, CG, MC>, csz, n_ctas, p, wmap, s, kSmemFwd); \
+    rc = train ? launch_fused(fused_fwd_kernel<true, CG, MC>, csz, n_ctas, p, wmap, s, kSmemFwd, kFwdThreads)                \
+               : launch_fused(fused_fwd_kernel<false, CG, MC>, csz, n_ctas, p, wmap, s, kSmemFwd, kFwdThreads);              \
   } while (0)
   if (mode == 1) EO_LAUNCH_FWD(1, 1);
   else if (mode == 2) EO_LAUNCH_FWD(2, 1);

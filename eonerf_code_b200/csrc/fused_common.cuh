@@ -57,6 +57,11 @@ constexpr int kDutyWarpId = 10;
 #endif
 constexpr bool kDutyStores = kDutyWarp && EONERF_DUTY_STORES != 0;   // the duty warp also owns the bulk stores (measured slower)
 constexpr int kFusedThreads = kDutyWarp ? 352 : 320;
+// Forward kernel only: a 12th warp computes the positional encoding of the NEXT work item while the current one is in its
+// layers (the ENC block of a slot is free once layer 5's MMAs have read it), so consecutive items form one uninterrupted
+// pipeline: no per-item prologue during which the tensor core has nothing to do.  12 warps x 168 registers = 64 512 <= 65 536.
+constexpr int kEncWarpId = kDutyWarp ? 11 : 10;
+constexpr int kFwdThreads = kFusedThreads + 32;
 constexpr int kEpiThreads = 256;
 constexpr int kBarThreads = kDutyWarp ? 288 : 256;      // participants of the end-of-layer named barrier
 constexpr int kSignalThread = 128;    // epilogue thread (warp 6) that signals act_ready after the end-of-layer barrier
@@ -274,11 +279,16 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
 
 // the whole MMA warp (kCG = 2: of the leader CTA), converged: issue the MMAs of every stage for both slots
 // kAccInit: the epilogue warps have pre-loaded every accumulator (with the layer's bias): the first MMA of a stage accumulates too
+// enc_full / enc_free (forward kernel): per-slot handshake with the encoder warp.  Stage 0 of an item waits until the item's
+// positional encoding is in the slot's ENC block; the MMAs of stage kEncLastStage (layer 5, the skip connection) are the last
+// readers of it, and their completion (tcgen05.commit) hands the block back for the next item's encoding.
+constexpr int kEncLastStage = 5;
 template <int kCG, int kMC = 1, bool kAccInit = false, int kRing = kRingStages, int kSlotBlk = (kRing > 3 ? 4 : 5)>
 __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t* smem, const FusedBars& B, uint32_t tmem_base, int64_t it0,
-                                                 int64_t n_items, int64_t it_stride) {
+                                                 int64_t n_items, int64_t it_stride, uint64_t* enc_full = nullptr, uint64_t* enc_free = nullptr) {
   int rs = 0; uint32_t rph = 0;
   uint32_t aph = 0;                                  // bit `slot` = phase of act_ready[slot]
+  uint32_t eph = 0;                                  // bit `slot` = phase of enc_full[slot]
   const uint32_t ring0 = smem_u32(smem + kOffRing);
   const bool elected = elect_one_sync();
 #ifdef EONERF_TIMING
@@ -292,6 +302,10 @@ __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t
       for (int slot = 0; slot < 2; ++slot) {
         { EO_T0(); mbar_wait(&B.act_ready[slot], (aph >> slot) & 1u); EO_T1(0); }
         aph ^= 1u << slot;
+        if (enc_full && s == 0) {
+          EO_T0(); mbar_wait(&enc_full[slot], (eph >> slot) & 1u); EO_T1(0);
+          eph ^= 1u << slot;
+        }
         tc_fence_after();
         const uint32_t slot0 = smem_u32(smem + off_slot(kRing) + slot * (kSlotBlk * kBlkBytes));
         for (int h = 0; h < n_h; ++h) {
@@ -316,6 +330,9 @@ __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t
         }
         if (elected) {
           if (kCG == 2) umma_commit_2cta(&B.acc_full[slot]); else umma_commit(&B.acc_full[slot]);
+          if (enc_free && s == kEncLastStage) {
+            if (kCG == 2) umma_commit_2cta(&enc_free[slot]); else umma_commit(&enc_free[slot]);
+          }
         }
         __syncwarp();
       }
@@ -333,10 +350,11 @@ __device__ __forceinline__ void signal_act_ready(const FusedBars& B, int slot, u
 }
 
 template <class Kernel, class Params>
-static int launch_fused(Kernel kernel, int cg, int n_ctas, const Params& p, const CUtensorMap& wmap, cudaStream_t s, int smem_bytes = kSmemFused) {
+static int launch_fused(Kernel kernel, int cg, int n_ctas, const Params& p, const CUtensorMap& wmap, cudaStream_t s, int smem_bytes = kSmemFused,
+                        int threads = kFusedThreads) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)n_ctas);
-  cfg.blockDim = dim3(kFusedThreads);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];

@@ -239,6 +239,28 @@ def gen_vanilla(ref):
     print("vanilla: ok", tuple(rgb.shape), tuple(sigma.shape), f"sigma>0: {(sigma > 0).float().mean():.2f}")
 
 
+def gen_nadir(ref):
+    """create_rays_from_nadir / generate_rays_from_virtual_pinhole (eval_eonerf.py:78-249) and the UTM/altitude point cloud of
+    get_utmalt_from_nerf_prediction (satellite.py:502-531, utm_sampling branch) from the reference's own functions."""
+    import importlib
+    import types
+    ev = importlib.import_module("eval_eonerf")
+    scale, offset = torch.tensor([143.5, 139.25, 51.0], dtype=torch.float64), torch.tensor([435500.5, 3354950.25, 12.5], dtype=torch.float64)
+    out = {"scene_scale": scale.numpy(), "scene_offset": offset.numpy()}
+    for tag, (h, w, ds, el, az) in {"a": (12, 10, 1.0, 27.5, 151.0), "b": (33, 48, 2.0, 61.0, 110.5)}.items():
+        dataset = types.SimpleNamespace(scene_scale=scale, img_downscale=ds)
+        rays = ev.create_rays_from_nadir(dataset, h, w, el, az)
+        out.update({f"{tag}_h": np.int64(h), f"{tag}_w": np.int64(w), f"{tag}_downscale": np.float64(ds), f"{tag}_sun_el": np.float64(el),
+                    f"{tag}_sun_az": np.float64(az), f"{tag}_rays": rays.numpy()})
+    rays = torch.from_numpy(out["b_rays"])
+    depth = torch.rand(rays.shape[0], 1, generator=torch.Generator().manual_seed(5)) * 2
+    ds_self = types.SimpleNamespace(scene_scale=scale, scene_offset=offset, utm_sampling=True)
+    e, n, a = ref.satellite.SatelliteDataset.get_utmalt_from_nerf_prediction(ds_self, rays, depth)
+    out.update({"utm_depth": depth.numpy(), "utm_easts": e.numpy(), "utm_norths": n.numpy(), "utm_alts": a.numpy()})
+    np.savez_compressed(os.path.join(GOLD, "nadir.npz"), **out)
+    print("nadir: ok", out["a_rays"].shape, out["b_rays"].shape, e.dtype)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(GOLD, exist_ok=True)
@@ -254,4 +276,5 @@ if __name__ == "__main__":
     gen_render(ref)
     gen_redraw(ref)
     gen_vanilla(ref)
+    gen_nadir(ref)
     print("golden fixtures written to", GOLD)

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
   const int64_t it0 = blockIdx.x / kCl, it_stride = gridDim.x / kCl;
 
   if (warp == 0) {
-    if (lane == 0) fused_producer<kCG, kMC, kFwdRing>(p.prog, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank);
+    if (lane == 0) fused_producer<kCG, kMC, kFwdRing>(p.prog, p.wblob, &wmap, smem, B, it0, n_items, it_stride, rank, p.training & 16);
   } else if (warp == 1) {
     if (kCG == 1 || rank == 0)      // whole warp, converged
       fused_mma_issuer<kCG, kMC, true, kFwdRing, 5>(p.prog, smem, B, tmem_base, it0, n_items, it_stride, enc_full, enc_free);
@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
     const uint32_t s_part = smem_u32(part);
     uint32_t cph = 0;                               // bit `slot` = phase of acc_full[slot]
     uint64_t* const acc_full = B.acc_full;
+    int tr_i = 0; (void)tr_i;
     // The accumulators start from the layer's bias: every epilogue writes the NEXT layer's bias over the columns it has just
     // drained (tcgen05.st), so no bias add sits between the TMEM load and the bf16 pack.  Layer 0's goes in here for the
     // first item (later items: the last stage of the previous item writes it).
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
           cph ^= 1u << slot;
           tc_fence_after();
           EO_TN(tb);
+          EO_TRACE(1, tr_i, threadIdx.x == 64);
           const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + col0;
           float h0 = 0.f, h1 = 0.f, h2 = 0.f;               // head partial sums
 
@@ -366,7 +368,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
 
           // software pipeline over the chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
           uint32_t va[32], vb[32];
-          uint32_t m0, m1, m2 = 0u, m3 = 0u;
+          uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+          if (!(p.training & 8)) {                           // ablation knob 8: no accumulator drain at all (timing experiments only)
           tmem_ld32(taddr, va);
           tmem_ld_wait_dep(va);
           tmem_ld32(taddr + 32, vb);
@@ -391,8 +394,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
             next_bias_cols(128 + col0);
             next_bias_cols(128 + col0 + 32);
           }
+          }
           if (has_next) tmem_st_wait();
           EO_TN(tc);
+          EO_TRACE(1, tr_i, threadIdx.x == 64);
           if (want_mask && valid) {
             uint32_t* mrow = p.mask[d.mask] + pt * 8 + col0 / 32;
             if (cpt == 128) *(uint4*)mrow = make_uint4(m0, m1, m2, m3);
@@ -408,6 +413,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
           EO_TN(te);
           { EO_T0(); named_bar_sync(1, kBarThreads); if (e == 32) EO_T1(5); }
           EO_TN(tf);
+          EO_TRACE(1, tr_i, threadIdx.x == 64);
           if (!kDutyWarp && e == kSignalThread && has_next) signal_act_ready<kCG>(B, slot, rank);
           if (kTrain && store_id >= 0 && tile < n_tiles && !(p.training & 2)) {
             const int nb = d.halves * 2;                     // 16 KB blocks store_id, store_id + kStoreThreads, ... of the layer's output
@@ -604,7 +610,7 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   p.n_tiles = (N + kTileM - 1) / kTileM;
   p.n_stages = a->density_only ? 8 : kFwdStages;
   p.training = train;
-  if (const char* dbg = getenv("EONERF_FUSED_DBG")) p.training |= atoi(dbg);   // experiment knob: 2 = skip stash stores, 4 = skip masks
+  if (const char* dbg = getenv("EONERF_FUSED_DBG")) p.training |= atoi(dbg);   // experiment knobs: 2 = skip stash stores, 4 = skip masks, 8 = skip the accumulator drain, 16 = skip the weight loads
   p.x = a->x;
   p.origins = a->origins; p.o_stride = a->origins_stride; p.viewdirs = a->viewdirs; p.d_stride = a->viewdirs_stride;
   p.ray_indices = a->ray_indices; p.t_starts = a->t_starts; p.t_ends = a->t_ends; p.z_mid = a->z_mid;
@@ -654,6 +660,11 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
 }  // namespace eonerf
 
 #ifdef EONERF_TIMING
+extern "C" int eonerf_debug_trace(long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, eonerf::g_fused_trace, sizeof(long long) * 2048);
+  return 0;
+}
 extern "C" int eonerf_debug_timing(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, eonerf::g_fused_timing, sizeof(unsigned long long) * 16);

@@ -172,6 +172,10 @@ static inline int fused_grid(int64_t n_pairs) {
 // 4 epilogue start barrier (incl. stash-store drain), 5 epilogue end barrier, 6 total cycles of the MMA thread
 #ifdef EONERF_TIMING
 static __device__ unsigned long long g_fused_timing[16];   // one copy per translation unit
+// raw clock64 trace of CTA 0: [0][..] MMA thread (per slot-stage: slot handed over, MMAs issued), [1][..] epilogue thread 64 (per
+// slot-stage: accumulator seen, chunks done, end barrier passed)
+static __device__ long long g_fused_trace[2][1024];
+#define EO_TRACE(role, idx, cond) do { if (blockIdx.x == 0 && (cond) && (idx) < 1024) g_fused_trace[role][(idx)++] = clock64(); } while (0)
 #define EO_T0() const long long _t0 = clock64()
 #define EO_TN(name) const long long name = clock64()
 #define EO_TD(slot, a, b) do { if (blockIdx.x == 0 && threadIdx.x == 64) g_fused_timing[slot] += (unsigned long long)((b) - (a)); } while (0)
@@ -181,6 +185,7 @@ static __device__ unsigned long long g_fused_timing[16];   // one copy per trans
 #define EO_TN(name) do {} while (0)
 #define EO_TD(slot, a, b) do {} while (0)
 #define EO_T1(slot) do {} while (0)
+#define EO_TRACE(role, idx, cond) do {} while (0)
 #endif
 
 // ---- the tensor-core side of both fused kernels -------------------------------------------------------------------
@@ -230,8 +235,10 @@ __device__ __forceinline__ void fused_teardown(uint32_t tmem_base) {
 // one thread: stream this CTA's weight blocks through the ring
 template <int kCG, int kMC = 1, int kRing = kRingStages>
 __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uint8_t* wblob, const CUtensorMap* wmap, uint8_t* smem,
-                                               const FusedBars& B, int64_t it0, int64_t n_items, int64_t it_stride, uint32_t rank) {
+                                               const FusedBars& B, int64_t it0, int64_t n_items, int64_t it_stride, uint32_t rank,
+                                               int no_loads = 0) {
   int rs = 0; uint32_t rph = 0;
+  int filled = 0;                                    // ablation (no_loads): only the first ring fill is loaded, later blocks are "ready" at once
 #if EONERF_WEIGHT_HINT
   const uint64_t pol = l2_policy_evict_last();        // the weight blob is re-read by every CTA for every tile: keep it in L2
 #endif
@@ -245,6 +252,12 @@ __device__ __forceinline__ void fused_producer(const MmaProgram& prog, const uin
       for (int rep = 0; rep < 2; ++rep)
         for (int b = 0; b < nblk; ++b) {
           { EO_T0(); mbar_wait(&B.w_empty[rs], rph ^ 1); EO_T1(2); }
+          if (no_loads && filled >= kRing) {
+            if (kCG != 2 || rank == 0) mbar_arrive(&B.w_full[rs]);
+            if (++rs == kRing) { rs = 0; rph ^= 1; }
+            continue;
+          }
+          ++filled;
           if (kCG == 2) {
             // pair: both CTAs' copies are counted on the leader's barrier; block (stage, half = rank, kb) or, for the
             // 128-wide stages, rows rank*64.. of block kb
@@ -289,6 +302,7 @@ __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t
   int rs = 0; uint32_t rph = 0;
   uint32_t aph = 0;                                  // bit `slot` = phase of act_ready[slot]
   uint32_t eph = 0;                                  // bit `slot` = phase of enc_full[slot]
+  int tr_i = 0; (void)tr_i;
   const uint32_t ring0 = smem_u32(smem + kOffRing);
   const bool elected = elect_one_sync();
 #ifdef EONERF_TIMING
@@ -307,6 +321,7 @@ __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t
           eph ^= 1u << slot;
         }
         tc_fence_after();
+        EO_TRACE(0, tr_i, elected);
         const uint32_t slot0 = smem_u32(smem + off_slot(kRing) + slot * (kSlotBlk * kBlkBytes));
         for (int h = 0; h < n_h; ++h) {
           const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
@@ -334,6 +349,7 @@ __device__ __forceinline__ void fused_mma_issuer(const MmaProgram& prog, uint8_t
             if (kCG == 2) umma_commit_2cta(&enc_free[slot]); else umma_commit(&enc_free[slot]);
           }
         }
+        EO_TRACE(0, tr_i, elected);
         __syncwarp();
       }
     }

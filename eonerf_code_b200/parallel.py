@@ -62,18 +62,34 @@ class FlatGrads:
             self.flat.div_(world)
 
 
-def gather_rows(t, world, dst=0):
-    """Evaluation: every rank renders a contiguous block of rows; rank `dst` receives the concatenation."""
+def gather_rows(t, world, dst=0, n_total=None, out=None):
+    """Evaluation: every rank renders the contiguous block of rows `shard_bounds(n_total, rank, world)` gives it; rank `dst`
+    receives the concatenation [n_total, ...] (everybody else gets None).  The row counts follow from shard_bounds, so there
+    is no size exchange, no host synchronisation and no padding: rank `dst` posts one receive per peer straight into the
+    slice of the (pre-allocated, reusable via `out`) result, the peers post one send each, all in one batched P2P group.
+    n_total: total number of rows (default: world * t.shape[0], equal shards)."""
     if world == 1:
         return t
-    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
-    sizes = [int(s) for s in sizes]
-    mx = max(sizes)
-    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    pad[:t.shape[0]] = t
-    outs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(outs, pad)
-    if dist.get_rank() != dst:
+    rank = dist.get_rank()
+    if n_total is None:
+        n_total = world * t.shape[0]
+    b0, b1 = shard_bounds(n_total, rank, world)
+    if b1 - b0 != t.shape[0]:
+        raise ValueError(f"rank {rank} holds {t.shape[0]} rows, shard_bounds gives {b1 - b0}")
+    t = t.contiguous()
+    if rank != dst:
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, t, dst)]):
+            w.wait()
         return None
-    return torch.cat([o[:s] for o, s in zip(outs, sizes)], 0)
+    if out is None:
+        out = torch.empty((n_total,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    ops = []
+    for r in range(world):
+        r0, r1 = shard_bounds(n_total, r, world)
+        if r == dst:
+            out[r0:r1].copy_(t)
+        elif r1 > r0:
+            ops.append(dist.P2POp(dist.irecv, out[r0:r1], r))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    return out

@@ -78,6 +78,7 @@ def render_packed(
     uniforms=None,
     z_steps=None,
     static=False,
+    counters=None,
 ):
     """The body of render_image: -> (packed [B,21] per-ray outputs in the column order of OUT_SLICES (or depth [B,1] when
     only_depth), n_rendering_samples, rays_shape).  training.TrainStep evaluates its fused loss on the packed tensor."""
@@ -120,6 +121,8 @@ def render_packed(
             geo = ops._SunPassFn.apply(torch.is_grad_enabled(), e, chunk_rays.origins, chunk_rays.viewdirs, chunk_rays.sundirs, comp[:, 3:4], n,
                                        us.get("u_sun"), z_steps, info, static, *e.tensors())
             sc_ppr = info["sc_pts_per_ray"]
+            if counters is not None:                        # kept sun samples Q (int, or a 0-d device tensor when static)
+                counters["n_sun_samples"] = counters.get("n_sun_samples", 0) + info["n_sun_samples"]
         rad = radiance_field.radiometricT_enc.weight if radiance_field.radiometric_normalization else None
         rad_sink = e.grad_sink.get("radiometricT_enc.weight") if (rad is not None and e.grad_sink is not None) else None
         outs.append(ops._EpilogueFn.apply(comp, geo, ppr, sc_ppr, chunk_rays.img_idx, eval, rad, e.n_images, rad_sink))
@@ -148,18 +151,20 @@ def render_image(
     uniforms=None,
     z_steps=None,
     static=False,
+    counters=None,
 ):
     """sat_rendering.py:176-335 -> (dict of 12 [..., C] tensors (or {"depth"}), n_rendering_samples).
     `uniforms`: optional list with one dict per chunk {u_cam, u_sun, u_cam2} replacing the device RNG.
     `static=True` (fused precision only): the sync-free form used under CUDA-graph capture.  Sample counts never reach
     the host: packed arrays keep their B*(n-1) capacity and the kernels read P / Q on the device, the reference's
     "some ray kept no sample -> draw again" branch becomes a device-side condition (its uniforms are always drawn), and
-    n_rendering_samples comes back as a 0-d int64 device tensor."""
+    n_rendering_samples comes back as a 0-d int64 device tensor.
+    `counters`: optional dict; receives "n_sun_samples" = kept sun-ray samples (the FLOP count of the shadow pass follows it)."""
     out, n_rendering_samples, rays_shape = render_packed(
         radiance_field, occupancy_grid, rays, scene_aabb, args, epoch_idx=epoch_idx, chunk=chunk, near_plane=near_plane,
         far_plane=far_plane, render_step_size=render_step_size, render_bkgd=render_bkgd, cone_angle=cone_angle, alpha_thre=alpha_thre,
         early_stop_eps=early_stop_eps, timestamps=timestamps, only_depth=only_depth, eval=eval, uniforms=uniforms, z_steps=z_steps,
-        static=static)
+        static=static, counters=counters)
     if only_depth:
         return {"depth": out.view((*rays_shape[:-1], -1))}, n_rendering_samples
     return {k: out[:, a:b].view((*rays_shape[:-1], -1)) for k, a, b in OUT_SLICES}, n_rendering_samples

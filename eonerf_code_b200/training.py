@@ -44,6 +44,7 @@ class TrainStep:
         self._first_done = False
         self.launches_per_step = None           # kernels of libeonerf_b200 inside one captured step
         self.n_rendered_total = None            # graph mode: running sum of n_rendering_samples, on the device
+        self.n_sun_total = None                 # graph mode: running sum of the kept sun-ray samples, on the device
 
     # ------------------------------------------------------------------------------------------------------------------
     def _forward_backward(self, rays, ts, pixels, epoch_idx, static, uniforms=None):
@@ -55,13 +56,14 @@ class TrainStep:
         B = rays.shape[0]
         mb = self.micro_batch or B
         total_loss, total_rendered = None, 0
+        stats = {}
         for b0 in range(0, B, mb):
             sl = slice(b0, min(B, b0 + mb))
             sat = define_satrays_from_tensors(rays[sl], ts[sl])
             us = None if uniforms is None else [{k: v[sl] for k, v in uniforms.items()}]
             out, n_rendered, _ = sat_rendering.render_packed(self.field, None, sat, None, None, epoch_idx=epoch_idx,
                                                              chunk=self.chunk or (sl.stop - sl.start), render_step_size=self.render_step_size,
-                                                             static=static, uniforms=us)
+                                                             static=static, uniforms=us, counters=stats)
             if not static and n_rendered == 0:                               # train_eonerf.py:135-136
                 continue
             loss, _ = metrics.packed_loss(out, pixels[sl], epoch_idx)       # MSE (epoch < 2) / uncertainty-aware loss, value + gradient
@@ -72,6 +74,9 @@ class TrainStep:
             total_rendered = total_rendered + n_rendered
         if total_loss is None:
             return None, 0
+        self.last_sun_samples = stats.get("n_sun_samples", 0)     # int (eager) or 0-d device tensor (static)
+        if static and self.n_sun_total is not None and torch.is_tensor(self.last_sun_samples):
+            self.n_sun_total += self.last_sun_samples
         return total_loss, total_rendered
 
     def _update(self, averaged):
@@ -122,6 +127,7 @@ class TrainStep:
             return self.eager(rays, ts, pixels, epoch_idx, uniforms=uniforms)
         if self.n_rendered_total is None:
             self.n_rendered_total = torch.zeros((), dtype=torch.int64, device=rays.device)
+            self.n_sun_total = torch.zeros((), dtype=torch.int64, device=rays.device)
         if not self._first_done:
             self._first_done = True
             loss, n = self._forward_backward(rays, ts, pixels, epoch_idx, static=True, uniforms=uniforms)

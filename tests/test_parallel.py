@@ -42,6 +42,14 @@ def _worker(rank, world, port, out):
     loss.backward()
     flat.all_reduce_mean(world)
     rows = parallel.gather_rows(out_l.detach()[:, :4].contiguous(), world)
+    # uneven shards (7 rows over 2 ranks = 4 + 3) into a caller-provided buffer: no size exchange, only rank 0 receives
+    u0, u1 = parallel.shard_bounds(7, rank, world)
+    mine = torch.arange(u0, u1, dtype=torch.float32)[:, None].repeat(1, 3) + 0.5
+    buf = torch.full((7, 3), -1.0) if rank == 0 else None
+    uneven = parallel.gather_rows(mine, world, n_total=7, out=buf)
+    assert (uneven is None) == (rank != 0)
+    if rank == 0:
+        assert uneven.data_ptr() == buf.data_ptr() and torch.equal(uneven, torch.arange(7.0)[:, None].repeat(1, 3) + 0.5)
     if rank == 0:       # per-parameter views (the flat buffer pads every tensor to a 16-byte boundary)
         torch.save({"grad": torch.cat([q.grad.reshape(-1) for q in params]), "rows": rows, "bounds": (b, e),
                     "flat_numel": flat.flat.numel(), "offsets": flat.offsets}, out)

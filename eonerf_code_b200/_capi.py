@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeonerf_b200.so")
 
-ABI_VERSION = 13
+ABI_VERSION = 15
 COMP_COLS = 12
 OUT_COLS = 21
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16_FUSED = 0, 1, 2, 3
@@ -29,7 +29,7 @@ class SampleArgs(C.Structure):
     _fields_ = [("origins", P), ("origins_stride", I64), ("viewdirs", P), ("viewdirs_stride", I64),
                 ("near", P), ("near_stride", I64), ("u", P), ("z_steps", P), ("n_rays", I64), ("n_samples", I32),
                 ("ray_indices", P), ("t_starts", P), ("t_ends", P), ("pts_per_ray", P), ("ray_offsets", P), ("stats", P),
-                ("run_if", P)]
+                ("run_if", P), ("scratch", P)]
 
 
 class WeightsFwdArgs(C.Structure):
@@ -108,7 +108,7 @@ class FieldFwdArgs(C.Structure):
     _fields_ = [("field", I32), ("precision", I32), ("params", C.POINTER(FieldParams)), ("prepared", P), ("n_pts", I64),
                 ("x", P), ("origins", P), ("origins_stride", I64), ("viewdirs", P), ("viewdirs_stride", I64),
                 ("ray_indices", P), ("t_starts", P), ("t_ends", P), ("z_mid", P), ("img_idx", P), ("img_idx_stride", I64),
-                ("cond_dirs", P), ("cond_dirs_stride", I64), ("density_only", I32), ("stash", P),
+                ("cond_dirs", P), ("cond_dirs_stride", I64), ("cond_dirs_per_ray", I32), ("density_only", I32), ("stash", P),
                 ("sigma", P), ("rgb", P), ("transient_s", P), ("transient_beta", P), ("n_pts_dev", P)]
 
 
@@ -154,6 +154,12 @@ class LossArgs(C.Structure):
     _fields_ = [("out", P), ("gt_rgb", P), ("n_rays", I64), ("mode", I32), ("loss", P), ("g_out", P), ("partials", P)]
 
 
+class MarchArgs(C.Structure):
+    _fields_ = [("origins", P), ("origins_stride", I64), ("viewdirs", P), ("viewdirs_stride", I64), ("jitter", P), ("n_rays", I64),
+                ("aabb", F32 * 6), ("near_plane", F32), ("far_plane", F32), ("step", F32), ("max_per_ray", I32),
+                ("counts", P), ("t0_out", P), ("t_max_out", P), ("ray_offsets", P), ("ray_indices", P), ("t_starts", P), ("t_ends", P)]
+
+
 class UtmPointsArgs(C.Structure):
     _fields_ = [("rays", P), ("rays_stride", I64), ("depth", P), ("depth_stride", I64), ("n_rays", I64),
                 ("scene_scale", C.c_double * 3), ("scene_offset", C.c_double * 3), ("easts", P), ("norths", P), ("alts", P),
@@ -175,6 +181,7 @@ SYMBOLS = {
     "eonerf_launch_count": (I64, [I32]),
     "eonerf_profile_enable": (C.c_int, [I32]),
     "eonerf_profile_read": (C.c_int, [C.POINTER(Profile), I32]),
+    "eonerf_sample_scratch_bytes": (I64, [I64]),
     "eonerf_sample_compact": (C.c_int, _ARGS(SampleArgs)),
     "eonerf_pack_info": (C.c_int, [P, I64, I64, P, P]),
     "eonerf_set_last_t_end": (C.c_int, [P, P, I64, F32, P]),
@@ -204,6 +211,8 @@ SYMBOLS = {
     "eonerf_gather_batch": (C.c_int, _ARGS(GatherBatchArgs)),
     "eonerf_loss_partials": (I64, [I64]),
     "eonerf_loss_fwd_bwd": (C.c_int, _ARGS(LossArgs)),
+    "eonerf_march_count": (C.c_int, _ARGS(MarchArgs)),
+    "eonerf_march_write": (C.c_int, _ARGS(MarchArgs)),
     "eonerf_utm_points": (C.c_int, _ARGS(UtmPointsArgs)),
     "eonerf_dsm_rasterize": (C.c_int, _ARGS(DsmArgs)),
 }

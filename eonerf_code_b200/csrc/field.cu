@@ -134,20 +134,22 @@ __global__ void __launch_bounds__(256) encode_kernel(EonerfFieldFwdArgs a, float
 }
 
 // view-direction encoding (L=4) -> BOTT[:, 256:288]  (vanilla field, mlp.py:153-165)
+// rays != NULL: dirs holds one row per RAY (looked up through rays[p]); else one row per sample
 template <class T>
 __global__ void __launch_bounds__(256) encode_dirs_kernel(const float* __restrict__ dirs, int64_t stride, int64_t n,
-                                                          T* __restrict__ dst, int64_t ld, int col0) {
+                                                          T* __restrict__ dst, int64_t ld, int col0, const int64_t* __restrict__ rays) {
   int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t p = gid >> 5;
   int c = (int)(gid & 31);
   if (p >= n) return;
+  const int64_t row = rays ? __ldg(rays + p) : p;
   float v = 0.f;
-  if (c < 3) v = __ldg(dirs + p * stride + c);
+  if (c < 3) v = __ldg(dirs + row * stride + c);
   else if (c < 27) {
     int e = c - 3;
     int half = e >= 12;
     e -= half * 12;
-    float xb = __ldg(dirs + p * stride + e % 3) * (float)(1 << (e / 3));
+    float xb = __ldg(dirs + row * stride + e % 3) * (float)(1 << (e / 3));
     v = sinf(half ? __fadd_rn(xb, kHalfPi) : xb);
   }
   dst[p * ld + col0 + c] = from_f32<T>(v);
@@ -640,7 +642,8 @@ static int field_fwd_impl(const EonerfFieldFwdArgs* a, cudaStream_t s) {
     EO_REQUIRE(a->cond_dirs, "field_fwd: the vanilla field needs cond_dirs");
     EO_TRY(by_type(prec, [&](auto* tag) {
       using T = std::remove_pointer_t<decltype(tag)>;
-      encode_dirs_kernel<T><<<div_up(N * 32, 256), 256, 0, s>>>(a->cond_dirs, a->cond_dirs_stride, N, (T*)(st + S.bott), S.ld_bott, kW);
+      encode_dirs_kernel<T><<<div_up(N * 32, 256), 256, 0, s>>>(a->cond_dirs, a->cond_dirs_stride, N, (T*)(st + S.bott), S.ld_bott, kW,
+                                                                a->cond_dirs_per_ray ? a->ray_indices : nullptr);
       EO_LAUNCH_CHECK();
       return EONERF_OK;
     }));
@@ -896,7 +899,7 @@ extern "C" int eonerf_ambient_fwd(const EonerfAmbientFwdArgs* a, eonerf_stream_t
   int64_t B = a->n_rays;
   float* enc = a->stash;
   float* hid = a->stash + B * kDirEnc;
-  encode_dirs_kernel<float><<<div_up(B * 32, 256), 256, 0, s>>>(a->sundirs, a->sundirs_stride, B, enc, kDirEnc, 0);
+  encode_dirs_kernel<float><<<div_up(B * 32, 256), 256, 0, s>>>(a->sundirs, a->sundirs_stride, B, enc, kDirEnc, 0, nullptr);
   EO_LAUNCH_CHECK();
   GemmNT g;
   g.M = B; g.N = kHid; g.K = 27; g.A = enc; g.lda = kDirEnc; g.B = a->w0; g.ldb = 27; g.C = hid; g.ldc = kHid;

@@ -95,6 +95,10 @@ def on_tensor_device(fn):
     return wrapped
 
 
+# one-pass sampler (decoupled look-back; csrc/sampling.cu); EONERF_SAMPLER=3pass selects the count / scan / scatter form (A/B)
+import os as _os
+ONE_PASS_SAMPLER = _os.environ.get("EONERF_SAMPLER", "1pass") != "3pass"
+
 _Z_STEPS = {}
 
 
@@ -146,6 +150,9 @@ def sample_compact(origins, viewdirs, near, u, z_steps=None, redraw_of=None):
     a.pts_per_ray, a.ray_offsets, a.stats = _p(ppr), _p(offs), _p(stats)
     if redraw_of is not None:
         a.run_if = stats.data_ptr() + 8
+    if ONE_PASS_SAMPLER:
+        scratch = torch.empty(K.lib().eonerf_sample_scratch_bytes(B) // 8, dtype=torch.int64, device=dev)
+        a.scratch = _p(scratch)
     K.call("sample_compact", a, _stream())
     return ri, ts, te, ppr, offs, stats
 
@@ -165,6 +172,36 @@ def set_last_t_end(t_ends, ray_offsets, value=1e10):
     """In place: t_ends[last sample of each ray] = 1e10 (eonerf.py:218-220)."""
     n_rays = ray_offsets.numel() - 1
     K.check(K.lib().eonerf_set_last_t_end(_p(t_ends), _p(ray_offsets), n_rays, value, _stream()), "set_last_t_end")
+
+
+@on_tensor_device
+def march_aabb(origins, viewdirs, aabb, near_plane, far_plane, step, jitter=None, max_per_ray=4096):
+    """Uniform marching inside the scene box (csrc/march.cu; BASELINE configs[1]).  -> (ray_indices i64[P], t_starts[P],
+    t_ends[P], ray_offsets i64[B+1]).  One host read (the total P), like the reference's samplers."""
+    _need_cuda(origins, viewdirs, jitter)
+    o, os_ = _rows(origins)
+    d, ds_ = _rows(viewdirs)
+    B, dev = o.shape[0], o.device
+    a = K.MarchArgs()
+    a.origins, a.origins_stride, a.viewdirs, a.viewdirs_stride, a.n_rays = _p(o), os_, _p(d), ds_, B
+    if jitter is not None:
+        jitter = _f32(jitter).contiguous()
+        a.jitter = _p(jitter)
+    for i, v in enumerate([float(x) for x in torch.as_tensor(aabb).flatten().tolist()]):
+        a.aabb[i] = v
+    a.near_plane, a.far_plane, a.step, a.max_per_ray = float(near_plane), float(min(far_plane, 3.0e38)), float(step), int(max_per_ray)
+    counts = torch.empty(B, dtype=torch.int64, device=dev)
+    t0, tmax = torch.empty(B, dtype=torch.float32, device=dev), torch.empty(B, dtype=torch.float32, device=dev)
+    a.counts, a.t0_out, a.t_max_out = _p(counts), _p(t0), _p(tmax)
+    K.call("march_count", a, _stream())
+    offs = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=offs[1:])
+    P = int(offs[-1])
+    ri = torch.empty(P, dtype=torch.int64, device=dev)
+    ts, te = torch.empty(P, dtype=torch.float32, device=dev), torch.empty(P, dtype=torch.float32, device=dev)
+    a.ray_offsets, a.ray_indices, a.t_starts, a.t_ends = _p(offs), _p(ri), _p(ts), _p(te)
+    K.call("march_write", a, _stream())
+    return ri, ts, te, offs
 
 
 # ------------------------------------------------------------------------------------------------
@@ -358,7 +395,8 @@ class FieldEngine:
         return K.lib().eonerf_field_scratch_bytes(self.field, self.precision, n, self.n_images)
 
     @on_tensor_device
-    def fwd(self, n, density_only, x=None, rays=None, img_idx=None, cond_dirs=None, want_z=False, keep=True, n_dev=None):
+    def fwd(self, n, density_only, x=None, rays=None, img_idx=None, cond_dirs=None, want_z=False, keep=True, n_dev=None,
+            cond_dirs_per_ray=False):
         """rays = (origins, viewdirs, ray_indices, t_starts, t_ends).  Returns dict of outputs + stash.
         keep=False (inference): the fused mode keeps no activations at all; the layered modes still need the buffer.
         n_dev: int64[1] device tensor holding the live sample count (n is then the capacity): no host read of P."""
@@ -396,7 +434,7 @@ class FieldEngine:
             keep.append(ii)
         if cond_dirs is not None:
             cd, cs_ = _rows(cond_dirs)
-            a.cond_dirs, a.cond_dirs_stride = _p(cd), cs_
+            a.cond_dirs, a.cond_dirs_stride, a.cond_dirs_per_ray = _p(cd), cs_, int(bool(cond_dirs_per_ray))
             keep.append(cd)
         a.density_only, a.stash, a.sigma = int(density_only), _p(out["stash"]), _p(out["sigma"])
         a.n_pts_dev = _p(n_dev)
@@ -493,6 +531,34 @@ class _FieldFn(torch.autograd.Function):
         if e.grad_sync is not None and not direct:
             e.grad_sync(flat)
         return (None, None, None, gx, None, None) + _grads_tuple(e, views, ctx.params, direct)
+
+
+class _VanillaRaysFn(torch.autograd.Function):
+    """rgb_sigma_fn of nerfacc.rendering for the vanilla field (train_mlp_nerf.py:155-170 via nerfacc examples/utils.py):
+    positions x = o[ri] + d[ri] (t_s + t_e) / 2 and the per-sample view directions d[ri] are formed inside the kernels.
+    -> (sigma[P,1], rgb[P,3], z_mid[P])."""
+
+    @staticmethod
+    @on_tensor_device
+    def forward(ctx, grad_on, engine, origins, viewdirs, ri, ts, te, *params):
+        _need_cuda(origins, viewdirs, ri, ts, te)
+        P = ts.numel()
+        out = engine.fwd(P, False, rays=(origins, viewdirs, ri.contiguous(), ts, te), cond_dirs=viewdirs, cond_dirs_per_ray=True, want_z=True,
+                         keep=grad_on and any(ctx.needs_input_grad))
+        ctx.engine, ctx.n, ctx.out, ctx.params = engine, P, out, params
+        ctx.mark_non_differentiable(out["z_mid"])
+        return out["sigma"][:, None], out["rgb"], out["z_mid"]
+
+    @staticmethod
+    @on_tensor_device
+    def backward(ctx, g_sigma, g_rgb, _g_z):
+        e = ctx.engine
+        c = lambda g: None if g is None else _f32(g).contiguous()
+        flat, views, gstruct, direct = e.grads_for_backward()
+        e.bwd(ctx.n, False, ctx.out, g_sigma=c(g_sigma), g_rgb=c(g_rgb), grads_struct=gstruct)
+        if e.grad_sync is not None and not direct:
+            e.grad_sync(flat)
+        return (None,) * 7 + _grads_tuple(e, views, ctx.params, direct)
 
 
 class _AmbientFn(torch.autograd.Function):

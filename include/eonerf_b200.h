@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 13
+#define EONERF_ABI_VERSION 15
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -73,7 +73,13 @@ typedef struct {
    * stats[0] only: the sync-free form of the reference's "some ray kept no sample -> draw again" (sat_rendering.py:259-262),
    * called with run_if = &stats[1] of the first draw and the same output buffers. */
   const int64_t* run_if;
+  /* Scratch of eonerf_sample_scratch_bytes(n_rays) bytes (8-byte aligned; zeroed by the call).  When given, the sampler runs
+   * as ONE pass: each CTA evaluates a tile of rays once (kept intervals stay in registers), a decoupled look-back over
+   * per-tile descriptors in the scratch gives the tile its global offset, and the kept intervals are written in order.
+   * NULL: the three-launch count / scan / scatter form (evaluates every interval twice). */
+  int64_t* scratch;
 } EonerfSampleArgs;
+int64_t eonerf_sample_scratch_bytes(int64_t n_rays);
 int eonerf_sample_compact(const EonerfSampleArgs* a, eonerf_stream_t stream);
 
 /* ray_offsets[B+1] from sorted ray_indices[P] (nerfacc pack_info; used when the operator-level API is
@@ -290,6 +296,7 @@ typedef struct {
    * else per sample [N] */
   const int64_t* img_idx; int64_t img_idx_stride;
   const float* cond_dirs; int64_t cond_dirs_stride; /* vanilla field only: per-sample view directions [N,3] */
+  int32_t cond_dirs_per_ray;       /* 1: cond_dirs holds one row per RAY, looked up through ray_indices */
   int32_t density_only;            /* 1: query_density (trunk + sigma), eonerf.py:141-145 */
   void* stash;                     /* activations kept for backward */
   /* outputs, fp32 */
@@ -420,6 +427,31 @@ typedef struct {
 } EonerfLossArgs;
 int64_t eonerf_loss_partials(int64_t n_rays);
 int eonerf_loss_fwd_bwd(const EonerfLossArgs* a, eonerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Uniform in-box ray marching: the sampler of BASELINE configs[1] (train_mlp_nerf.py:155-170 -> nerfacc v0.5.2
+ * estimator.sampling with every cell occupied; the reference's own helper module `utils2` is missing, train_mlp_nerf.py:17,
+ * so this path is a benchmark without a pin).  Two calls around an exclusive scan of `counts` (done by the caller):
+ *   eonerf_march_count: counts[r] = number of render_step_size intervals of ray r inside aabb and [near_plane, far_plane]
+ *                       (+ t0_out / t_max_out per ray for the second call); jitter[r] in [0,1) shifts the ray's first
+ *                       interval (nerfacc's `stratified`), NULL = no shift;
+ *   eonerf_march_write: packed (ray_indices, t_starts, t_ends) from ray_offsets[B+1].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* origins; int64_t origins_stride;   /* [B,3] */
+  const float* viewdirs; int64_t viewdirs_stride; /* [B,3] */
+  const float* jitter;                            /* [B] or NULL */
+  int64_t n_rays;
+  float aabb[6];                                  /* minx miny minz maxx maxy maxz */
+  float near_plane; float far_plane; float step;
+  int32_t max_per_ray;
+  int64_t* counts;                                /* [B]   (march_count) */
+  float* t0_out; float* t_max_out;                /* [B]   (march_count writes, march_write reads) */
+  const int64_t* ray_offsets;                     /* [B+1] (march_write) */
+  int64_t* ray_indices; float* t_starts; float* t_ends;   /* [P] (march_write) */
+} EonerfMarchArgs;
+int eonerf_march_count(const EonerfMarchArgs* a, eonerf_stream_t stream);
+int eonerf_march_write(const EonerfMarchArgs* a, eonerf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Evaluation epilogue.

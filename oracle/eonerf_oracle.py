@@ -476,3 +476,42 @@ def train_step_grads(p, rays, pixels, n_samples, epoch_idx, u_cam, u_sun=None, u
     loss.backward()
     grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v))) for k, v in q.items())
     return loss.detach(), out.detach(), grads, n_rendered
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE configs[1]: vanilla NeRF rendering (train_mlp_nerf.py:155-170 -> nerfacc v0.5.2 examples/utils.py
+# render_image_with_occgrid + nerfacc.rendering).  The reference's own helper module is missing (train_mlp_nerf.py:17):
+# PARITY UNPINNED.  Restated: the occupancy-free limit of the sampler + the published conventions of nerfacc.rendering.
+# --------------------------------------------------------------------------------------------
+def march_aabb(origins, viewdirs, aabb, near_plane, far_plane, step, jitter=None, max_per_ray=4096):
+    """fp32, one torch op per arithmetic step (the CUDA kernel uses the same separately rounded operations)."""
+    o, d = origins.float(), viewdirs.float()
+    aabb = torch.as_tensor(aabb, dtype=torch.float32)
+    t1, t2 = (aabb[:3] - o) / d, (aabb[3:] - o) / d
+    tmin = torch.maximum(torch.minimum(t1, t2).max(dim=1).values, torch.tensor(float(near_plane)))
+    tmax = torch.minimum(torch.maximum(t1, t2).min(dim=1).values, torch.tensor(min(float(far_plane), 3.0e38)))
+    step_t = torch.tensor(step, dtype=torch.float32)
+    t0 = tmin + (jitter.float() * step_t if jitter is not None else 0.0)
+    n = torch.where(tmax > t0, torch.ceil((tmax - t0) / step_t), torch.zeros_like(t0)).long().clamp(max=max_per_ray)
+    ri = torch.repeat_interleave(torch.arange(o.shape[0]), n)
+    starts = torch.cumsum(n, 0) - n
+    k = (torch.arange(ri.numel()) - starts[ri]).float()
+    ts = t0[ri] + k * step_t
+    te = torch.minimum(ts + step_t, tmax[ri])
+    return ri, ts, te
+
+
+def vanilla_render(p, origins, viewdirs, aabb, near_plane, far_plane, step, jitter=None, render_bkgd=None):
+    """-> (colors[B,3], opacities[B,1], depths[B,1], n_samples) with nerfacc.rendering's conventions."""
+    B = origins.shape[0]
+    ri, ts, te = march_aabb(origins, viewdirs, aabb, near_plane, far_plane, step, jitter)
+    z = (ts + te)[:, None] / 2.0
+    x = origins[ri] + viewdirs[ri] * z
+    rgb, sigma = vanilla_forward(p, x, viewdirs[ri])
+    w, _, _ = nv.render_weight_from_density(ts, te, sigma.squeeze(-1), ray_indices=ri, n_rays=B)
+    colors = nv.accumulate_along_rays(w, rgb, ri, B)
+    opac = nv.accumulate_along_rays(w, None, ri, B)
+    depth = nv.accumulate_along_rays(w, z, ri, B) / opac.clamp_min(torch.finfo(torch.float32).eps)
+    if render_bkgd is not None:
+        colors = colors + render_bkgd * (1.0 - opac)
+    return colors, opac, depth, int(ts.numel())

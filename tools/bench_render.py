@@ -57,8 +57,20 @@ def main():
         rows.append((name, ms * 1e3, bytes_ / 1e6, gbs, gbs / peak))
         print(f"{name:28s} {ms * 1e3:9.1f} us  {bytes_ / 1e6:9.1f} MB algorithmic  {gbs:8.1f} GB/s  {100 * gbs / peak:5.1f} % of {peak:.0f}", flush=True)
 
-    report("sample_compact (3 kernels)", timeit(lambda: ops.sample_compact(rays[:, 0:3], rays[:, 3:6], rays[:, 6:7], u)),
-           P * 16 + B * 28 + B * n * 4)
+    # the C entry point alone, outputs pre-allocated (the Python wrapper's allocations are not the kernel's time)
+    sa_ = K.SampleArgs()
+    sa_.origins, sa_.origins_stride, sa_.viewdirs, sa_.viewdirs_stride = rays.data_ptr(), 11, rays.data_ptr() + 12, 11
+    sa_.near, sa_.near_stride = rays.data_ptr() + 24, 11
+    zs = ops.z_steps_for(n, dev)
+    sa_.u, sa_.z_steps, sa_.n_rays, sa_.n_samples = p(u), p(zs), B, n
+    sa_.ray_indices, sa_.t_starts, sa_.t_ends, sa_.pts_per_ray, sa_.ray_offsets, sa_.stats = p(ri), p(ts), p(te), p(ppr), p(offs), p(stats)
+    for one_pass in (True, False):
+        scratch = torch.empty(K.lib().eonerf_sample_scratch_bytes(B) // 8, dtype=torch.int64, device=dev)
+        sa_.scratch = p(scratch) if one_pass else None
+        report("sample_compact (" + ("one pass" if one_pass else "3 kernels") + ")", timeit(lambda: K.call("sample_compact", sa_, s())),
+               P * 16 + B * 28 + B * n * 4)
+    sa_.scratch = p(scratch)
+    K.call("sample_compact", sa_, s())
 
     f32 = lambda *sh: torch.rand(*sh, device=dev, dtype=torch.float32)
     z, sigma, alb, tsc, tb, amb = f32(P), f32(P) * 3, f32(P, 3), f32(P), f32(P) + 0.1, f32(B, 3)

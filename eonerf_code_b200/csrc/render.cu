@@ -14,6 +14,8 @@
 //
 // The exclusive scan is a *true* exclusive scan (inclusive scan shifted by one lane): the last interval
 // of a camera ray is 1e10 long (eonerf.py:220), "inclusive minus self" would cancel catastrophically.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace eonerf {
@@ -410,6 +412,261 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(EonerfCompositeBwdAr
 }
 
 // ------------------------------------------------------------------------------------------------
+// 128-bit vectorised forms.  A ray's samples are read through 16-byte-aligned windows of 128 samples: window w starts at
+// (beg & ~3) + 128 w, lane l owns the four consecutive samples s = start + 4 l .. s + 3 and fetches them with ONE 128-bit load
+// per array (three for the [P,3] albedo: its 12 floats are contiguous and 48-byte aligned).  Samples of the neighbouring rays
+// that fall into the first / last group are masked; the per-ray exclusive scan is a 4-step serial prefix inside the lane plus
+// a warp shuffle scan of the lane totals.  Used when every array is 16-byte aligned (checked on the host), else the scalar forms.
+// ------------------------------------------------------------------------------------------------
+struct Quad { float v[4]; };
+__device__ __forceinline__ Quad ldq(const float* __restrict__ p, int64_t s, int64_t n_pts) {
+  Quad q;
+  if (s + 4 <= n_pts) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p + s));
+    q.v[0] = t.x; q.v[1] = t.y; q.v[2] = t.z; q.v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) q.v[e] = (s + e < n_pts) ? __ldg(p + s + e) : 0.f;
+  }
+  return q;
+}
+__device__ __forceinline__ Quad zero_quad() { Quad q; q.v[0] = q.v[1] = q.v[2] = q.v[3] = 0.f; return q; }
+
+// transmittance in front of each of the lane's four samples (exclusive scan over the ray), carry across windows
+struct QuadScan { float pre[4]; };
+__device__ __forceinline__ QuadScan quad_exclusive(const float (&tau)[4], int lane, float& carry) {
+  const float p1 = tau[0], p2 = p1 + tau[1], p3 = p2 + tau[2], tot_lane = p3 + tau[3];
+  float tot;
+  const float ex = carry + warp_exclusive_sum(tot_lane, lane, tot);
+  carry += tot;
+  QuadScan r;
+  r.pre[0] = ex; r.pre[1] = ex + p1; r.pre[2] = ex + p2; r.pre[3] = ex + p3;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) weights_fwd_vec_kernel(EonerfWeightsFwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t ray = warp_ray(); ray < a.n_rays; ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+    float carry = 0.f;
+    for (int64_t wb = beg & ~(int64_t)3; wb < end; wb += 128) {
+      const int64_t s = wb + 4 * lane;
+      const bool any = s < end;
+      const Quad ts = any ? ldq(a.t_starts, s, a.n_pts) : zero_quad(), te = any ? ldq(a.t_ends, s, a.n_pts) : zero_quad(),
+                 sg = any ? ldq(a.sigmas, s, a.n_pts) : zero_quad();
+      float tau[4];
+      bool ok[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { ok[e] = s + e >= beg && s + e < end; tau[e] = ok[e] ? sg.v[e] * (te.v[e] - ts.v[e]) : 0.f; }
+      const QuadScan sc = quad_exclusive(tau, lane, carry);
+      float w[4], T[4], al[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const SampleW x = sample_weight(ts.v[e], te.v[e], sg.v[e], sc.pre[e]); w[e] = x.w; T[e] = x.T; al[e] = x.alpha; }
+      if (ok[0] && ok[3] && s + 4 <= a.n_pts) {                 // whole group inside the ray: 128-bit stores
+        if (a.weights) *reinterpret_cast<float4*>(a.weights + s) = make_float4(w[0], w[1], w[2], w[3]);
+        if (a.trans) *reinterpret_cast<float4*>(a.trans + s) = make_float4(T[0], T[1], T[2], T[3]);
+        if (a.alphas) *reinterpret_cast<float4*>(a.alphas + s) = make_float4(al[0], al[1], al[2], al[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (ok[e]) {
+            if (a.weights) a.weights[s + e] = w[e];
+            if (a.trans) a.trans[s + e] = T[e];
+            if (a.alphas) a.alphas[s + e] = al[e];
+          }
+      }
+    }
+  }
+}
+
+// C == 3 (or values == NULL, C == 1): out[r, c] = sum_i w_i v_{i,c}
+__global__ void __launch_bounds__(256) accumulate_fwd_vec_kernel(EonerfAccumFwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int C = a.n_channels;
+  for (int64_t ray = warp_ray(); ray < a.n_rays; ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int64_t wb = beg & ~(int64_t)3; wb < end; wb += 128) {
+      const int64_t s = wb + 4 * lane;
+      if (s >= end) continue;
+      const Quad w = ldq(a.weights, s, a.n_pts);
+      if (a.values && C == 3) {
+        const Quad v0 = ldq(a.values, 3 * s, 3 * a.n_pts), v1 = ldq(a.values, 3 * s + 4, 3 * a.n_pts), v2 = ldq(a.values, 3 * s + 8, 3 * a.n_pts);
+        const float vv[12] = {v0.v[0], v0.v[1], v0.v[2], v0.v[3], v1.v[0], v1.v[1], v1.v[2], v1.v[3], v2.v[0], v2.v[1], v2.v[2], v2.v[3]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (s + e >= beg && s + e < end) { acc[0] += w.v[e] * vv[3 * e]; acc[1] += w.v[e] * vv[3 * e + 1]; acc[2] += w.v[e] * vv[3 * e + 2]; }
+      } else {
+        const Quad v = a.values ? ldq(a.values, s, a.n_pts) : zero_quad();
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (s + e >= beg && s + e < end) acc[0] += w.v[e] * (a.values ? v.v[e] : 1.0f);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float t = warp_sum(acc[c]);
+      if (c < C && lane == 0) a.out[ray * C + c] = t;
+    }
+  }
+}
+
+struct CompQuad { Quad ts, te, sg, z, al0, al1, al2, tb, tsc; };
+template <class Args>
+__device__ __forceinline__ CompQuad comp_ldq(const Args& a, int64_t s) {
+  CompQuad q;
+  q.ts = ldq(a.t_starts, s, a.n_pts); q.te = ldq(a.t_ends, s, a.n_pts); q.sg = ldq(a.sigma, s, a.n_pts); q.z = ldq(a.z_mid, s, a.n_pts);
+  if (a.albedo) { q.al0 = ldq(a.albedo, 3 * s, 3 * a.n_pts); q.al1 = ldq(a.albedo, 3 * s + 4, 3 * a.n_pts); q.al2 = ldq(a.albedo, 3 * s + 8, 3 * a.n_pts); }
+  else { q.al0 = zero_quad(); q.al1 = zero_quad(); q.al2 = zero_quad(); }
+  q.tb = a.transient_beta ? ldq(a.transient_beta, s, a.n_pts) : zero_quad();
+  q.tsc = a.transient_s ? ldq(a.transient_s, s, a.n_pts) : zero_quad();
+  return q;
+}
+// albedo channel c of the lane's sample e: element 3 e + c of the 12 contiguous floats
+__device__ __forceinline__ float alb_of(const CompQuad& q, int e, int c) {
+  const int k = 3 * e + c;
+  return k < 4 ? q.al0.v[k] : (k < 8 ? q.al1.v[k - 4] : q.al2.v[k - 8]);
+}
+
+__global__ void __launch_bounds__(256) composite_fwd_vec_kernel(EonerfCompositeFwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t ray = warp_ray(); ray < a.n_rays; ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // albedo3, depth, beta, ts, sumw
+    float carry = 0.f;
+    for (int64_t wb = beg & ~(int64_t)3; wb < end; wb += 128) {
+      const int64_t s = wb + 4 * lane;
+      const bool any = s < end;
+      CompQuad q;
+      if (any) q = comp_ldq(a, s);
+      float tau[4];
+      bool ok[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { ok[e] = any && s + e >= beg && s + e < end; tau[e] = ok[e] ? q.sg.v[e] * (q.te.v[e] - q.ts.v[e]) : 0.f; }
+      const QuadScan sc = quad_exclusive(tau, lane, carry);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (ok[e]) {
+          const SampleW x = sample_weight(q.ts.v[e], q.te.v[e], q.sg.v[e], sc.pre[e]);
+          acc[0] += x.w * alb_of(q, e, 0); acc[1] += x.w * alb_of(q, e, 1); acc[2] += x.w * alb_of(q, e, 2);
+          acc[3] += x.w * q.z.v[e];
+          acc[4] += x.w * q.tb.v[e];
+          acc[5] += x.w * q.tsc.v[e];
+          acc[6] += x.w;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) acc[c] = warp_sum(acc[c]);
+    if (lane == 0) {
+      float* o = a.comp + ray * EONERF_COMP_COLS;
+      float am[3];
+      for (int c = 0; c < 3; ++c) am[c] = a.ambient_ray ? acc[6] * __ldg(a.ambient_ray + 3 * ray + c) : 0.f;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] + a.beta_min, acc[5], am[0], am[1]);
+      *reinterpret_cast<float4*>(o + 8) = make_float4(am[2], acc[6], 0.f, 0.f);
+    }
+  }
+}
+
+// two sweeps over the windows (S = sum_i G_i w_i first, then the exclusive suffixes): the second sweep's loads hit L1 / L2
+__global__ void __launch_bounds__(256) composite_bwd_vec_kernel(EonerfCompositeBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t ray = warp_ray(); ray < a.n_rays; ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t beg = a.ray_offsets[ray], end = a.ray_offsets[ray + 1];
+    const float* g = a.g_comp + ray * EONERF_COMP_COLS;
+    const float4 g03 = __ldg(reinterpret_cast<const float4*>(g)), g47 = __ldg(reinterpret_cast<const float4*>(g + 4)),
+                 g8b = __ldg(reinterpret_cast<const float4*>(g + 8));
+    const float ga[3] = {g03.x, g03.y, g03.z}, gd = g03.w, gb = g47.x, gs = g47.y;
+    const float gam[3] = {g47.z, g47.w, g8b.x};
+    float gconst = g8b.y;
+    if (a.ambient_ray)
+      for (int c = 0; c < 3; ++c) gconst += gam[c] * __ldg(a.ambient_ray + 3 * ray + c);
+    float S = 0.f, sumw = 0.f;
+    for (int sweep = 0; sweep < 2; ++sweep) {
+      float carry = 0.f, run = 0.f;
+      for (int64_t wb = beg & ~(int64_t)3; wb < end; wb += 128) {
+        const int64_t s = wb + 4 * lane;
+        const bool any = s < end;
+        CompQuad q;
+        if (any) q = comp_ldq(a, s);
+        float tau[4];
+        bool ok[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { ok[e] = any && s + e >= beg && s + e < end; tau[e] = ok[e] ? q.sg.v[e] * (q.te.v[e] - q.ts.v[e]) : 0.f; }
+        const QuadScan sc = quad_exclusive(tau, lane, carry);
+        float G[4], w[4], T1[4], v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          G[e] = w[e] = T1[e] = v[e] = 0.f;
+          if (ok[e]) {
+            const SampleW x = sample_weight(q.ts.v[e], q.te.v[e], q.sg.v[e], sc.pre[e]);
+            G[e] = gconst + gd * q.z.v[e] + ga[0] * alb_of(q, e, 0) + ga[1] * alb_of(q, e, 1) + ga[2] * alb_of(q, e, 2) + gb * q.tb.v[e] + gs * q.tsc.v[e];
+            w[e] = x.w;
+            T1[e] = x.T * expf(-x.tau);                       // T_{j+1} = T_j exp(-tau_j)
+            v[e] = G[e] * x.w;
+          }
+        }
+        if (sweep == 0) {
+          S += (v[0] + v[1]) + (v[2] + v[3]);
+          sumw += (w[0] + w[1]) + (w[2] + w[3]);
+          continue;
+        }
+        // inclusive prefix of v inside the ray, then suffix_i = S - prefix_i (exactly 0 for the 1e10-long last interval)
+        const float i0 = v[0], i1 = i0 + v[1], i2 = i1 + v[2], i3 = i2 + v[3];
+        float tot;
+        const float ex = run + warp_exclusive_sum(i3, lane, tot);
+        run += tot;
+        const float inc[4] = {ex + i0, ex + i1, ex + i2, ex + i3};
+        float gsig[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float suffix = (s + e == end - 1) ? 0.f : S - inc[e];
+          gsig[e] = (q.te.v[e] - q.ts.v[e]) * (G[e] * T1[e] - suffix);
+        }
+        if (ok[0] && ok[3] && s + 4 <= a.n_pts) {
+          *reinterpret_cast<float4*>(a.g_sigma + s) = make_float4(gsig[0], gsig[1], gsig[2], gsig[3]);
+          if (a.g_albedo) {
+            float4* ga4 = reinterpret_cast<float4*>(a.g_albedo + 3 * s);
+            ga4[0] = make_float4(w[0] * ga[0], w[0] * ga[1], w[0] * ga[2], w[1] * ga[0]);
+            ga4[1] = make_float4(w[1] * ga[1], w[1] * ga[2], w[2] * ga[0], w[2] * ga[1]);
+            ga4[2] = make_float4(w[2] * ga[2], w[3] * ga[0], w[3] * ga[1], w[3] * ga[2]);
+          }
+          if (a.g_transient_beta) *reinterpret_cast<float4*>(a.g_transient_beta + s) = make_float4(w[0] * gb, w[1] * gb, w[2] * gb, w[3] * gb);
+          if (a.g_transient_s) *reinterpret_cast<float4*>(a.g_transient_s + s) = make_float4(w[0] * gs, w[1] * gs, w[2] * gs, w[3] * gs);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (ok[e]) {
+              a.g_sigma[s + e] = gsig[e];
+              if (a.g_albedo) { a.g_albedo[3 * (s + e)] = w[e] * ga[0]; a.g_albedo[3 * (s + e) + 1] = w[e] * ga[1]; a.g_albedo[3 * (s + e) + 2] = w[e] * ga[2]; }
+              if (a.g_transient_beta) a.g_transient_beta[s + e] = w[e] * gb;
+              if (a.g_transient_s) a.g_transient_s[s + e] = w[e] * gs;
+            }
+        }
+      }
+      if (sweep == 0) {
+        S = warp_sum(S);
+        sumw = warp_sum(sumw);
+        if (lane == 0 && a.g_ambient_ray)
+          for (int c = 0; c < 3; ++c) a.g_ambient_ray[3 * ray + c] = gam[c] * sumw;
+      }
+    }
+  }
+}
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+// Measured at 65 536 rays x 128 samples (profiles/r2c_render_vec_ab.log): the 128-bit forms win only where the scalar form was
+// instruction-limited (accumulate_fwd: 60 % -> 68 % of the HBM peak); compositing / weights are bound by the per-ray scan + exp
+// chain and by register pressure (4 samples per lane: 118 registers), not by the load width, and the scalar forms with four
+// 32-sample chunks in flight stay faster (composite_fwd 69 % vs 61 %, composite_bwd 73 % vs 44 %, weights_fwd 71 % vs 66 %).
+// EONERF_RENDER_VEC: 1 (default) = accumulate_fwd only, 2 = every vectorised form (A/B timing), 0 = none.
+static inline int render_vec_level() {
+  static const int lvl = [] { const char* e = getenv("EONERF_RENDER_VEC"); return e ? atoi(e) : 1; }();
+  return lvl;
+}
+static inline bool render_vec_enabled() { return render_vec_level() >= 2; }
+
+// ------------------------------------------------------------------------------------------------
 // Sun-ray shadow pass (sat_rendering.py:87-118)
 // ------------------------------------------------------------------------------------------------
 __global__ void sun_rays_kernel(EonerfSunRaysArgs a) {
@@ -602,7 +859,11 @@ extern "C" int eonerf_weights_fwd(const EonerfWeightsFwdArgs* a, eonerf_stream_t
   EO_REQUIRE(a && a->ray_offsets && a->n_rays >= 0, "weights_fwd: bad arguments");
   if (a->n_rays == 0) return EONERF_OK;
   EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->sigmas), "weights_fwd: null input");
-  weights_fwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  if (render_vec_enabled() && aligned16(a->t_starts) && aligned16(a->t_ends) && aligned16(a->sigmas) && aligned16(a->weights) && aligned16(a->trans) &&
+      aligned16(a->alphas))
+    weights_fwd_vec_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  else
+    weights_fwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -621,7 +882,10 @@ extern "C" int eonerf_accumulate_fwd(const EonerfAccumFwdArgs* a, eonerf_stream_
   EO_REQUIRE(a->values || a->n_channels == 1, "accumulate_fwd: values==NULL needs n_channels==1");
   if (a->n_rays == 0) return EONERF_OK;
   EO_REQUIRE(a->out && (a->n_pts == 0 || a->weights), "accumulate_fwd: null pointer");
-  accumulate_fwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  if (render_vec_level() >= 1 && aligned16(a->weights) && aligned16(a->values) && (a->n_channels == 3 || a->n_channels == 1))
+    accumulate_fwd_vec_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  else
+    accumulate_fwd_kernel<<<RAY_BLOCKS(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -640,7 +904,11 @@ extern "C" int eonerf_composite_fwd(const EonerfCompositeFwdArgs* a, eonerf_stre
   EO_REQUIRE(a && a->ray_offsets && a->comp && a->n_rays >= 0, "composite_fwd: bad arguments");
   if (a->n_rays == 0) return EONERF_OK;
   EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->z_mid && a->sigma), "composite_fwd: null input");
-  composite_fwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  if (render_vec_enabled() && aligned16(a->t_starts) && aligned16(a->t_ends) && aligned16(a->z_mid) && aligned16(a->sigma) && aligned16(a->albedo) &&
+      aligned16(a->transient_s) && aligned16(a->transient_beta))
+    composite_fwd_vec_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  else
+    composite_fwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }
@@ -650,7 +918,12 @@ extern "C" int eonerf_composite_bwd(const EonerfCompositeBwdArgs* a, eonerf_stre
   if (a->n_rays == 0) return EONERF_OK;
   EO_REQUIRE(a->n_pts == 0 || (a->t_starts && a->t_ends && a->z_mid && a->sigma && a->g_sigma),
              "composite_bwd: null pointer");
-  composite_bwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  if (render_vec_enabled() && aligned16(a->t_starts) && aligned16(a->t_ends) && aligned16(a->z_mid) && aligned16(a->sigma) && aligned16(a->albedo) &&
+      aligned16(a->transient_s) && aligned16(a->transient_beta) && aligned16(a->g_sigma) && aligned16(a->g_albedo) && aligned16(a->g_transient_s) &&
+      aligned16(a->g_transient_beta))
+    composite_bwd_vec_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
+  else
+    composite_bwd_kernel<<<ray_blocks_capped(a->n_rays), 256, 0, as_stream(stream)>>>(*a);
   EO_LAUNCH_CHECK();
   return EONERF_OK;
 }

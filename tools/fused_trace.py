@@ -14,7 +14,7 @@ keep = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dev = torch.device("cuda:0")
 n, n_img = 1_000_000, 19
 x = torch.rand(n, 3, device=dev) * 2 - 1
-img = torch.randint(0, n_img, (n, 1), device=dev)
+img = ((torch.arange(n, device=dev) // 127) % n_img)[:, None] if os.environ.get("REAL_IMG", "1") == "1" else torch.randint(0, n_img, (n, 1), device=dev)
 m = EONerfMLP(n_img, radiometric_normalization=True, precision="bf16_fused").to(dev)
 e = m._engine()
 lib = C.CDLL(K.LIB_PATH)

@@ -65,7 +65,9 @@ def table(rep):
         res.append((name, float(g("gpu__time_duration.sum")), rr[1][idx["gpu__time_duration.sum"]], float(g("dram__bytes_read.sum")),
                     rr[1][idx["dram__bytes_read.sum"]], float(g("dram__bytes_write.sum")), rr[1][idx["dram__bytes_write.sum"]],
                     g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"), g("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
-                    g("smsp__issue_active.avg.pct_of_peak_sustained_active"), g("launch__registers_per_thread")))
+                    g("smsp__issue_active.avg.pct_of_peak_sustained_active"), g("launch__registers_per_thread"),
+                    g("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                    g("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")))
     return res
 
 
@@ -76,9 +78,10 @@ for rep, head in reps:
     if not os.path.exists(path):
         continue
     out += [f"## `ncu --set full` of {head}\n",
-            "| kernel | duration | dram read | dram write | tensor pipe active % | lts throughput % | issue active % | regs |", "|---|---:|---:|---:|---:|---:|---:|---:|"]
+            "| kernel | duration | dram read | dram write | tensor pipe active % | lts throughput % | issue active % | regs | smem wavefronts LSU % | smem wavefronts tensor % |",
+            "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
     for r in table(path):
-        out.append(f"| `{r[0]}` | {r[1]:.3f} {r[2]} | {r[3]:.2f} {r[4]} | {r[5]:.2f} {r[6]} | {float(r[7] or 0):.1f} | {float(r[8] or 0):.1f} | {float(r[9] or 0):.1f} | {r[10]} |")
+        out.append(f"| `{r[0]}` | {r[1]:.3f} {r[2]} | {r[3]:.2f} {r[4]} | {r[5]:.2f} {r[6]} | {float(r[7] or 0):.1f} | {float(r[8] or 0):.1f} | {float(r[9] or 0):.1f} | {r[10]} | {float(r[11] or 0):.1f} | {float(r[12] or 0):.1f} |")
     out.append("")
 # per-launch DRAM traffic of the dominant kernels for bench.py's roofline.traffic (read by bench.py from profiles/traffic.json)
 ff = table(os.path.join(G, "fused_full.ncu-rep")) if os.path.exists(os.path.join(G, "fused_full.ncu-rep")) else []
@@ -90,6 +93,10 @@ if fused:
                "fused_fwd_bwd_bytes_per_launch": sum(fused) / len(fused), "fused_launches": len(fused),
                "dw_gemm_bytes_per_launch": (sum(dw) / len(dw)) if dw else None, "dw_launches": len(dw)},
               open(os.path.join(P, "traffic.json"), "w"), indent=1)
+if os.path.exists(os.path.join(G, "bench_field.log")):
+    out.append("## Fused field kernels alone, 1 M samples, CUDA events (`tools/bench_field.py --bwd`; bwd = input-gradient chain + dW GEMM + head gradients)\n\n```")
+    out += [l.rstrip() for l in open(os.path.join(G, "bench_field.log")).read().splitlines()]
+    out.append("```\n")
 out.append("## HBM-bound SIMT kernels, CUDA events (`tools/bench_render.py`)\n\n```")
 out += [l.rstrip() for l in open(os.path.join(G, "bench_render.log")).read().splitlines() if not l.startswith("{")]
 out.append("```")

@@ -258,7 +258,7 @@ def extra_train_arms(args, rank, world, dev, barrier, max_over_ranks):
     from eonerf_code_b200.radiance_fields import VanillaNeRFRadianceField
     from eonerf_code_b200.vanilla_rendering import Rays, render_image_with_occgrid
     torch.manual_seed(42)
-    vm = VanillaNeRFRadianceField(precision="bf16").to(dev).train()
+    vm = VanillaNeRFRadianceField(precision="bf16_fused" if args.precision == "bf16_fused" else "bf16").to(dev).train()
     est = OccGridEstimator(roi_aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], resolution=64, levels=1).to(dev)
     vopt = torch.optim.Adam(vm.parameters(), lr=5e-4)
     vb = [tuple(t.to(dev) for t in make_pinhole_rays(4096, seed=77 + i)) for i in range(2)]
@@ -288,7 +288,7 @@ def extra_train_arms(args, rank, world, dev, barrier, max_over_ranks):
                    "samples_per_step": int(n_v), "samples_per_sec": n_v / (vms * 1e-3), "loss": float(vl),
                    "workload": "BASELINE configs[1]: VanillaNeRFRadianceField (8x256 + 1x128, view-conditioned), 4096 pinhole rays of an 800x800 "
                                "lego-shaped camera, box +-1.5, uniform marching at 5e-3, nerfacc.rendering conventions, smooth-L1 + Adam; "
-                               "layer-by-layer tcgen05 GEMMs (bf16); the reference's own marcher module is missing (parity unpinned)"}
+                               "fused tcgen05 field kernels (first ten stages of the EO-NeRF program); the reference's own marcher module is missing (parity unpinned)"}
     del vm, vopt, vb, est
     torch.cuda.empty_cache()
     if 65536 % world == 0:

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeonerf_b200.so")
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 COMP_COLS = 12
 OUT_COLS = 21
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16_FUSED = 0, 1, 2, 3
@@ -109,7 +109,7 @@ class FieldFwdArgs(C.Structure):
                 ("x", P), ("origins", P), ("origins_stride", I64), ("viewdirs", P), ("viewdirs_stride", I64),
                 ("ray_indices", P), ("t_starts", P), ("t_ends", P), ("z_mid", P), ("img_idx", P), ("img_idx_stride", I64),
                 ("cond_dirs", P), ("cond_dirs_stride", I64), ("cond_dirs_per_ray", I32), ("density_only", I32), ("stash", P),
-                ("sigma", P), ("rgb", P), ("transient_s", P), ("transient_beta", P), ("n_pts_dev", P)]
+                ("sigma", P), ("rgb", P), ("transient_s", P), ("transient_beta", P), ("n_pts_dev", P), ("dir_bias", P), ("n_cond", I64)]
 
 
 class FieldBwdArgs(C.Structure):
@@ -117,7 +117,7 @@ class FieldBwdArgs(C.Structure):
                 ("density_only", I32), ("stash", P), ("scratch", P),
                 ("sigma", P), ("rgb", P), ("transient_s", P), ("transient_beta", P),
                 ("g_sigma", P), ("g_rgb", P), ("g_transient_s", P), ("g_transient_beta", P),
-                ("grads", C.POINTER(FieldParams)), ("g_x", P), ("n_pts_dev", P)]
+                ("grads", C.POINTER(FieldParams)), ("g_x", P), ("n_pts_dev", P), ("cond_dirs", P), ("cond_dirs_stride", I64), ("n_cond", I64)]
 
 
 class AmbientFwdArgs(C.Structure):

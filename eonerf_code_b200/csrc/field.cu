@@ -835,17 +835,17 @@ static bool valid_field(int f) { return f == EONERF_FIELD_EONERF || f == EONERF_
 
 extern "C" int64_t eonerf_field_prepared_bytes(int32_t field, int32_t precision, int64_t n_images) {
   if (!valid_prec(precision) || !valid_field(field)) return -1;
-  if (fused(precision)) return field == EONERF_FIELD_EONERF ? prep_layout(field, EONERF_PREC_BF16, n_images).total + fused_prepared_extra_bytes(n_images) : -1;
+  if (fused(precision)) return prep_layout(field, EONERF_PREC_BF16, n_images).total + fused_prepared_extra_bytes(n_images);
   return prep_layout(field, precision, n_images).total;
 }
 extern "C" int64_t eonerf_field_stash_bytes(int32_t field, int32_t precision, int64_t n_pts, int32_t density_only) {
   if (!valid_prec(precision) || !valid_field(field) || n_pts < 0) return -1;
-  if (fused(precision)) return field == EONERF_FIELD_EONERF ? fused_stash_bytes(n_pts, density_only) : -1;
+  if (fused(precision)) return fused_stash_bytes(n_pts, density_only);
   return stash_layout(field, precision, n_pts, density_only).total;
 }
 extern "C" int64_t eonerf_field_scratch_bytes(int32_t field, int32_t precision, int64_t n_pts, int64_t n_images) {
   if (!valid_prec(precision) || !valid_field(field) || n_pts < 0) return -1;
-  if (fused(precision)) return field == EONERF_FIELD_EONERF ? fused_scratch_bytes(n_pts, n_images, 0) : -1;
+  if (fused(precision)) return fused_scratch_bytes(n_pts, n_images, 0);
   return scratch_layout(field, precision, n_pts, n_images).total;
 }
 
@@ -855,9 +855,8 @@ extern "C" int eonerf_field_prepare(int32_t field, int32_t precision, const Eone
   EO_REQUIRE(params && prepared, "field_prepare: null pointer");
   EO_REQUIRE(field == EONERF_FIELD_VANILLA || (params->n_images > 0 && params->transient_emb), "field_prepare: need n_images > 0");
   if (fused(precision)) {
-    EO_REQUIRE(field == EONERF_FIELD_EONERF, "field_prepare: the fused precision mode supports the EO-NeRF field only");
     EO_TRY(field_prepare_impl(field, EONERF_PREC_BF16, params, prepared, as_stream(stream)));
-    return fused_prepare(params, prepared, as_stream(stream));
+    return fused_prepare(field, params, prepared, as_stream(stream));
   }
   return field_prepare_impl(field, precision, params, prepared, as_stream(stream));
 }

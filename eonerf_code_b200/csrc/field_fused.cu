@@ -56,6 +56,10 @@ __constant__ FStage c_fstage[kFwdStages] = {
 
 struct FusedFwdParams {
   int64_t M; int64_t n_tiles; int n_stages; int training;
+  // cls_mode: class of a sample = row of `class_delta` added to the HD0 stage's bias.  0: EO-NeRF, image index of the sample's ray
+  // (columns 128..255: transient half); 1 / 2: vanilla field, the ray (1) or the sample itself (2): row of the per-direction bias
+  // table (columns 0..127: rgb hidden layer).  vanilla also selects sigma = relu(.) instead of softplus(.)  (mlp.py:243,250).
+  int cls_mode; int vanilla;
   const int64_t* M_dev;          // live sample count on the device (M, n_tiles are then capacities)
   const float* x;
   const float* origins; int64_t o_stride; const float* viewdirs; int64_t d_stride;
@@ -141,8 +145,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
             }
             if (kTrain) {
               p.xf[3 * pt] = x[0]; p.xf[3 * pt + 1] = x[1]; p.xf[3 * pt + 2] = x[2];
-              if (p.cls && p.img_idx)
+              if (p.cls && p.cls_mode == 0 && p.img_idx)
                 p.cls[pt] = (int32_t)(p.ray_indices ? __ldg(p.img_idx + ray * p.img_stride) : __ldg(p.img_idx + pt * p.img_stride));
+              if (p.cls && p.cls_mode != 0) p.cls[pt] = (int32_t)(p.cls_mode == 1 ? ray : pt);
             }
           }
           uint32_t w[16];
@@ -239,13 +244,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
       const bool next_item = it + it_stride < n_items;
       // image index of this row in slot 0 (low 16 bits) / slot 1: selects the per-image bias row of the HD0 stage (fetched now,
       // used eight stages later)
-      uint32_t cls_pack = 0;
-      if (p.img_idx)
+      uint32_t cls0 = 0u, cls1 = 0u;
+      if (p.img_idx || p.cls_mode != 0)
         for (int slot = 0; slot < 2; ++slot) {
           const int64_t pt = (2 * kCl * it + 2 * rank + slot) * kTileM + r;
           if (pt < M) {
-            const int64_t img = p.ray_indices ? __ldg(p.img_idx + __ldg(p.ray_indices + pt) * p.img_stride) : __ldg(p.img_idx + pt * p.img_stride);
-            cls_pack |= ((uint32_t)img & 0xFFFFu) << (16 * slot);
+            int64_t c;
+            if (p.cls_mode == 0) c = p.ray_indices ? __ldg(p.img_idx + __ldg(p.ray_indices + pt) * p.img_stride) : __ldg(p.img_idx + pt * p.img_stride);
+            else c = p.cls_mode == 1 ? __ldg(p.ray_indices + pt) : pt;
+            if (slot == 0) cls0 = (uint32_t)c; else cls1 = (uint32_t)c;
           }
         }
 
@@ -265,7 +272,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
           const bool valid = pt < M;
           const uint32_t act = smem_u32(smem + kFOffSlot + slot * kFSlotBytes);
           // per-image part of the HD0 bias (transient half only): W[:,256:260] . emb[img]
-          const float* delta_next = (has_next && dn.kind == 2) ? p.class_delta + (size_t)((cls_pack >> (16 * slot)) & 0xFFFFu) * kHid : nullptr;
+          const float* delta_next = (has_next && dn.kind == 2 && p.class_delta) ? p.class_delta + (size_t)(slot == 0 ? cls0 : cls1) * kHid : nullptr;
+          const int delta_col0 = p.vanilla ? 0 : kHid;       // first of the 128 accumulator columns the class row is added to
           EO_TN(ta); { EO_T0(); mbar_wait(&acc_full[slot], (cph >> slot) & 1u); if (e == 0) EO_T1(3); }
           cph ^= 1u << slot;
           tc_fence_after();
@@ -287,10 +295,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
               cf4<kFwdConstG>(p.consts, sb + j * 16, b0, b1, b2, b3);
               b[4 * j] = __float_as_uint(b0); b[4 * j + 1] = __float_as_uint(b1); b[4 * j + 2] = __float_as_uint(b2); b[4 * j + 3] = __float_as_uint(b3);
             }
-            if (delta_next && colg >= kHid) {
+            if (delta_next && colg >= delta_col0 && colg < delta_col0 + kHid) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 t = __ldg((const float4*)(delta_next + colg - kHid) + j);
+                const float4 t = __ldg((const float4*)(delta_next + colg - delta_col0) + j);
                 b[4 * j] = __float_as_uint(__uint_as_float(b[4 * j]) + t.x); b[4 * j + 1] = __float_as_uint(__uint_as_float(b[4 * j + 1]) + t.y);
                 b[4 * j + 2] = __float_as_uint(__uint_as_float(b[4 * j + 2]) + t.z); b[4 * j + 3] = __float_as_uint(__uint_as_float(b[4 * j + 3]) + t.w);
               }
@@ -425,7 +433,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
             float p0 = 0.f, p1 = 0.f;
             if (d.kind != 2) lds_f2(s_part + slot * 1024 + r * 8, p0, p1);
             if (d.kind == 1) {
-              p.sigma[pt] = softplus_f(h0 + p0 + cscal(0));                          // eonerf.py:106,145
+              const float pre = h0 + p0 + cscal(0);
+              p.sigma[pt] = p.vanilla ? fmaxf(pre, 0.f) : softplus_f(pre);           // eonerf.py:106,145 / mlp.py:243,250
             } else if (d.kind == 2) {
               p.rgb[3 * pt + 0] = sigmoid_f(h0 + cscal(1));
               p.rgb[3 * pt + 1] = sigmoid_f(h1 + cscal(2));
@@ -536,12 +545,42 @@ int fused_cta_group() {
   return mode;
 }
 
-int fused_prepare(const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
-  const PrepLayout W = prep_layout(EONERF_FIELD_EONERF, EONERF_PREC_BF16, p->n_images);
+// dir_bias[r, j] = sum_e W_rgb0[j, 256 + e] enc4(dir_r)[e]   (mlp.py:153-165,199-205: the view-direction columns of
+// rgb_layer.hidden_layers.0 folded into a bias row per conditioning row; fp32)
+__global__ void __launch_bounds__(128) vanilla_dir_bias_kernel(const float* __restrict__ dirs, int64_t stride, int64_t n, const float* __restrict__ w,
+                                                               float* __restrict__ out) {
+  __shared__ float enc[32];
+  const int64_t r = blockIdx.x;
+  if (r >= n) return;
+  const int t = threadIdx.x;
+  if (t < 32) {
+    float v = 0.f;
+    if (t < 3) v = __ldg(dirs + r * stride + t);
+    else if (t < 27) {
+      int e = t - 3;
+      const int half = e >= 12;
+      e -= half * 12;
+      const float xb = __ldg(dirs + r * stride + e % 3) * (float)(1 << (e / 3));
+      v = sinf(half ? __fadd_rn(xb, kHalfPi) : xb);
+    }
+    enc[t] = v;
+  }
+  __syncthreads();
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < 27; ++e) acc = fmaf(__ldg(w + t * 283 + 256 + e), enc[e], acc);
+  out[r * kHid + t] = acc;
+}
+
+int fused_prepare(int field, const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
+  const bool vanilla = field == EONERF_FIELD_VANILLA;
+  const PrepLayout W = prep_layout(field, EONERF_PREC_BF16, p->n_images);
   const FusedPrepLayout F = fused_prep_layout(p->n_images);
   uint8_t* base = (uint8_t*)prepared;
   uint8_t* ext = base + W.total;
   auto bf = [&](int64_t off) { return (const __nv_bfloat16*)(base + off); };
+  // the vanilla field runs the first ten stages of the same program: its rgb hidden layer takes the place of the albedo half of
+  // the HD0 stage (the other half, and the three transient stages, are zero blocks)
   {  // forward blocks: stage-major, then output half, then k block;  B = W [out, Kp]
     PackJobs J{};
     int n = 0;
@@ -549,10 +588,16 @@ int fused_prepare(const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
       for (int h = 0; h < out_rows / 128; ++h)
         for (int kb = 0; kb < kp / 64; ++kb) J.j[n++] = PackJob{src, ld, h * 128, 128, kb * 64};
     };
+    auto zeros = [&](int count) { for (int i = 0; i < count; ++i) J.j[n++] = PackJob{bf(W.w[0]), 64, 0, 0, 0}; };
     for (int i = 0; i < 8; ++i) add(bf(W.w[i]), trunk_kp(i), kW, trunk_kp(i));
     add(bf(W.bott), kW, kW, kW);
-    add(bf(W.hd0), kW, kW, kW);
-    for (int i = 0; i < 3; ++i) add(bf(W.tr[i]), kHid, kHid, kHid);
+    if (!vanilla) {
+      add(bf(W.hd0), kW, kW, kW);
+      for (int i = 0; i < 3; ++i) add(bf(W.tr[i]), kHid, kHid, kHid);
+    } else {
+      for (int kb = 0; kb < 4; ++kb) J.j[n++] = PackJob{bf(W.hd0), kW + kDirEnc, 0, 128, kb * 64};   // rgb hidden [128, 256 | dir 32]
+      zeros(4 + 3 * 2);
+    }
     if (n != kFwdBlocks) { set_error("fused_prepare: forward block count %d != %d", n, kFwdBlocks); return EONERF_EINVAL; }
     J.n = n;
     pack_blocks_kernel<<<n * 4, 256, 0, s>>>(J, ext + F.fblob);
@@ -568,8 +613,18 @@ int fused_prepare(const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
           J.j[n++] = PackJob{src, ld, row0 + h * 128, rr, kb * 64};
         }
     };
-    for (int i = 2; i >= 0; --i) add(bf(W.tr_t[i]), kHid, 0, kHid, kHid);      // S0..S2
-    add(bf(W.hd0_t), 2 * kHid, 0, kW, 2 * kHid);                               // S3
+    auto zeros = [&](int count) { for (int i = 0; i < count; ++i) J.j[n++] = PackJob{bf(W.w[0]), 64, 0, 0, 0}; };
+    if (!vanilla) {
+      for (int i = 2; i >= 0; --i) add(bf(W.tr_t[i]), kHid, 0, kHid, kHid);      // S0..S2
+      add(bf(W.hd0_t), 2 * kHid, 0, kW, 2 * kHid);                               // S3
+    } else {
+      zeros(3 * 2);                                                              // S0..S2: no transient branch
+      for (int h = 0; h < 2; ++h)                                                // S3: W_rgb0[:, :256]^T = [256 in, 128 out | 128 zero]
+        for (int kb = 0; kb < 4; ++kb) {
+          if (kb < 2) J.j[n++] = PackJob{bf(W.hd0_t), kHid, h * 128, 128, kb * 64};
+          else zeros(1);
+        }
+    }
     add(bf(W.bott_t), kW, 0, kW, kW);                                          // S4
     add(bf(W.wt[7]), kW, 0, kW, kW);                                           // S5
     add(bf(W.wt[6]), kW, 0, kW, kW);                                           // S6
@@ -585,22 +640,31 @@ int fused_prepare(const EonerfFieldParams* p, void* prepared, cudaStream_t s) {
   ConstSrc c{};
   for (int i = 0; i < 8; ++i) c.bt[i] = p->trunk_b[i];
   c.bb = p->bott_b;
-  for (int i = 0; i < 3; ++i) c.btr[i] = p->trans_b[i + 1];
-  c.ws = p->sigma_w; c.wa = p->head1_w; c.wts = p->ts_w; c.wtb = p->tb_w;
-  c.bs = p->sigma_b; c.ba = p->head1_b; c.bts = p->ts_b; c.btb = p->tb_b;
-  c.bh0 = p->head0_b; c.bt0 = p->trans_b[0];
+  c.ws = p->sigma_w; c.wa = p->head1_w; c.bs = p->sigma_b; c.ba = p->head1_b; c.bh0 = p->head0_b;
+  if (!vanilla) {
+    for (int i = 0; i < 3; ++i) c.btr[i] = p->trans_b[i + 1];
+    c.wts = p->ts_w; c.wtb = p->tb_w; c.bts = p->ts_b; c.btb = p->tb_b; c.bt0 = p->trans_b[0];
+  } else {
+    // no transient branch: its constants read a zeroed 128-float row (the unused per-image table of the extras)
+    float* z = (float*)(ext + F.delta);
+    EO_CUDA(cudaMemsetAsync(z, 0, kHid * sizeof(float), s));
+    for (int i = 0; i < 3; ++i) c.btr[i] = z;
+    c.wts = z; c.wtb = z; c.bts = z; c.btb = z; c.bt0 = z;
+  }
   pack_consts_kernel<<<div_up(kCFloats, 256), 256, 0, s>>>(c, (float*)(ext + F.consts));
   EO_LAUNCH_CHECK();
-  class_delta_kernel<<<div_up(p->n_images * kHid, 128), 128, 0, s>>>(p->trans_w[0], p->transient_emb, p->n_images, (float*)(ext + F.delta));
-  EO_LAUNCH_CHECK();
+  if (!vanilla) {
+    class_delta_kernel<<<div_up(p->n_images * kHid, 128), 128, 0, s>>>(p->trans_w[0], p->transient_emb, p->n_images, (float*)(ext + F.delta));
+    EO_LAUNCH_CHECK();
+  }
   return EONERF_OK;
 }
 
 int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
-  EO_REQUIRE(a->field == EONERF_FIELD_EONERF, "fused precision mode supports the EO-NeRF field only");
+  const bool vanilla = a->field == EONERF_FIELD_VANILLA;
   const int64_t N = a->n_pts;
   const EonerfFieldParams* prm = a->params;
-  const PrepLayout W = prep_layout(EONERF_FIELD_EONERF, EONERF_PREC_BF16, prm->n_images);
+  const PrepLayout W = prep_layout(a->field, EONERF_PREC_BF16, prm->n_images);
   const FusedPrepLayout F = fused_prep_layout(prm->n_images);
   const uint8_t* ext = (const uint8_t*)a->prepared + W.total;
   const bool train = a->stash != nullptr;
@@ -608,7 +672,15 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   p.M = N;
   p.M_dev = a->n_pts_dev;
   p.n_tiles = (N + kTileM - 1) / kTileM;
-  p.n_stages = a->density_only ? 8 : kFwdStages;
+  p.n_stages = a->density_only ? 8 : (vanilla ? 10 : kFwdStages);
+  p.vanilla = vanilla;
+  if (vanilla && !a->density_only) {
+    EO_REQUIRE(a->cond_dirs && a->dir_bias && a->n_cond > 0, "field_fwd: the fused vanilla field needs cond_dirs, dir_bias and n_cond");
+    EO_REQUIRE(!a->cond_dirs_per_ray || a->ray_indices, "field_fwd: cond_dirs_per_ray needs ray_indices");
+    p.cls_mode = a->cond_dirs_per_ray ? 1 : 2;
+    vanilla_dir_bias_kernel<<<(unsigned)a->n_cond, 128, 0, s>>>(a->cond_dirs, a->cond_dirs_stride, a->n_cond, prm->head0_w, a->dir_bias);
+    EO_LAUNCH_CHECK();
+  }
   p.training = train;
   if (const char* dbg = getenv("EONERF_FUSED_DBG")) p.training |= atoi(dbg);   // experiment knobs: 2 = skip stash stores, 4 = skip masks, 8 = skip the accumulator drain, 16 = skip the weight loads
   p.x = a->x;
@@ -616,7 +688,7 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   p.ray_indices = a->ray_indices; p.t_starts = a->t_starts; p.t_ends = a->t_ends; p.z_mid = a->z_mid;
   p.img_idx = a->density_only ? nullptr : a->img_idx; p.img_stride = a->img_idx_stride;
   p.wblob = ext + F.fblob; p.consts = (const float*)(ext + F.consts);
-  p.class_delta = (const float*)(ext + F.delta);
+  p.class_delta = vanilla ? (a->density_only ? nullptr : a->dir_bias) : (const float*)(ext + F.delta);
   p.prog = fwd_program(p.n_stages);
   if (train) {
     const FusedStashLayout S = fused_stash_layout(N, a->density_only);
@@ -630,7 +702,7 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   const int mode = fused_cta_group();
   const int csz = mode == 1 ? 1 : (mode == 14 ? 4 : 2);
   const int n_ctas = fused_ctas(p.n_tiles, csz);
-  const double flops = (double)N * (a->density_only ? 982528.0 : 1345280.0);
+  const double flops = (double)N * (a->density_only ? 982528.0 : (vanilla ? 1186816.0 : 1345280.0));
   int rc = EONERF_OK;
   CUtensorMap wmap;
   if ((rc = make_blob_map(&wmap, p.wblob, kFwdBlocks)) != EONERF_OK) return rc;

@@ -63,6 +63,7 @@ struct FusedBwdParams {
   const int64_t* M_dev;          // live sample count on the device (M, n_tiles are then capacities)
   int n_prog; int8_t prog[kBwdStages];
   int density_only;
+  int vanilla;         // vanilla field: sigma = relu(.) (mlp.py:243,250), no transient branch (the chain starts at the HD0 stage)
   const uint8_t* wblob; const float* consts;
   MmaProgram mma;      // MMA side of prog[]
   const uint32_t* mask[kNumMask];
@@ -185,7 +186,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
         float dsig = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, dts = 0.f, dtb = 0.f;
         if (valid) {
           // derivatives through the forward outputs: softplus' = 1 - exp(-y), sigmoid' = y (1 - y)
-          if (p.g_sigma) dsig = __ldg(p.g_sigma + pt) * (-expm1f(-__ldg(p.sigma + pt)));
+          if (p.g_sigma) {
+            const float y = __ldg(p.sigma + pt);
+            dsig = __ldg(p.g_sigma + pt) * (p.vanilla ? (y > 0.f ? 1.0f : 0.f) : -expm1f(-y));
+          }
           if (!p.density_only) {
             if (p.g_rgb) {
               const float y0 = __ldg(p.rgb + 3 * pt), y1 = __ldg(p.rgb + 3 * pt + 1), y2 = __ldg(p.rgb + 3 * pt + 2);
@@ -624,6 +628,60 @@ static int run_heads_dw_blocked(const uint8_t* X, int nb, int chunk0, int K, int
 // grouped dW GEMM: they run on a side stream, forked after the chain and joined after the GEMM, so they overlap it (all of them
 // are HBM readers that do not saturate the bus on their own).  Fork and join are event edges, which a stream capture turns into
 // graph dependencies.  One side stream + two events per device, created on first use; EONERF_SIDE_STREAM=0 keeps one stream.
+// Vanilla field: gradient of the view-direction columns of rgb_layer.hidden_layers.0,
+//   dW[j, 256 + e] += sum_m G_HD0[m, j] enc4(dir_{cls(m)})[e]      (j < 128, e < 27; G in the blocked layout, first two blocks of four)
+// Persistent CTAs: each one sums its tiles in registers (thread t: output row j = t & 127, 14 of the 27 columns), then adds once.
+__global__ void __launch_bounds__(256) vanilla_dir_grad_kernel(const uint8_t* __restrict__ G, const int32_t* __restrict__ cls, int64_t M, int64_t n_tiles,
+                                                               const float* __restrict__ dirs, int64_t stride, int64_t n_cond, float* __restrict__ dw,
+                                                               const int64_t* __restrict__ M_dev) {
+  __shared__ float enc[128][28];
+  __shared__ __align__(16) uint8_t gt[2 * kBlkBytes];
+  if (M_dev) { M = __ldg(M_dev); n_tiles = (M + kTileM - 1) / kTileM; }
+  const int t = threadIdx.x, j = t & 127, e0 = (t >> 7) * 14, ne = (t >> 7) ? 13 : 14;
+  float acc[14];
+#pragma unroll
+  for (int e = 0; e < 14; ++e) acc[e] = 0.f;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();
+    // the tile's G blocks 0, 1 (columns 0..127) as they lie in memory (swizzled images), 32 KB
+    const uint4* src = (const uint4*)(G + (size_t)tile * 4 * kBlkBytes);
+    for (int i = t; i < 2 * kBlkBytes / 16; i += 256) ((uint4*)gt)[i] = __ldg(src + i);
+    // enc4 of every sample's direction
+    for (int i = t; i < 128 * 27; i += 256) {
+      const int m = i / 27, c = i % 27;
+      const int64_t pt = tile * kTileM + m;
+      float v = 0.f;
+      if (pt < M) {
+        int64_t row = __ldg(cls + pt);
+        if (row < 0 || row >= n_cond) row = 0;
+        const float* d = dirs + row * stride;
+        if (c < 3) v = __ldg(d + c);
+        else {
+          int e = c - 3;
+          const int half = e >= 12;
+          e -= half * 12;
+          const float xb = __ldg(d + e % 3) * (float)(1 << (e / 3));
+          v = sinf(half ? __fadd_rn(xb, kHalfPi) : xb);
+        }
+      }
+      enc[m][c] = v;
+    }
+    __syncthreads();
+    // column j of sample m: block j >> 6, 16-byte chunk (j & 63) >> 3, element j & 7
+    const int blk = j >> 6, ch = (j & 63) >> 3, el = j & 7;
+    for (int m = 0; m < 128; ++m) {
+      const __nv_bfloat16* row = (const __nv_bfloat16*)(gt + blk * kBlkBytes + m * 128 + ((ch ^ (m & 7)) << 4));
+      const float g = __bfloat162float(row[el]);
+#pragma unroll
+      for (int e = 0; e < 14; ++e)
+        if (e < ne) acc[e] = fmaf(g, enc[m][e0 + e], acc[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 14; ++e)
+    if (e < ne) atomicAdd(dw + (int64_t)j * 283 + 256 + e0 + e, acc[e]);
+}
+
 struct SideStream { int dev = -1; cudaStream_t owner = nullptr; cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
 // One side stream + event pair per (host thread, device, caller stream): two host threads, or one thread driving two streams,
 // never share (and re-record) the same events.  thread_local => no locking; entries live as long as the thread.
@@ -676,11 +734,11 @@ struct SideFork {
 };
 
 int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
-  EO_REQUIRE(a->field == EONERF_FIELD_EONERF, "fused precision mode supports the EO-NeRF field only");
+  const bool vanilla = a->field == EONERF_FIELD_VANILLA;
   const int64_t N = a->n_pts;
   const EonerfFieldParams* prm = a->params;
   const EonerfFieldParams* G = a->grads;
-  const PrepLayout W = prep_layout(EONERF_FIELD_EONERF, EONERF_PREC_BF16, prm->n_images);
+  const PrepLayout W = prep_layout(a->field, EONERF_PREC_BF16, prm->n_images);
   const FusedPrepLayout F = fused_prep_layout(prm->n_images);
   const uint8_t* ext = (const uint8_t*)a->prepared + W.total;
   const FusedStashLayout S = fused_stash_layout(N, a->density_only);
@@ -690,7 +748,7 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   const bool want_x = a->g_x != nullptr;
 
   FusedBwdParams p{};
-  p.M = N; p.n_tiles = S.n_tiles; p.M_dev = a->n_pts_dev; p.density_only = a->density_only;
+  p.M = N; p.n_tiles = S.n_tiles; p.M_dev = a->n_pts_dev; p.density_only = a->density_only; p.vanilla = vanilla;
   p.wblob = ext + F.bblob; p.consts = (const float*)(ext + F.consts);
   {
     static const int8_t halves[kBwdStages] = {1, 1, 1, 2, 2, 2, 2, 1, 2, 2, 2, 2, 2, 1};
@@ -701,7 +759,7 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
     int o = 0;
     for (int i = 0; i < kBwdStages; ++i) { blk_off[i] = o; o += kBwdBlkCount[i]; }
     int n = 0;
-    for (int i = a->density_only ? 5 : 0; i < kBwdStages; ++i) {
+    for (int i = a->density_only ? 5 : (vanilla ? 2 : 0); i < kBwdStages; ++i) {   // vanilla: stage 2 = HD0 (its transient half stays zero)
       if ((i == 7 || i == 13) && !want_x) continue;
       p.mma.st[n].halves = halves[i]; p.mma.st[n].nkb = nkb[i]; p.mma.st[n].blk_off = blk_off[i];
       for (int k = 0; k < 4; ++k) p.mma.st[n].a[k] = ablk[i][k];
@@ -720,7 +778,7 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   const int mode = fused_cta_group();
   const int csz = mode == 1 ? 1 : (mode == 14 ? 4 : 2);
   const int n_ctas = fused_ctas(p.n_tiles, csz);
-  const double flops = (double)N * (a->density_only ? 982528.0 : 1345280.0);
+  const double flops = (double)N * (a->density_only ? 982528.0 : (vanilla ? 1186816.0 : 1345280.0));
   int rc = EONERF_OK;
   CUtensorMap wmap;
   if ((rc = make_blob_map(&wmap, p.wblob, kBwdBlocks)) != EONERF_OK) return rc;
@@ -767,7 +825,20 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   SideFork side(side_stream(s), s);
   EO_TRY(side.fork());
   cudaStream_t hs = side.stream();                          // stream of the head / per-image gradient kernels
-  if (!a->density_only) {
+  if (!a->density_only && vanilla) {
+    // rgb_layer.hidden_layers.0[:, :256] : G_HD0[:, :128]^T BOTT;  [:, 256:283] : G_HD0[:, :128]^T enc4(dir) (per-class sums)
+    EO_REQUIRE(a->cond_dirs && a->n_cond > 0, "field_bwd: the fused vanilla field needs the forward call's cond_dirs / n_cond");
+    EO_TRY(dW(garr(9), 4, 0, 1, sarr(8), 4, 0, 4, kW, G->head0_w, kW + 27, G->head0_b, nullptr, 0, nullptr));
+    EO_TRY(dW(garr(8), 4, 0, 2, sarr(7), 4, 0, 4, kW, G->bott_w, kW, G->bott_b, G->bott_w + (int64_t)kHid * kW, kW, G->bott_b + kHid));
+    HeadGradsB ha{{G->head1_w, G->head1_w + kHid, G->head1_w + 2 * kHid}, {G->head1_b, G->head1_b + 1, G->head1_b + 2}};
+    EO_TRY(run_heads_dw_blocked<3>(sarr(9), 4, 0, kHid, N, dpre, 1, ha, hs, a->n_pts_dev));
+    int64_t blocks = 2 * 148;
+    if (blocks > S.n_tiles) blocks = S.n_tiles;
+    vanilla_dir_grad_kernel<<<(unsigned)blocks, 256, 0, hs>>>(garr(9), (const int32_t*)(st + S.cls), N, S.n_tiles, a->cond_dirs, a->cond_dirs_stride,
+                                                              a->n_cond, G->head0_w, a->n_pts_dev);
+    EO_LAUNCH_CHECK();
+  }
+  if (!a->density_only && !vanilla) {
     // transient_mlp.3 / .2 / .1 : G_T3^T T2, G_T2^T T1, G_T1^T HD0[:,128:256]
     EO_TRY(dW(garr(12), 2, 0, 1, sarr(11), 2, 0, 2, kHid, G->trans_w[3], kHid, G->trans_b[3], nullptr, 0, nullptr));
     EO_TRY(dW(garr(11), 2, 0, 1, sarr(10), 2, 0, 2, kHid, G->trans_w[2], kHid, G->trans_b[2], nullptr, 0, nullptr));

@@ -91,7 +91,7 @@ int64_t fused_prepared_extra_bytes(int64_t n_images);
 int64_t fused_stash_bytes(int64_t n_pts, int density_only);
 int64_t fused_scratch_bytes(int64_t n_pts, int64_t n_images, int density_only);
 // `prepared` is the layered bf16 blob (PrepLayout) followed by the fused extras at PrepLayout::total
-int fused_prepare(const EonerfFieldParams* p, void* prepared, cudaStream_t s);
+int fused_prepare(int field, const EonerfFieldParams* p, void* prepared, cudaStream_t s);
 int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s);
 int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s);
 

@@ -436,6 +436,11 @@ class FieldEngine:
             cd, cs_ = _rows(cond_dirs)
             a.cond_dirs, a.cond_dirs_stride, a.cond_dirs_per_ray = _p(cd), cs_, int(bool(cond_dirs_per_ray))
             keep.append(cd)
+            if self.precision == K.PREC_BF16_FUSED and not density_only:
+                # the view-direction term of the rgb hidden layer as one bias row per conditioning row (csrc/field_fused.cu)
+                out["dir_bias"] = f32(cd.shape[0], 128)
+                a.dir_bias, a.n_cond = _p(out["dir_bias"]), cd.shape[0]
+                out["cond"] = (cd, cs_)
         a.density_only, a.stash, a.sigma = int(density_only), _p(out["stash"]), _p(out["sigma"])
         a.n_pts_dev = _p(n_dev)
         if not density_only:
@@ -464,6 +469,9 @@ class FieldEngine:
             a.grads = C.pointer(grads_struct)
         a.g_x = _p(gx)
         a.n_pts_dev = _p(n_dev)
+        if fwd_out.get("cond") is not None:
+            cd, cs_ = fwd_out["cond"]
+            a.cond_dirs, a.cond_dirs_stride, a.n_cond = _p(cd), cs_, cd.shape[0]
         K.call("field_bwd", a, _stream())
         return gx
 

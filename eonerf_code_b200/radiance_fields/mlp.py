@@ -73,7 +73,9 @@ class NerfMLP(nn.Module):
 
 
 class VanillaNeRFRadianceField(nn.Module, _EngineMixin):
-    """mlp.py:211-250.  forward(x, condition) -> (rgb[N,3], sigma[N,1]); query_density(x) -> [N,1]."""
+    """mlp.py:211-250.  forward(x, condition) -> (rgb[N,3], sigma[N,1]); query_density(x) -> [N,1].
+    precision: "bf16_fused" runs the first ten stages of the fused tcgen05 program (trunk, sigma head, bottleneck, rgb hidden layer
+    with the view-direction term as a per-row bias, rgb head); "bf16" the layer-by-layer tcgen05 GEMMs; "fp32" the exactness mode."""
     _field_kind = K.FIELD_VANILLA
 
     def __init__(self, net_depth=8, net_width=256, skip_layer=4, net_depth_condition=1, net_width_condition=128,

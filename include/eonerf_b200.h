@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONERF_ABI_VERSION 15
+#define EONERF_ABI_VERSION 16
 
 #define EONERF_OK 0
 #define EONERF_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -308,6 +308,11 @@ typedef struct {
    * *n_pts_dev (<= n_pts); n_pts is then the capacity every buffer (stash included) is sized for, and rows >= *n_pts_dev
    * of the outputs are left untouched.  Lets a whole training step run without a host read of P (CUDA-graph capture). */
   const int64_t* n_pts_dev;
+  /* Vanilla field in the fused mode: the view-direction term of rgb_layer.hidden_layers.0 (mlp.py:153-165: columns 256:283 of
+   * its weight times enc4(dir)) enters the fused program as a bias row per conditioning row.  dir_bias = caller-provided
+   * scratch [n_cond,128] fp32 (written by this call, read again by eonerf_field_bwd's caller only through the stash);
+   * n_cond = rows of cond_dirs (rays when cond_dirs_per_ray, else samples). */
+  float* dir_bias; int64_t n_cond;
 } EonerfFieldFwdArgs;
 int eonerf_field_fwd(const EonerfFieldFwdArgs* a, eonerf_stream_t stream);
 
@@ -324,6 +329,7 @@ typedef struct {
   const EonerfFieldParams* grads;  /* fp32 gradients, same shapes as params, ACCUMULATED into; NULL: skip parameter gradients */
   float* g_x;                      /* [N,3] gradient wrt positions, or NULL */
   const int64_t* n_pts_dev;        /* as in EonerfFieldFwdArgs (must match the forward call) */
+  const float* cond_dirs; int64_t cond_dirs_stride; int64_t n_cond;   /* vanilla field, fused mode: the forward call's cond_dirs */
 } EonerfFieldBwdArgs;
 int eonerf_field_bwd(const EonerfFieldBwdArgs* a, eonerf_stream_t stream);
 

@@ -20,7 +20,7 @@ def _model(p, cuda, precision):
     return m.to(cuda)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16_fused"])
 def test_vanilla_field_golden(cuda, golden, precision):
     g = golden["vanilla"]
     p = O.init_vanilla_params(seed=int(g["seed"]), bias_scale=float(g["bias_scale"]))
@@ -62,7 +62,7 @@ def test_march_aabb_bit_exact_vs_oracle(cuda, jittered):
     assert float(x.abs().max()) <= 1.5 + 1e-3                                          # every sample inside the box
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16_fused"])
 def test_vanilla_render_vs_oracle(cuda, precision):
     """render_image_with_occgrid (train_mlp_nerf.py:162-170 signature) forward + smooth-L1 backward vs the oracle."""
     from eonerf_code_b200.datasets.synthetic import make_pinhole_rays
@@ -99,3 +99,52 @@ def test_vanilla_render_vs_oracle(cuda, precision):
         a2 = render_image_with_occgrid(m, est, Rays(o.to(cuda).view(4, B // 4, 3), d.to(cuda).view(4, B // 4, 3)), render_step_size=step, test_chunk_size=40)
     assert a2[0].shape == (4, B // 4, 3) and a1[3] == a2[3]
     close(a2[0].reshape(B, 3), a1[0], 1e-6, 1e-7)
+
+
+def _l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+@pytest.mark.parametrize("n,per_ray", [(300, False), (5000, False), (4099, True)])
+def test_vanilla_fused_matches_layered(cuda, n, per_ray):
+    """The fused tcgen05 program of the vanilla field (first ten stages of the EO-NeRF program, view-direction term as a per-row
+    bias) vs the layer-by-layer bf16 kernels and the fp32 kernels: outputs, every parameter gradient incl. the view-direction
+    columns 256:283 of rgb_layer.hidden_layers.0, with per-sample directions (forward(x, dirs)) and per-ray directions (the
+    renderer's form)."""
+    from eonerf_code_b200 import ops
+    p = O.init_vanilla_params(seed=9, bias_scale=0.1)
+    g = torch.Generator().manual_seed(n)
+    res = {}
+    if per_ray:
+        B = 37
+        o = (torch.rand(B, 3, generator=g) * 2 - 1).to(cuda)
+        d = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=1).to(cuda)
+        ri = torch.sort(torch.randint(0, B, (n,), generator=g))[0].to(cuda)
+        ts = (torch.rand(n, generator=g) * 0.5).to(cuda)
+        te = ts + 0.01
+    else:
+        x = (torch.rand(n, 3, generator=g) * 3 - 1.5).to(cuda)
+        d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=1).to(cuda)
+    g_rgb, g_sig = torch.randn(n, 3, generator=g).to(cuda), torch.randn(n, 1, generator=g).to(cuda)
+    for prec in ("fp32", "bf16", "bf16_fused"):
+        m = _model(p, cuda, prec)
+        if per_ray:
+            e = m._engine()
+            sig, rgb, _ = ops._VanillaRaysFn.apply(True, e, o, d, ri, ts, te, *e.tensors())
+        else:
+            rgb, sig = m(x, d)
+        ((rgb * g_rgb).sum() + (sig * g_sig).sum()).backward()
+        res[prec] = (rgb.detach(), sig.detach(), {k: v.grad.clone() for k, v in m.named_parameters()})
+    for a, b in ((res["bf16_fused"][0], res["bf16"][0]), (res["bf16_fused"][1], res["bf16"][1])):
+        assert float((a - b).abs().max()) <= 3e-3 * max(1.0, float(b.abs().max()))
+    assert float((res["bf16_fused"][0] - res["fp32"][0]).abs().max()) <= 4e-3
+    for k in res["fp32"][2]:
+        d_layer, d_fused = _l2(res["bf16"][2][k], res["fp32"][2][k]), _l2(res["bf16_fused"][2][k], res["fp32"][2][k])
+        assert torch.isfinite(res["bf16_fused"][2][k]).all(), k
+        assert d_fused <= 1.25 * d_layer + 1e-2, (k, d_fused, d_layer)
+    # the view-direction columns specifically (they take a separate kernel in the fused mode)
+    k = "mlp.rgb_layer.hidden_layers.0.weight"
+    d_layer = _l2(res["bf16"][2][k][:, 256:], res["fp32"][2][k][:, 256:])
+    d_fused = _l2(res["bf16_fused"][2][k][:, 256:], res["fp32"][2][k][:, 256:])
+    assert d_fused <= 1.25 * d_layer + 1e-2 and d_fused <= 6e-2, (d_fused, d_layer)

@@ -169,29 +169,41 @@ def render_arm(args, model, rank, world, dev, barrier, max_over_ranks):
     from eonerf_code_b200 import sat_rendering
     from eonerf_code_b200.datasets.satellite import define_satrays_from_tensors, get_utmalt_from_nerf_prediction
     from eonerf_code_b200.datasets.synthetic import make_rays
-    from eonerf_code_b200.parallel import gather_rows, shard_bounds
+    from eonerf_code_b200.parallel import ChunkQueue, guided_chunks, reduce_disjoint
     import torch.distributed as dist
-    r0, r1 = shard_bounds(RENDER_HW, rank, world)
-    rays, ts, _ = make_rays((r1 - r0) * RENDER_HW, N_IMAGES, seed=7 + rank, eval_mode=True)
+    # every rank holds the ray table of the whole image (46 MB) and pulls 8-row chunks (8192 rays) from a shared queue: faster
+    # GPUs render more chunks (parallel.ChunkQueue); the image is assembled on rank 0 by one sum-reduce of disjoint row blocks
+    rays, ts, _ = make_rays(RENDER_HW * RENDER_HW, N_IMAGES, seed=7, eval_mode=True)
     rays, ts = rays.to(dev), ts.to(dev)
+    rows_per_chunk = RENDER_CHUNK // RENDER_HW
+    chunks = ([(r, r + rows_per_chunk) for r in range(0, RENDER_HW, rows_per_chunk)] if world == 1
+              else guided_chunks(RENDER_HW, world))          # N > 1: large chunks first, 8-row chunks at the tail
+    n_chunks = len(chunks)
     model.eval()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    full = torch.empty(RENDER_HW, RENDER_HW, 6, dtype=torch.float32, device=dev) if rank == 0 else None
+    full = torch.zeros(RENDER_HW, RENDER_HW, 6, dtype=torch.float32, device=dev)
     host = torch.empty(RENDER_HW, RENDER_HW, 6, dtype=torch.float32).pin_memory() if rank == 0 else None
-    n_samples, counters = 0, {}
+    n_samples, n_sun, n_mine = 0, 0, 0
     runs = []
     with torch.no_grad():
         for it in range(3):
             counters = {}
+            n_samples, n_mine = 0, 0
+            if world > 1:
+                full.zero_()
             barrier()
             ev[0].record()
-            res, n_samples = sat_rendering.render_image(model, None, define_satrays_from_tensors(rays, ts), None, None,
-                                                        epoch_idx=EPOCH_IDX, chunk=RENDER_CHUNK, render_step_size=2.0 / N_SAMPLES, eval=True,
-                                                        static=args.precision == "bf16_fused", counters=counters)   # sync-free: counts stay on the device
-            alt = get_utmalt_from_nerf_prediction(rays, res["depth"], SCENE_SCALE, SCENE_OFFSET, want_alt_f32=True)[3]
-            out = torch.cat([res["rgb"], res["geo_shadows"], res["depth"], alt[:, None]], dim=1).view(r1 - r0, RENDER_HW, 6)
+            for c in ChunkQueue(n_chunks, world):
+                a0, a1 = chunks[c][0] * RENDER_HW, chunks[c][1] * RENDER_HW
+                res, ns = sat_rendering.render_image(model, None, define_satrays_from_tensors(rays[a0:a1], ts[a0:a1]), None, None,
+                                                     epoch_idx=EPOCH_IDX, chunk=RENDER_CHUNK, render_step_size=2.0 / N_SAMPLES, eval=True,
+                                                     static=args.precision == "bf16_fused", counters=counters)   # sync-free: counts stay on the device
+                alt = get_utmalt_from_nerf_prediction(rays[a0:a1], res["depth"], SCENE_SCALE, SCENE_OFFSET, want_alt_f32=True)[3]
+                torch.cat([res["rgb"], res["geo_shadows"], res["depth"], alt[:, None]], dim=1, out=full.view(-1, 6)[a0:a1])
+                n_samples = n_samples + ns
+                n_mine += 1
             ev[1].record()
-            img = gather_rows(out, world, n_total=RENDER_HW, out=full)
+            img = reduce_disjoint(full, world)
             ev[2].record()
             if rank == 0:
                 host.copy_(img, non_blocking=True)
@@ -199,6 +211,7 @@ def render_arm(args, model, rank, world, dev, barrier, max_over_ranks):
             barrier()
             if it > 0:
                 runs.append((ev[0].elapsed_time(ev[1]), ev[0].elapsed_time(ev[2]), ev[0].elapsed_time(ev[3])))
+            n_sun = counters.get("n_sun_samples", 0)
     ms_render = min(r[0] for r in runs)
     ms = max_over_ranks(min(r[1] for r in runs))
     ms_e2e = max_over_ranks(min(r[2] for r in runs))
@@ -208,13 +221,20 @@ def render_arm(args, model, rank, world, dev, barrier, max_over_ranks):
         dist.all_gather(lst, per_rank)
         per_rank = torch.cat(lst)
     model.train()
-    n_sun = counters.get("n_sun_samples", 0)
+    chunks_per_rank = torch.tensor([float(n_mine)], dtype=torch.float64, device=dev)
+    if world > 1:
+        lst = [torch.zeros_like(chunks_per_rank) for _ in range(world)]
+        dist.all_gather(lst, chunks_per_rank)
+        chunks_per_rank = torch.cat(lst)
     return {"metric": "render_rays_per_sec", "value": RENDER_HW * RENDER_HW / (ms * 1e-3), "unit": "rays/s", "ms_per_image": ms,
             "e2e": {"value": RENDER_HW * RENDER_HW / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_image": ms_e2e,
                     "d2h_bytes_per_image": RENDER_HW * RENDER_HW * 6 * 4, "note": "gathered [H,W,6] image copied to pinned host memory inside the timed region"},
             "render_ms_per_rank": [round(float(x), 3) for x in per_rank.tolist()],
+            "chunks_per_rank": [int(x) for x in chunks_per_rank.tolist()],
             "workload": f"BASELINE configs[3]: {RENDER_HW}x{RENDER_HW} eval render (rgb + geo_shadows + depth + altitude), n_samples={N_SAMPLES}, "
-                        f"{RENDER_CHUNK}-ray chunks, rows sharded over {world} GPU(s), gathered on rank 0 (pre-sized batched P2P)",
+                        + (f"{RENDER_CHUNK}-ray chunks on one GPU" if world == 1 else
+                           f"{n_chunks} chunks of {chunks[0][1] - chunks[0][0]}..{chunks[-1][1] - chunks[-1][0]} rows (large first) pulled from a shared queue by "
+                           f"{world} GPUs (dynamic balancing), assembled on rank 0 by one sum-reduce"),
             "kept_camera_samples_rank0": int(n_samples), "kept_sun_samples_rank0": int(n_sun)}
 
 

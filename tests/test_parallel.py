@@ -50,6 +50,17 @@ def _worker(rank, world, port, out):
     assert (uneven is None) == (rank != 0)
     if rank == 0:
         assert uneven.data_ptr() == buf.data_ptr() and torch.equal(uneven, torch.arange(7.0)[:, None].repeat(1, 3) + 0.5)
+    # dynamic chunk queue: every chunk index is handed out exactly once across the ranks; one sum-reduce assembles the result
+    mine = list(parallel.ChunkQueue(11, world))
+    img = torch.zeros(11, 2)
+    for c in mine:
+        img[c] = c + 1.0
+    img = parallel.reduce_disjoint(img, world)
+    got = [None] * world
+    dist.all_gather_object(got, mine)
+    assert sorted(sum(got, [])) == list(range(11))
+    if rank == 0:
+        assert torch.equal(img, (torch.arange(11.0) + 1)[:, None].repeat(1, 2))
     if rank == 0:       # per-parameter views (the flat buffer pads every tensor to a 16-byte boundary)
         torch.save({"grad": torch.cat([q.grad.reshape(-1) for q in params]), "rows": rows, "bounds": (b, e),
                     "flat_numel": flat.flat.numel(), "offsets": flat.offsets}, out)
@@ -91,3 +102,11 @@ def test_shard_bounds_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def test_guided_chunks_cover_the_rows_once():
+    from eonerf_code_b200.parallel import guided_chunks
+    for n, w in ((1024, 1), (1024, 8), (1000, 3), (17, 4)):
+        c = guided_chunks(n, w)
+        assert c[0][0] == 0 and c[-1][1] == n and all(a[1] == b[0] for a, b in zip(c, c[1:]))
+        assert c[0][1] - c[0][0] >= c[-1][1] - c[-1][0]

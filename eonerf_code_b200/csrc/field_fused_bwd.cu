@@ -173,34 +173,53 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
     const uint32_t s_hw = smem_u32(hw);
     uint32_t cph = 0;
     uint64_t* const acc_full = B.acc_full;
+    int tr_i = 0; (void)tr_i;
     for (int64_t it = it0; it < n_items; it += it_stride) {
+      EO_TRACE(1, tr_i, threadIdx.x == 64);                 // item start
       // ---- head gradients -> first G of the chain ----
       if (store_id >= 0) tma_store_wait_read<0>();
       named_bar_sync(1, kBarThreads);
+      // Every global load of the prologue (both slots: forward outputs, incoming gradients, ReLU sign words) is issued before
+      // the first dependent instruction: one memory round trip instead of ~8 per slot (the measured per-item prologue was
+      // 14 k cycles of a 100 k-cycle item, profiles/r2b_bwd_item_trace_before.log).
+      float in_gs[2], in_s[2], in_gr[2][3], in_r[2][3], in_gts[2], in_ts[2], in_gtb[2], in_tb[2];
+      uint4 in_mw[2];
+#pragma unroll
+      for (int slot = 0; slot < 2; ++slot) {
+        const int64_t pt = (2 * kCl * it + 2 * rank + slot) * kTileM + r;
+        const bool valid = pt < M;
+        in_gs[slot] = (valid && p.g_sigma) ? __ldg(p.g_sigma + pt) : 0.f;
+        in_s[slot] = valid ? __ldg(p.sigma + pt) : 0.f;
+        const bool full = valid && !p.density_only;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          in_gr[slot][c] = (full && p.g_rgb) ? __ldg(p.g_rgb + 3 * pt + c) : 0.f;
+          in_r[slot][c] = (full && p.g_rgb) ? __ldg(p.rgb + 3 * pt + c) : 0.f;
+        }
+        in_gts[slot] = (full && p.g_ts) ? __ldg(p.g_ts + pt) : 0.f;
+        in_ts[slot] = (full && p.g_ts) ? __ldg(p.ts + pt) : 0.f;
+        in_gtb[slot] = (full && p.g_tb) ? __ldg(p.g_tb + pt) : 0.f;
+        in_tb[slot] = (full && p.g_tb) ? __ldg(p.tb + pt) : 0.f;
+        in_mw[slot] = make_uint4(0, 0, 0, 0);
+        if (valid) {
+          if (p.density_only) in_mw[slot] = __ldg((const uint4*)(p.mask[kMaskH0 + 7] + pt * 8 + half * 4));
+          else { const uint2 t2 = __ldg((const uint2*)(p.mask[kMaskT1 + 2] + pt * 8 + half * 2)); in_mw[slot].x = t2.x; in_mw[slot].y = t2.y; }
+        }
+      }
+#pragma unroll
       for (int slot = 0; slot < 2; ++slot) {
         const int64_t tile = 2 * kCl * it + 2 * rank + slot;
         const int64_t pt = tile * kTileM + r;
         const bool valid = pt < M;
         const uint32_t act = smem_u32(smem + kOffSlotL + slot * kSlotBytesL);
         const uint32_t s_row = smem_u32(smem + kOffRows) + (uint32_t)(slot * 128 + r) * 16u;
-        float dsig = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, dts = 0.f, dtb = 0.f;
-        if (valid) {
-          // derivatives through the forward outputs: softplus' = 1 - exp(-y), sigmoid' = y (1 - y)
-          if (p.g_sigma) {
-            const float y = __ldg(p.sigma + pt);
-            dsig = __ldg(p.g_sigma + pt) * (p.vanilla ? (y > 0.f ? 1.0f : 0.f) : -expm1f(-y));
-          }
-          if (!p.density_only) {
-            if (p.g_rgb) {
-              const float y0 = __ldg(p.rgb + 3 * pt), y1 = __ldg(p.rgb + 3 * pt + 1), y2 = __ldg(p.rgb + 3 * pt + 2);
-              d0 = __ldg(p.g_rgb + 3 * pt) * y0 * (1.0f - y0);
-              d1 = __ldg(p.g_rgb + 3 * pt + 1) * y1 * (1.0f - y1);
-              d2 = __ldg(p.g_rgb + 3 * pt + 2) * y2 * (1.0f - y2);
-            }
-            if (p.g_ts) { const float y = __ldg(p.ts + pt); dts = __ldg(p.g_ts + pt) * y * (1.0f - y); }
-            if (p.g_tb) dtb = __ldg(p.g_tb + pt) * (-expm1f(-__ldg(p.tb + pt)));
-          }
-        }
+        // derivatives through the forward outputs: softplus' = 1 - exp(-y) (vanilla: relu'), sigmoid' = y (1 - y)
+        const float dsig = in_gs[slot] * (p.vanilla ? (in_s[slot] > 0.f ? 1.0f : 0.f) : -expm1f(-in_s[slot]));
+        const float d0 = in_gr[slot][0] * in_r[slot][0] * (1.0f - in_r[slot][0]);
+        const float d1 = in_gr[slot][1] * in_r[slot][1] * (1.0f - in_r[slot][1]);
+        const float d2 = in_gr[slot][2] * in_r[slot][2] * (1.0f - in_r[slot][2]);
+        const float dts = in_gts[slot] * in_ts[slot] * (1.0f - in_ts[slot]);
+        const float dtb = in_gtb[slot] * (-expm1f(-in_tb[slot]));
         if (half == 0) {
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_row), "f"(dsig), "f"(d0), "f"(d1), "f"(d2) : "memory");
           if (tile < n_tiles) {                            // rows of the padded tail are zero: they add nothing to dW
@@ -211,8 +230,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
         }
         if (p.density_only) {
           // G_H7 = dsigma (x) w_sigma, masked by H7 > 0: thread covers columns half*128 .. +128
-          uint4 mw = make_uint4(0, 0, 0, 0);
-          if (valid) mw = __ldg((const uint4*)(p.mask[kMaskH0 + 7] + pt * 8 + half * 4));
+          const uint4 mw = in_mw[slot];
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             const uint32_t m = c == 0 ? mw.x : (c == 1 ? mw.y : (c == 2 ? mw.z : mw.w));
@@ -233,8 +251,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           }
         } else {
           // G_T3 = (dts (x) w_ts + dtb (x) w_tb), masked by T3 > 0: thread covers columns half*64 .. +64 -> blocks 0,1
-          uint2 mw = make_uint2(0, 0);
-          if (valid) mw = __ldg((const uint2*)(p.mask[kMaskT1 + 2] + pt * 8 + half * 2));
+          const uint2 mw = make_uint2(in_mw[slot].x, in_mw[slot].y);
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             const uint32_t m = c == 0 ? mw.x : mw.y;
@@ -258,6 +275,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
       }
       fence_proxy_async();
       named_bar_sync(1, kBarThreads);
+      EO_TRACE(1, tr_i, threadIdx.x == 64);                 // prologue done
       if (!kDutyWarp && e == kSignalThread) {
         signal_act_ready<kCG>(B, 0, rank);
         signal_act_ready<kCG>(B, 1, rank);
@@ -892,6 +910,11 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
 }  // namespace eonerf
 
 #ifdef EONERF_TIMING
+extern "C" int eonerf_debug_trace_bwd(long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, eonerf::g_fused_trace, sizeof(long long) * 2048);
+  return 0;
+}
 extern "C" int eonerf_debug_timing_bwd(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, eonerf::g_fused_timing, sizeof(unsigned long long) * 16);

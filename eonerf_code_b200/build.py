@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeonerf_b200.so")
-SOURCES = ["error.cu", "sampling.cu", "render.cu", "gemm_simt.cu", "gemm_tc.cu", "field.cu", "field_fused.cu", "field_fused_bwd.cu", "optim.cu", "evalpost.cu", "march.cu"]
+SOURCES = ["error.cu", "sampling.cu", "render.cu", "gemm_simt.cu", "gemm_tc.cu", "field.cu", "field_fused.cu", "field_fused_ts.cu", "field_fused_bwd.cu", "optim.cu", "evalpost.cu", "march.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v", "-rdc=false"] + os.environ.get("EONERF_EXTRA_NVCC_FLAGS", "").split()

@@ -668,6 +668,7 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   const FusedPrepLayout F = fused_prep_layout(prm->n_images);
   const uint8_t* ext = (const uint8_t*)a->prepared + W.total;
   const bool train = a->stash != nullptr;
+  if (!train && !vanilla && fused_cta_group() == 2 && fused_ts_enabled()) return fused_field_fwd_ts(a, s);   // inference: activations in TMEM
   FusedFwdParams p{};
   p.M = N;
   p.M_dev = a->n_pts_dev;

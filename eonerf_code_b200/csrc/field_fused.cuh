@@ -121,5 +121,7 @@ int gemm_tn_blocked(const GemmTNBlocked& g, cudaStream_t s);
 int gemm_tn_blocked_group(const GemmTNBlocked* list, int n, cudaStream_t s);
 int fused_cta_group();
 int make_blob_map(CUtensorMap* map, const void* base, int64_t n_blocks);
+bool fused_ts_enabled();                                               // field_fused_ts.cu
+int fused_field_fwd_ts(const EonerfFieldFwdArgs* a, cudaStream_t s);
 
 }  // namespace eonerf

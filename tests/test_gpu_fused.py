@@ -69,6 +69,19 @@ def test_fused_forward_matches_layered(cuda, n, density_only):
             assert float(err.max()) <= 2e-3 and float(err.mean()) <= 5e-5, (k, keep, float(err.max()), float(err.mean()))
 
 
+def test_tmem_operand_inference_kernel_matches_layered(cuda):
+    """The opt-in TMEM-operand inference kernel (csrc/field_fused_ts.cu, EONERF_FUSED_TS=1; the switch is read once per process):
+    the forward parity cases above, re-run in a child process with the kernel enabled (keep=False rows go through it)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, EONERF_FUSED_TS="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k", "test_fused_forward_matches_layered or test_fused_forward_golden",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_fused_stash_is_the_blocked_image_of_the_layered_stash(cuda):
     n, n_img = 1000, 5
     p = O.init_params(n_img, seed=4, bias_scale=0.1)

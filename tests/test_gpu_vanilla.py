@@ -148,3 +148,45 @@ def test_vanilla_fused_matches_layered(cuda, n, per_ray):
     d_layer = _l2(res["bf16"][2][k][:, 256:], res["fp32"][2][k][:, 256:])
     d_fused = _l2(res["bf16_fused"][2][k][:, 256:], res["fp32"][2][k][:, 256:])
     assert d_fused <= 1.25 * d_layer + 1e-2 and d_fused <= 6e-2, (d_fused, d_layer)
+
+
+@pytest.mark.parametrize("kind", ["vanilla_rays", "eonerf_field"])
+def test_autograd_nodes_release_their_stash_without_the_cycle_collector(cuda, kind):
+    """The per-sample stash (6 KB per sample) kept for the backward must die with the autograd graph, by reference counting
+    alone: a forward dict holding the very tensors the Function returns closes a cycle (ctx -> dict -> output -> grad_fn ->
+    ctx) and leaks one stash per step until Python's cycle collector happens to run."""
+    import gc
+    from eonerf_code_b200.datasets.synthetic import make_pinhole_rays
+    from eonerf_code_b200.nerfacc_compat import OccGridEstimator
+    from eonerf_code_b200.vanilla_rendering import Rays, render_image_with_occgrid
+    if kind == "vanilla_rays":
+        m = _model(O.init_vanilla_params(seed=7, bias_scale=0.05), cuda, "bf16_fused").train()
+        est = OccGridEstimator(roi_aabb=AABB, resolution=16, levels=1).to(cuda)
+        o, d, px = (v.to(cuda) for v in make_pinhole_rays(256, seed=8))
+
+        def step():
+            rgb = render_image_with_occgrid(m, est, Rays(o, d), near_plane=0.0, render_step_size=1e-2, render_bkgd=torch.ones(3, device=cuda))[0]
+            torch.nn.functional.smooth_l1_loss(rgb, px).backward()
+    else:
+        from helpers import make_model
+        m = make_model(O.init_params(5, seed=3, bias_scale=0.1), 5, cuda, "bf16_fused").train()
+        x = (torch.rand(60000, 3, device=cuda) * 2 - 1)
+        sun = torch.nn.functional.normalize(torch.rand(60000, 3, device=cuda), dim=-1)
+        img = torch.randint(0, 5, (60000, 1), device=cuda)
+
+        def step():
+            outs = m(x, sun, img)
+            sum(v.sum() for v in outs).backward()
+    gc.collect()
+    gc.disable()
+    try:
+        step()
+        torch.cuda.synchronize()
+        base = torch.cuda.memory_allocated()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        grown = torch.cuda.memory_allocated() - base
+    finally:
+        gc.enable()
+    assert grown < 32 * 2**20, f"{grown / 2**20:.0f} MiB still allocated after three more steps"

@@ -648,56 +648,76 @@ static int run_heads_dw_blocked(const uint8_t* X, int nb, int chunk0, int K, int
 // graph dependencies.  One side stream + two events per device, created on first use; EONERF_SIDE_STREAM=0 keeps one stream.
 // Vanilla field: gradient of the view-direction columns of rgb_layer.hidden_layers.0,
 //   dW[j, 256 + e] += sum_m G_HD0[m, j] enc4(dir_{cls(m)})[e]      (j < 128, e < 27; G in the blocked layout, first two blocks of four)
-// Persistent CTAs: each one sums its tiles in registers (thread t: output row j = t & 127, 14 of the 27 columns), then adds once.
+// Samples arrive ray by ray, so a 128-sample tile holds a handful of runs of equal class (per-ray directions: one or two; per-sample
+// directions: 128).  Thread (j, half) sums G[:, j] over each run of its 64 rows and multiplies the run's sum with the run's encoding
+// once: 64 adds + 27 FMAs per run instead of 64 x 27 FMAs.  Persistent CTAs: 27 partial columns per thread in registers, added once.
 __global__ void __launch_bounds__(256) vanilla_dir_grad_kernel(const uint8_t* __restrict__ G, const int32_t* __restrict__ cls, int64_t M, int64_t n_tiles,
                                                                const float* __restrict__ dirs, int64_t stride, int64_t n_cond, float* __restrict__ dw,
                                                                const int64_t* __restrict__ M_dev) {
-  __shared__ float enc[128][28];
+  __shared__ float enc[128][28];                       // rows that start a run only
+  __shared__ int s_cls[128];                           // -1: past the end
   __shared__ __align__(16) uint8_t gt[2 * kBlkBytes];
   if (M_dev) { M = __ldg(M_dev); n_tiles = (M + kTileM - 1) / kTileM; }
-  const int t = threadIdx.x, j = t & 127, e0 = (t >> 7) * 14, ne = (t >> 7) ? 13 : 14;
-  float acc[14];
+  const int t = threadIdx.x, j = t & 127, m0 = (t >> 7) * 64;
+  float acc[27];
 #pragma unroll
-  for (int e = 0; e < 14; ++e) acc[e] = 0.f;
+  for (int e = 0; e < 27; ++e) acc[e] = 0.f;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();
     // the tile's G blocks 0, 1 (columns 0..127) as they lie in memory (swizzled images), 32 KB
     const uint4* src = (const uint4*)(G + (size_t)tile * 4 * kBlkBytes);
     for (int i = t; i < 2 * kBlkBytes / 16; i += 256) ((uint4*)gt)[i] = __ldg(src + i);
-    // enc4 of every sample's direction
-    for (int i = t; i < 128 * 27; i += 256) {
-      const int m = i / 27, c = i % 27;
-      const int64_t pt = tile * kTileM + m;
-      float v = 0.f;
+    if (t < 128) {
+      const int64_t pt = tile * kTileM + t;
+      int c = -1;
       if (pt < M) {
-        int64_t row = __ldg(cls + pt);
-        if (row < 0 || row >= n_cond) row = 0;
-        const float* d = dirs + row * stride;
-        if (c < 3) v = __ldg(d + c);
-        else {
-          int e = c - 3;
-          const int half = e >= 12;
-          e -= half * 12;
-          const float xb = __ldg(d + e % 3) * (float)(1 << (e / 3));
-          v = sinf(half ? __fadd_rn(xb, kHalfPi) : xb);
-        }
+        c = __ldg(cls + pt);
+        if (c < 0 || c >= n_cond) c = 0;
+      }
+      s_cls[t] = c;
+    }
+    __syncthreads();
+    // enc4 of the direction of every row that starts a run (rows 0 and 64 always do: the two thread halves work independently)
+    for (int i = t; i < 128 * 27; i += 256) {
+      const int m = i / 27, c = i - m * 27;
+      const int k = s_cls[m];
+      if (k < 0 || ((m & 63) != 0 && s_cls[m - 1] == k)) continue;
+      const float* d = dirs + (int64_t)k * stride;
+      float v;
+      if (c < 3) v = __ldg(d + c);
+      else {
+        int e = c - 3;
+        const int half = e >= 12;
+        e -= half * 12;
+        const float xb = __ldg(d + e % 3) * (float)(1 << (e / 3));
+        v = sinf(half ? __fadd_rn(xb, kHalfPi) : xb);
       }
       enc[m][c] = v;
     }
     __syncthreads();
     // column j of sample m: block j >> 6, 16-byte chunk (j & 63) >> 3, element j & 7
     const int blk = j >> 6, ch = (j & 63) >> 3, el = j & 7;
-    for (int m = 0; m < 128; ++m) {
-      const __nv_bfloat16* row = (const __nv_bfloat16*)(gt + blk * kBlkBytes + m * 128 + ((ch ^ (m & 7)) << 4));
-      const float g = __bfloat162float(row[el]);
+    int cur = s_cls[m0], start = m0;
+    float run = 0.f;
+    for (int m = m0; m < m0 + 64; ++m) {
+      const int k = s_cls[m];
+      if (k != cur) {
+        if (cur >= 0) {
 #pragma unroll
-      for (int e = 0; e < 14; ++e)
-        if (e < ne) acc[e] = fmaf(g, enc[m][e0 + e], acc[e]);
+          for (int e = 0; e < 27; ++e) acc[e] = fmaf(run, enc[start][e], acc[e]);
+        }
+        cur = k; start = m; run = 0.f;
+      }
+      const __nv_bfloat16* row = (const __nv_bfloat16*)(gt + blk * kBlkBytes + m * 128 + ((ch ^ (m & 7)) << 4));
+      run += __bfloat162float(row[el]);
+    }
+    if (cur >= 0) {
+#pragma unroll
+      for (int e = 0; e < 27; ++e) acc[e] = fmaf(run, enc[start][e], acc[e]);
     }
   }
 #pragma unroll
-  for (int e = 0; e < 14; ++e)
-    if (e < ne) atomicAdd(dw + (int64_t)j * 283 + 256 + e0 + e, acc[e]);
+  for (int e = 0; e < 27; ++e) atomicAdd(dw + (int64_t)j * 283 + 256 + e, acc[e]);
 }
 
 struct SideStream { int dev = -1; cudaStream_t owner = nullptr; cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };

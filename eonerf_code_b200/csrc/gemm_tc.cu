@@ -526,41 +526,55 @@ struct TNBGemm {
   int32_t g_nb, g_blk0, mt_count, x_nb, x_blk0, x_cnt;
   int32_t n_valid[2]; int32_t k_valid;
   float* D[2]; int64_t ldd[2]; float* db[2];
-  int64_t per0;            // boxes per chunk summed over the GEMMs before this one (cost0 = chunks * per0)
+  int32_t cost; int32_t pad_;  // cost units of one chunk of this GEMM (tnb_chunk_cost)
+  int64_t per0;            // cost units per chunk index summed over the GEMMs before this one (cost0 = chunks * per0)
 };
 struct TNBParams {
-  int32_t n; int32_t dbg_skip_tail;
+  int32_t n; int32_t dbg_skip_tail;   // timing experiments (EONERF_TN_DBG): bit 0 no red.global tail, bit 2 no MMAs
   int64_t chunks;          // 64-sample chunks of every GEMM of the group (they share the sample axis)
-  int64_t per_total;       // boxes per chunk summed over the group (total cost = chunks * per_total)
+  int64_t per_total;       // cost units per chunk index summed over the group (total cost = chunks * per_total)
   const int64_t* n_pts_dev;   // live sample count on the device: chunks = 2 * ceil(*n_pts_dev / 128)
   TNBGemm g[kTNGroupMax];
 };
 
-constexpr int kTNBStages = 3;
-constexpr int kTNBStageBytes = 8 * kBoxBytes;
-constexpr int kSmemTNB = kTNBStages * kTNBStageBytes + 1024;
+// The operand ring is 24 boxes (192 KB).  A stage holds one chunk of the CURRENT GEMM, so the stage count follows the chunk size:
+// 8 boxes -> 3 stages, 5 -> 4, 4 -> 6, 3 -> 8.  With a fixed three stages the CTAs that own the narrow GEMMs (4 / 5 boxes per chunk)
+// had 96-120 KB in flight, ran at 38 GB/s instead of 53 and finished 40 % after everybody else (tools/dw_cta_times.py,
+// profiles/r2c_dw_cta_times_*.log).  Every role walks the same (GEMM, chunk) sequence and restarts at stage 0 when it moves to the next
+// GEMM; the producer first waits until every stage of the old geometry has been consumed.
+constexpr int kTNBRingBoxes = 24;
+constexpr int kTNBMaxStages = 8;
+constexpr int kSmemTNB = kTNBRingBoxes * kBoxBytes + 1024;
+__device__ __forceinline__ int tnb_stages(int boxes) { const int n = kTNBRingBoxes / boxes; return n < kTNBMaxStages ? n : kTNBMaxStages; }
 
 // chunk range [c0, c1) of GEMM gi owned by the CTA whose cost interval is [lo, hi)
 __device__ __forceinline__ void tnb_range(const TNBGemm& g, int64_t chunks, int64_t lo, int64_t hi, int64_t& c0, int64_t& c1) {
-  const int64_t per = 2 * g.mt_count + g.x_cnt;                   // boxes per chunk
+  const int64_t per = g.cost;                                     // cost units per chunk
   const int64_t cost0 = chunks * g.per0;
   const int64_t end = cost0 + chunks * per;
   const int64_t a = lo > cost0 ? lo : cost0, b = hi < end ? hi : end;
   if (b <= a) { c0 = c1 = 0; return; }
-  c0 = (a - cost0 + per - 1) / per;                               // a chunk belongs to the CTA that owns its first box
+  c0 = (a - cost0 + per - 1) / per;                               // a chunk belongs to the CTA that owns its first cost unit
   c1 = (b - cost0 + per - 1) / per;
   if (c1 > chunks) c1 = chunks;
 }
 
+#ifdef EONERF_TIMING
+__device__ unsigned long long g_tnb_time[3][256];     // per CTA: globaltimer at start, when the producer has issued its last load, at exit
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __grid_constant__ TNBParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[kTNBStages], empty_bar[kTNBStages], acc_full, acc_empty;
+  __shared__ uint64_t full_bar[kTNBMaxStages], empty_bar[kTNBMaxStages], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef EONERF_TIMING
+  if (threadIdx.x == 0 && blockIdx.x < 256) g_tnb_time[0][blockIdx.x] = gtimer();
+#endif
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTNBStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 5); }   // MMA commit + 4 epilogue warps
+    for (int s = 0; s < kTNBMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (p.dbg_skip_tail & 16) ? 1 : 5); }   // MMA commit + 4 epilogue warps
     mbar_init(&acc_full, 1);
     mbar_init(&acc_empty, 4);
     fence_barrier_init();
@@ -576,7 +590,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      // uses: bit s = how often stage s has been filled, mod 2 (fill k + 1 of a stage waits for its k-th release: parity (k - 1) & 1)
+      int stage = 0; uint32_t uses = 0;
 #if EONERF_DW_LOAD_HINT
       const uint64_t pol = l2_policy_evict_first();            // G and X are streamed once: do not let them displace anything
 #define EO_DW_LOAD(dst, src, bytes, bar) bulk_load_hint(dst, src, bytes, bar, pol)
@@ -587,10 +602,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
         const TNBGemm& g = p.g[gi];
         int64_t c0, c1;
         tnb_range(g, chunks, lo, hi, c0, c1);
+        if (c1 <= c0) continue;
         const int a_boxes = g.mt_count * 2;
+        const int boxes = a_boxes + g.x_cnt, n_st = tnb_stages(boxes);
+        // new stage geometry: every stage of the previous GEMM must have been consumed before its bytes are overwritten
+        for (int st = 0; st < kTNBMaxStages; ++st) mbar_wait(&empty_bar[st], ((uses >> st) & 1u) ^ 1u);
+        stage = 0;
         for (int64_t c = c0; c < c1; ++c) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* s0 = smem + (size_t)stage * kTNBStageBytes;
+          mbar_wait(&empty_bar[stage], ((uses >> stage) & 1u) ^ 1u);
+          uses ^= 1u << stage;
+          uint8_t* s0 = smem + (size_t)stage * boxes * kBoxBytes;
           mbar_expect_tx(&full_bar[stage], (a_boxes + g.x_cnt) * kBoxBytes);
           const int64_t tile = c >> 1;
           const size_t hoff = (size_t)(c & 1) * kBoxBytes;
@@ -598,14 +619,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
             EO_DW_LOAD(s0 + b * kBoxBytes, g.G + ((size_t)tile * g.g_nb + g.g_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
           for (int b = 0; b < g.x_cnt; ++b)
             EO_DW_LOAD(s0 + (a_boxes + b) * kBoxBytes, g.X + ((size_t)tile * g.x_nb + g.x_blk0 + b) * kBlkBytes + hoff, kBoxBytes, &full_bar[stage]);
-          if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
+          if (++stage == n_st) stage = 0;
         }
       }
+#ifdef EONERF_TIMING
+      if (blockIdx.x < 256) g_tnb_time[1][blockIdx.x] = gtimer();
+#endif
     }
   } else if (warp == 1) {
     // whole warp converged, MMAs predicated on one elected lane: keeps the descriptors in uniform registers (tc_ptx.cuh)
     const bool elected = elect_one_sync();
-    int stage = 0; uint32_t phase = 0;
+    int stage = 0; uint32_t uses = 0;                        // bit s = how often stage s has been consumed, mod 2
     uint32_t items = 0;
     for (int gi = 0; gi < p.n; ++gi) {
       const TNBGemm& g = p.g[gi];
@@ -614,26 +638,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
       if (c1 <= c0) continue;
       const uint32_t idesc = instr_desc(kBlockM, g.x_cnt * 64, 1, 1);
       const int a_boxes = g.mt_count * 2;
+      const int boxes = a_boxes + g.x_cnt, n_st = tnb_stages(boxes);
+      stage = 0;
       if (items > 0) {                                           // the epilogue has drained the previous item's accumulators
         mbar_wait(&acc_empty, (items - 1) & 1u);
         tc_fence_after();
       }
       for (int64_t c = c0; c < c1; ++c) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&full_bar[stage], (uses >> stage) & 1u);
+        uses ^= 1u << stage;
         tc_fence_after();
-        const uint32_t s0 = smem_u32(smem + (size_t)stage * kTNBStageBytes);
+        const uint32_t s0 = smem_u32(smem + (size_t)stage * boxes * kBoxBytes);
         const uint32_t sx = s0 + a_boxes * kBoxBytes;
         if (elected) {
+          if (!(p.dbg_skip_tail & 4))
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             const uint64_t dx = smem_desc(sx + k * 2048, kBoxBytes, 1024);
             umma_bf16(tmem_base, smem_desc(s0 + k * 2048, kBoxBytes, 1024), dx, idesc, (c > c0) || k != 0);
             if (g.mt_count == 2) umma_bf16(tmem_base + 256, smem_desc(s0 + 2 * kBoxBytes + k * 2048, kBoxBytes, 1024), dx, idesc, (c > c0) || k != 0);
           }
+          if (p.dbg_skip_tail & 8) mbar_arrive(&empty_bar[stage]); else
           umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
-        if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
+        if (++stage == n_st) stage = 0;
       }
       if (elected) umma_commit(&acc_full);
       __syncwarp();
@@ -644,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
     const int t = threadIdx.x - 64;                       // 0..127: box t/32, 32-bit word `lane` of each 128-byte row
     const int box = t >> 5;
     const int quarter = warp & 3;
-    int stage = 0; uint32_t phase = 0;
+    int stage = 0; uint32_t uses = 0;
     uint32_t items = 0;
     for (int gi = 0; gi < p.n; ++gi) {
       const TNBGemm& g = p.g[gi];
@@ -652,30 +681,49 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
       tnb_range(g, chunks, lo, hi, c0, c1);
       if (c1 <= c0) continue;
       const int a_boxes = g.mt_count * 2;
+      const int boxes = a_boxes + g.x_cnt, n_st = tnb_stages(boxes);
+      stage = 0;
       const int block_k = g.x_cnt * 64;
       const bool do_sum = box < a_boxes && g.db[box >> 1] != nullptr;
-      float s_lo = 0.f, s_hi = 0.f;
-      for (int64_t c = c0; c < c1; ++c) {
-        mbar_wait(&full_bar[stage], phase);
+      // bias gradient: lane (ro = lane >> 3, lc = lane & 7) sums the eight features of 16-byte chunk lc over rows ro, ro + 4, ...
+      // (one LDS.128 per four rows of the box, eight independent accumulators); the four row groups are merged at the end of the item
+      float bs[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bs[e] = 0.f;
+      const int lc = lane & 7, ro = lane >> 3;
+      for (int64_t c = c0; c < c1 && !(p.dbg_skip_tail & 16); ++c) {
+        mbar_wait(&full_bar[stage], (uses >> stage) & 1u);
+        uses ^= 1u << stage;
         if (do_sum) {
-          const uint32_t base = smem_u32(smem + (size_t)stage * kTNBStageBytes + box * kBoxBytes) + (lane & 3) * 4;
-#pragma unroll 8
-          for (int rr = 0; rr < 64; ++rr) {
-            uint32_t w;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4)) : "memory");
-            s_lo += __uint_as_float(w << 16);
-            s_hi += __uint_as_float(w & 0xFFFF0000u);
+          const uint32_t base = smem_u32(smem + ((size_t)stage * boxes + box) * kBoxBytes);
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int rr = 4 * i + ro;
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + rr * 128 + ((lc ^ (rr & 7)) << 4)));
+            bs[0] += __uint_as_float(w0 << 16); bs[1] += __uint_as_float(w0 & 0xFFFF0000u);
+            bs[2] += __uint_as_float(w1 << 16); bs[3] += __uint_as_float(w1 & 0xFFFF0000u);
+            bs[4] += __uint_as_float(w2 << 16); bs[5] += __uint_as_float(w2 & 0xFFFF0000u);
+            bs[6] += __uint_as_float(w3 << 16); bs[7] += __uint_as_float(w3 & 0xFFFF0000u);
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
-        if (++stage == kTNBStages) { stage = 0; phase ^= 1; }
+        if (++stage == n_st) stage = 0;
       }
       if (do_sum) {
-        const int mt = box >> 1;
-        const int n = (box & 1) * 64 + 2 * lane;
-        if (n < g.n_valid[mt]) atomicAdd(g.db[mt] + n, s_lo);
-        if (n + 1 < g.n_valid[mt]) atomicAdd(g.db[mt] + n + 1, s_hi);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          bs[e] += __shfl_xor_sync(0xffffffffu, bs[e], 8);
+          bs[e] += __shfl_xor_sync(0xffffffffu, bs[e], 16);
+        }
+        if (ro == 0) {
+          const int mt = box >> 1;
+          const int n0 = (box & 1) * 64 + lc * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (n0 + e < g.n_valid[mt]) atomicAdd(g.db[mt] + n0 + e, bs[e]);
+        }
       }
       mbar_wait(&acc_full, items & 1u);
       tc_fence_after();
@@ -688,7 +736,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
-          if (n >= g.n_valid[mt] || g.D[mt] == nullptr || p.dbg_skip_tail) continue;
+          if (n >= g.n_valid[mt] || g.D[mt] == nullptr || (p.dbg_skip_tail & 1)) continue;
           float* drow = g.D[mt] + (int64_t)n * g.ldd[mt] + c;
           if (vec && c + 32 <= g.k_valid) {
 #pragma unroll
@@ -711,11 +759,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_blocked_kernel(const __gr
   }
   tc_fence_before();
   __syncthreads();
+#ifdef EONERF_TIMING
+  if (threadIdx.x == 0 && blockIdx.x < 256) g_tnb_time[2][blockIdx.x] = gtimer();
+#endif
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// Cost of one 64-sample chunk in 1/16-box units.  Bytes (8 KB boxes) are the first-order cost; the measured per-box time of a CTA
+// (tools/dw_cta_times.py, 1 M samples, after the variable stage count) deviates from it by GEMM shape: 4-box chunks (six stages, two
+// bias boxes) 0.93, 5-box chunks (four stages = 160 KB in flight) 1.02, 5-box chunks that also carry the bias-gradient side job on
+// four G boxes 1.14, 8-box chunks 1.00.  Weighting the split by it lets all CTAs finish together.
+static int tnb_chunk_cost(const GemmTNBlocked& g) {
+  const int boxes = 2 * g.mt_count + g.x_cnt;
+  const bool bias = g.db[0] != nullptr || g.db[1] != nullptr;
+  double w = 1.0;
+  if (boxes <= 4) w = 0.93;
+  else if (boxes < 8) w = bias ? 1.14 : 1.02;
+  return (int)(16.0 * boxes * w + 0.5);
 }
 
 int gemm_tn_blocked_group(const GemmTNBlocked* list, int n, cudaStream_t s) {
@@ -741,8 +805,9 @@ int gemm_tn_blocked_group(const GemmTNBlocked* list, int n, cudaStream_t s) {
       for (int j = 0; j < 2; ++j) { q.n_valid[j] = g.n_valid[j]; q.D[j] = g.D[j]; q.ldd[j] = g.ldd[j]; q.db[j] = (dbg & 2) ? nullptr : g.db[j]; }
       EO_REQUIRE(n_tiles < 0 || (n_tiles == g.n_tiles && n_dev == g.n_pts_dev), "gemm_tn_blocked: the GEMMs of a group share the sample axis");
       n_tiles = g.n_tiles; n_dev = g.n_pts_dev;
+      q.cost = tnb_chunk_cost(g);
       q.per0 = per;
-      per += 2 * g.mt_count + g.x_cnt;
+      per += q.cost;
       chunks_total += g.n_tiles * 2;
       const double M = (double)g.n_tiles * kTileM;
       flops += 2.0 * M * g.mt_count * 128 * g.k_valid;
@@ -752,7 +817,7 @@ int gemm_tn_blocked_group(const GemmTNBlocked* list, int n, cudaStream_t s) {
     p.chunks = n_tiles * 2;
     p.per_total = per;
     p.n_pts_dev = n_dev;
-    p.dbg_skip_tail = dbg & 1;
+    p.dbg_skip_tail = dbg & 29;
     int64_t grid = sm_count();
     if (grid > chunks_total) grid = chunks_total;
     profile_begin(1, flops, bytes, s);
@@ -766,3 +831,11 @@ int gemm_tn_blocked_group(const GemmTNBlocked* list, int n, cudaStream_t s) {
 int gemm_tn_blocked(const GemmTNBlocked& g, cudaStream_t s) { return gemm_tn_blocked_group(&g, 1, s); }
 
 }  // namespace eonerf
+
+#ifdef EONERF_TIMING
+extern "C" int eonerf_debug_tnb_time(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, eonerf::g_tnb_time, sizeof(unsigned long long) * 3 * 256);
+  return 0;
+}
+#endif

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
   const uint32_t rank = kCl > 1 ? cluster_ctarank() : 0;
   FusedBars B;
   uint32_t* tmem_base_s;
+  EO_CTA_TIME(0);
   fused_setup<kCG, kMC, kFwdRing>(smem, B, tmem_base_s, rank, kFOffBar);
   // encoder handshake (see fused_mma_issuer): enc_full[slot] counts the encoder warp of every CTA whose rows the MMA covers
   uint64_t* const enc_full = (uint64_t*)(smem + kFOffBar + 88);
@@ -452,6 +453,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) fused_fwd_kernel(const __grid_
     if (store_id >= 0) tma_store_wait_all();
   }
   fused_teardown<kCG, kMC>(tmem_base);
+  EO_CTA_TIME(1);
 }
 
 // ---- prepare: weight blocks + constants ----------------------------------------------------------------------------
@@ -742,6 +744,11 @@ extern "C" int eonerf_debug_timing(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, eonerf::g_fused_timing, sizeof(unsigned long long) * 16);
   if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(eonerf::g_fused_timing, z, sizeof(z)); }
+  return 0;
+}
+extern "C" int eonerf_debug_cta_time_fwd(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, eonerf::g_fused_cta_time, sizeof(unsigned long long) * 512);
   return 0;
 }
 #endif

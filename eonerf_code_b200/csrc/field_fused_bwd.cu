@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
   FusedBars B;
   uint32_t* tmem_base_s;
   constexpr int kOffSlotL = off_slot(kRing), kSlotBytesL = slot_bytes(kRing);
+  EO_CTA_TIME(0);
   fused_setup<kCG, kMC, kRing>(smem, B, tmem_base_s, rank);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 896; i += kFusedThreads) hw[i] = __ldg(p.consts + kCWSigma + i);
@@ -447,6 +448,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
     if (store_id >= 0) tma_store_wait_all();
   }
   fused_teardown<kCG, kMC>(tmem_base);
+  EO_CTA_TIME(1);
 }
 
 // ---- SIMT side kernels over the blocked layout ------------------------------------------------------------------------
@@ -939,6 +941,11 @@ extern "C" int eonerf_debug_timing_bwd(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, eonerf::g_fused_timing, sizeof(unsigned long long) * 16);
   if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(eonerf::g_fused_timing, z, sizeof(z)); }
+  return 0;
+}
+extern "C" int eonerf_debug_cta_time_bwd(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, eonerf::g_fused_cta_time, sizeof(unsigned long long) * 512);
   return 0;
 }
 #endif

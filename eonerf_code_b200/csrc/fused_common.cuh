@@ -175,6 +175,10 @@ static __device__ unsigned long long g_fused_timing[16];   // one copy per trans
 // raw clock64 trace of CTA 0: [0][..] MMA thread (per slot-stage: slot handed over, MMAs issued), [1][..] epilogue thread 64 (per
 // slot-stage: accumulator seen, chunks done, end barrier passed)
 static __device__ long long g_fused_trace[2][1024];
+// per-CTA wall time (globaltimer, ns): [0][cta] at entry, [1][cta] at exit
+static __device__ unsigned long long g_fused_cta_time[2][256];
+__device__ __forceinline__ unsigned long long eo_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define EO_CTA_TIME(i) do { if (threadIdx.x == 0 && blockIdx.x < 256) g_fused_cta_time[i][blockIdx.x] = eo_gtimer(); } while (0)
 #define EO_TRACE(role, idx, cond) do { if (blockIdx.x == 0 && (cond) && (idx) < 1024) g_fused_trace[role][(idx)++] = clock64(); } while (0)
 #define EO_T0() const long long _t0 = clock64()
 #define EO_TN(name) const long long name = clock64()
@@ -186,6 +190,7 @@ static __device__ long long g_fused_trace[2][1024];
 #define EO_TD(slot, a, b) do {} while (0)
 #define EO_T1(slot) do {} while (0)
 #define EO_TRACE(role, idx, cond) do {} while (0)
+#define EO_CTA_TIME(i) do {} while (0)
 #endif
 
 // ---- the tensor-core side of both fused kernels -------------------------------------------------------------------

@@ -9,7 +9,10 @@ Two ways to run the same step:
   the reference has more) and returns n_rendering_samples as an int.
 * CUDA graph (`graph=True`, fused precision): the whole step is sync-free (`render_image(static=True)`: sample counts
   stay on the device), so it is captured once and replayed: ~200 kernel launches and all of Python leave the step.
-  With world > 1 the NCCL all-reduce stays outside the graphs (render + backward | all-reduce | Adam)."""
+  With world > 1 the NCCL all-reduce stays outside the graphs (render + backward | all-reduce | Adam); EONERF_GRAPH_NCCL=1 captures it
+  inside one graph instead (measured: no gain)."""
+import os
+
 import torch
 
 from . import _capi as K
@@ -97,14 +100,24 @@ class TrainStep:
              "uniforms": None if uniforms is None else {k: v.clone() for k, v in uniforms.items()}}
         lib = K.lib()
         before = int(lib.eonerf_launch_count(0))
+        # world > 1, EONERF_GRAPH_NCCL=1: the flat-gradient all-reduce is captured INSIDE the graph (NCCL collectives are capturable): one
+        # launch per step.  Measured at N = 2: 8.59 ms per step against 8.56 ms for the default form (graph | host-issued all-reduce |
+        # graph) — no gain, so the default stays; tools/check_graph_nccl.py checks both against the eager data-parallel step.
+        fuse_nccl = self.world > 1 and os.environ.get("EONERF_GRAPH_NCCL", "0") == "1"
+        if fuse_nccl:
+            torch.distributed.all_reduce(torch.zeros(1, device=rays.device))      # communicator set-up happens outside the capture
+            torch.cuda.synchronize()
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1, capture_error_mode="thread_local"):
             loss, n = self._forward_backward(g["rays"], g["ts"], g["pixels"], epoch_idx, static=True, uniforms=g["uniforms"])
             self.n_rendered_total += n
             if self.world == 1:
                 self._update(averaged=True)
+            elif fuse_nccl:
+                torch.distributed.all_reduce(self.grads.flat)
+                self._update(averaged=False)
         g["g1"], g["loss"], g["n"] = g1, loss, n
-        if self.world > 1:
+        if self.world > 1 and not fuse_nccl:
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2, capture_error_mode="thread_local"):
                 self._update(averaged=False)
@@ -148,7 +161,7 @@ class TrainStep:
                 v.copy_(uniforms[k], non_blocking=True)
         self.optimizer.sync_hyper()            # the captured Adam reads lr on the device: follow schedulers between replays
         g["g1"].replay()
-        if self.world > 1:
+        if "g2" in g:
             torch.distributed.all_reduce(self.grads.flat)
             g["g2"].replay()
         self._params_changed()

@@ -280,22 +280,31 @@ def extra_train_arms(args, rank, world, dev, barrier, max_over_ranks):
     torch.manual_seed(42)
     vm = VanillaNeRFRadianceField(precision="bf16_fused" if args.precision == "bf16_fused" else "bf16").to(dev).train()
     est = OccGridEstimator(roi_aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], resolution=64, levels=1).to(dev)
-    vopt = torch.optim.Adam(vm.parameters(), lr=5e-4)
+    from eonerf_code_b200.training import VanillaTrainStep
     vb = [tuple(t.to(dev) for t in make_pinhole_rays(4096, seed=77 + i)) for i in range(2)]
     bk = torch.ones(3, device=dev)
     n_v = 0
+    v_graph = use_graph
+    vts = VanillaTrainStep(vm, est, render_step_size=5e-3, near_plane=0.0, render_bkgd=bk, lr=5e-4, graph=v_graph)
 
     def vstep(i):
         nonlocal n_v
         o, d, px = vb[i % 2]
-        rgb, acc, depth, n_v = render_image_with_occgrid(vm, est, Rays(o, d), near_plane=0.0, render_step_size=5e-3, render_bkgd=bk)
-        loss = torch.nn.functional.smooth_l1_loss(rgb, px)
-        vopt.zero_grad()
-        loss.backward()
-        vopt.step()
+        loss, n_v = vts(o, d, px)
         return loss
-    for i in range(3):
-        vstep(i)
+    try:
+        for i in range(3):
+            vstep(i)
+    except Exception as ex:                      # the captured form is an optimisation of this arm, not a requirement: fall back to eager
+        if not v_graph:
+            raise
+        print(f"cfg2: graph step unavailable ({type(ex).__name__}: {ex}); eager step", file=sys.stderr)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        v_graph = False
+        vts = VanillaTrainStep(vm, est, render_step_size=5e-3, near_plane=0.0, render_bkgd=bk, lr=5e-4, graph=False)
+        for i in range(3):
+            vstep(i)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -304,12 +313,13 @@ def extra_train_arms(args, rank, world, dev, barrier, max_over_ranks):
     e1.record()
     barrier()
     vms = e0.elapsed_time(e1) / 5
+    n_v = int(n_v)
     out["cfg2"] = {"metric": "train_rays_per_sec", "value": 4096 / (vms * 1e-3), "unit": "rays/s", "ms_per_step": vms, "steps": 5, "rays": 4096,
                    "samples_per_step": int(n_v), "samples_per_sec": n_v / (vms * 1e-3), "loss": float(vl.detach()),
                    "workload": "BASELINE configs[1]: VanillaNeRFRadianceField (8x256 + 1x128, view-conditioned), 4096 pinhole rays of an 800x800 "
                                "lego-shaped camera, box +-1.5, uniform marching at 5e-3, nerfacc.rendering conventions, smooth-L1 + Adam; "
-                               "fused tcgen05 field kernels (first ten stages of the EO-NeRF program); the reference's own marcher module is missing (parity unpinned)"}
-    del vm, vopt, vb, est
+                               "fused tcgen05 field kernels (first ten stages of the EO-NeRF program); " + ("one CUDA graph per step (sample count on the device, flat Adam); " if v_graph else "eager step; ") + "the reference's own marcher module is missing (parity unpinned)"}
+    del vm, vts, vb, est
     torch.cuda.empty_cache()
     if 65536 % world == 0:
         run("cfg5", 20, 65536 // world, 8192 if 65536 // world > 8192 else None, 4,

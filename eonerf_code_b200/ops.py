@@ -175,9 +175,11 @@ def set_last_t_end(t_ends, ray_offsets, value=1e10):
 
 
 @on_tensor_device
-def march_aabb(origins, viewdirs, aabb, near_plane, far_plane, step, jitter=None, max_per_ray=4096):
+def march_aabb(origins, viewdirs, aabb, near_plane, far_plane, step, jitter=None, max_per_ray=4096, static=False):
     """Uniform marching inside the scene box (csrc/march.cu; BASELINE configs[1]).  -> (ray_indices i64[P], t_starts[P],
-    t_ends[P], ray_offsets i64[B+1]).  One host read (the total P), like the reference's samplers."""
+    t_ends[P], ray_offsets i64[B+1]).  One host read (the total P), like the reference's samplers.
+    static=True: no host read (CUDA-graph capturable): the outputs have the worst-case capacity B * min(max_per_ray, box diagonal / step + 2)
+    and a fifth return value holds the live count P as an int64[1] device tensor (a view of ray_offsets[B])."""
     _need_cuda(origins, viewdirs, jitter)
     o, os_ = _rows(origins)
     d, ds_ = _rows(viewdirs)
@@ -187,7 +189,8 @@ def march_aabb(origins, viewdirs, aabb, near_plane, far_plane, step, jitter=None
     if jitter is not None:
         jitter = _f32(jitter).contiguous()
         a.jitter = _p(jitter)
-    for i, v in enumerate([float(x) for x in torch.as_tensor(aabb).flatten().tolist()]):
+    box = [float(x) for x in torch.as_tensor(aabb).flatten().tolist()]
+    for i, v in enumerate(box):
         a.aabb[i] = v
     a.near_plane, a.far_plane, a.step, a.max_per_ray = float(near_plane), float(min(far_plane, 3.0e38)), float(step), int(max_per_ray)
     counts = torch.empty(B, dtype=torch.int64, device=dev)
@@ -196,11 +199,17 @@ def march_aabb(origins, viewdirs, aabb, near_plane, far_plane, step, jitter=None
     K.call("march_count", a, _stream())
     offs = torch.zeros(B + 1, dtype=torch.int64, device=dev)
     torch.cumsum(counts, 0, out=offs[1:])
-    P = int(offs[-1])
+    if static:
+        diag = sum((box[3 + k] - box[k]) ** 2 for k in range(3)) ** 0.5
+        P = B * min(int(max_per_ray), int(diag / float(step)) + 2)
+    else:
+        P = int(offs[-1])
     ri = torch.empty(P, dtype=torch.int64, device=dev)
     ts, te = torch.empty(P, dtype=torch.float32, device=dev), torch.empty(P, dtype=torch.float32, device=dev)
     a.ray_offsets, a.ray_indices, a.t_starts, a.t_ends = _p(offs), _p(ri), _p(ts), _p(te)
     K.call("march_write", a, _stream())
+    if static:
+        return ri, ts, te, offs, offs[B:]
     return ri, ts, te, offs
 
 
@@ -557,12 +566,13 @@ class _VanillaRaysFn(torch.autograd.Function):
 
     @staticmethod
     @on_tensor_device
-    def forward(ctx, grad_on, engine, origins, viewdirs, ri, ts, te, *params):
+    def forward(ctx, grad_on, engine, origins, viewdirs, ri, ts, te, n_dev, *params):
+        """n_dev: None, or int64[1] on the device = live sample count (ri / ts / te then have their full capacity)."""
         _need_cuda(origins, viewdirs, ri, ts, te)
         P = ts.numel()
         out = engine.fwd(P, False, rays=(origins, viewdirs, ri.contiguous(), ts, te), cond_dirs=viewdirs, cond_dirs_per_ray=True, want_z=True,
-                         keep=grad_on and any(ctx.needs_input_grad))
-        ctx.engine, ctx.n, ctx.out, ctx.params = engine, P, _keep_for_backward(out), params
+                         keep=grad_on and any(ctx.needs_input_grad), n_dev=n_dev)
+        ctx.engine, ctx.n, ctx.out, ctx.params, ctx.n_dev = engine, P, _keep_for_backward(out), params, n_dev
         ctx.mark_non_differentiable(out["z_mid"])
         return out["sigma"][:, None], out["rgb"], out["z_mid"]
 
@@ -572,11 +582,11 @@ class _VanillaRaysFn(torch.autograd.Function):
         e = ctx.engine
         c = lambda g: None if g is None else _f32(g).contiguous()
         flat, views, gstruct, direct = e.grads_for_backward()
-        e.bwd(ctx.n, False, ctx.out, g_sigma=c(g_sigma), g_rgb=c(g_rgb), grads_struct=gstruct)
+        e.bwd(ctx.n, False, ctx.out, g_sigma=c(g_sigma), g_rgb=c(g_rgb), grads_struct=gstruct, n_dev=ctx.n_dev)
         ctx.out = None
         if e.grad_sync is not None and not direct:
             e.grad_sync(flat)
-        return (None,) * 7 + _grads_tuple(e, views, ctx.params, direct)
+        return (None,) * 8 + _grads_tuple(e, views, ctx.params, direct)
 
 
 class _AmbientFn(torch.autograd.Function):

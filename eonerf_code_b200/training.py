@@ -166,3 +166,70 @@ class TrainStep:
             g["g2"].replay()
         self._params_changed()
         return g["loss"], g["n"]
+
+
+class VanillaTrainStep:
+    """One training step of BASELINE configs[1] (/root/reference/train_mlp_nerf.py:155-190): render_image_with_occgrid on a batch of
+    pinhole rays -> smooth-L1 against the pixels -> backward -> Adam(lr).  Eager (torch control flow, one host read of the sample
+    count) or, with precision "bf16_fused", sync-free and replayed as ONE CUDA graph like the EO-NeRF step (the marcher leaves the
+    sample count on the device, the flat Adam keeps its step counter there)."""
+
+    def __init__(self, radiance_field, estimator, render_step_size=5e-3, near_plane=0.0, far_plane=1e10, render_bkgd=None, lr=5e-4,
+                 graph=False):
+        from .vanilla_rendering import Rays, render_image_with_occgrid
+        self._Rays, self._render = Rays, render_image_with_occgrid
+        self.field, self.estimator = radiance_field, estimator
+        self.step_size, self.near, self.far, self.bkgd = render_step_size, near_plane, far_plane, render_bkgd
+        self.graph = graph
+        if graph and radiance_field.precision != "bf16_fused":
+            raise RuntimeError("graph=True needs precision='bf16_fused' (device-side sample counts)")
+        params = list(radiance_field.parameters())
+        self.grads = FlatGrads(params)
+        self.optimizer = FlatAdam(params, self.grads.flat, lr=lr)
+        radiance_field._engine().use_grad_sink({k: p.grad for k, p in radiance_field.named_parameters()})
+        self._graphs = {}
+
+    def _forward_backward(self, origins, viewdirs, pixels, static, jitter=None):
+        self.field.train()
+        if static:
+            self.field._engine().refresh_prepared()
+        self.grads.zero()
+        rgb, acc, depth, n = self._render(self.field, self.estimator, self._Rays(origins, viewdirs), near_plane=self.near, far_plane=self.far,
+                                          render_step_size=self.step_size, render_bkgd=self.bkgd, jitter=jitter, static=static)
+        loss = torch.nn.functional.smooth_l1_loss(rgb, pixels)                    # train_mlp_nerf.py:183
+        loss.backward()
+        return loss.detach(), n
+
+    def eager(self, origins, viewdirs, pixels, jitter=None):
+        loss, n = self._forward_backward(origins, viewdirs, pixels, static=False, jitter=jitter)
+        self.optimizer.step()
+        return loss, n
+
+    def __call__(self, origins, viewdirs, pixels, jitter=None):
+        """-> (loss, n_rendering_samples).  Graph mode: both are 0-d device tensors that the next call overwrites."""
+        if not self.graph:
+            return self.eager(origins, viewdirs, pixels, jitter)
+        key = (tuple(origins.shape), jitter is not None)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = {"o": origins.clone(), "d": viewdirs.clone(), "px": pixels.clone(),
+                                     "jit": None if jitter is None else jitter.clone()}
+            self._forward_backward(g["o"], g["d"], g["px"], static=True, jitter=g["jit"])      # warm-up outside the capture (lazy init)
+            self.grads.zero()
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()               # the capture allocates its own (worst-case sized) buffers from a private pool
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                loss, n = self._forward_backward(g["o"], g["d"], g["px"], static=True, jitter=g["jit"])
+                self.optimizer.step()
+            g["graph"], g["loss"], g["n"] = graph, loss, n
+        g["o"].copy_(origins, non_blocking=True)
+        g["d"].copy_(viewdirs, non_blocking=True)
+        g["px"].copy_(pixels, non_blocking=True)
+        if jitter is not None:
+            g["jit"].copy_(jitter, non_blocking=True)
+        self.optimizer.sync_hyper()
+        g["graph"].replay()
+        for p in self.optimizer._params:                 # Adam ran behind Python's back: see TrainStep._params_changed
+            torch.autograd.graph.increment_version(p)
+        return g["loss"], g["n"]

@@ -20,15 +20,30 @@ from . import ops
 Rays = namedtuple("Rays", ("origins", "viewdirs"))            # /root/reference/datasets/utils.py:6
 
 
+def _aabb_floats(estimator):
+    """The estimator's first box as Python floats, read from the device once per version of the buffer (the marcher takes the box by
+    value: a per-step .tolist() would be a host synchronisation, and is illegal inside a graph capture)."""
+    if estimator is None:
+        return [-1.5, -1.5, -1.5, 1.5, 1.5, 1.5]
+    key = (estimator.aabbs.data_ptr(), estimator.aabbs._version)
+    cached = getattr(estimator, "_aabb_floats", None)
+    if cached is None or cached[0] != key:
+        cached = (key, [float(v) for v in estimator.aabbs[0].tolist()])
+        estimator._aabb_floats = cached
+    return cached[1]
+
+
 def render_image_with_occgrid(radiance_field, estimator, rays, near_plane=0.0, far_plane=1e10, render_step_size=1e-3,
-                              render_bkgd=None, cone_angle=0.0, alpha_thre=0.0, test_chunk_size=8192, jitter=None):
-    """-> (rgb[...,3], acc[...,1], depth[...,1], n_rendering_samples).  `jitter` [B] in [0,1) replaces the device RNG."""
+                              render_bkgd=None, cone_angle=0.0, alpha_thre=0.0, test_chunk_size=8192, jitter=None, static=False):
+    """-> (rgb[...,3], acc[...,1], depth[...,1], n_rendering_samples).  `jitter` [B] in [0,1) replaces the device RNG.
+    static=True (precision "bf16_fused"): no host synchronisation — the sample count stays on the device (buffers have the worst-case
+    capacity) and n_rendering_samples comes back as a 0-d device tensor: the whole step can be captured in a CUDA graph."""
     if cone_angle != 0.0 or alpha_thre != 0.0:
         raise NotImplementedError("cone_angle / alpha_thre pruning needs the occupancy-grid traversal of nerfacc (not in the reference)")
     shape = rays.origins.shape
     o, d = rays.origins.reshape(-1, 3), rays.viewdirs.reshape(-1, 3)
     n = o.shape[0]
-    aabb = estimator.aabbs[0] if estimator is not None else torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
+    aabb = _aabb_floats(estimator)
     e = radiance_field._engine()
     chunk = n if radiance_field.training else test_chunk_size
     outs, total = [], 0
@@ -38,9 +53,14 @@ def render_image_with_occgrid(radiance_field, estimator, rays, near_plane=0.0, f
         jit = None
         if radiance_field.training:                                        # stratified=radiance_field.training upstream
             jit = jitter[i:i + chunk] if jitter is not None else torch.rand(B, device=oc.device)
-        ri, ts, te, offs = ops.march_aabb(oc, dc, aabb, near_plane, far_plane, render_step_size, jit)
-        total += ts.numel()
-        sigma, rgb, z = ops._VanillaRaysFn.apply(torch.is_grad_enabled(), e, oc, dc, ri, ts, te, *e.tensors())
+        n_dev = None
+        if static:
+            ri, ts, te, offs, n_dev = ops.march_aabb(oc, dc, aabb, near_plane, far_plane, render_step_size, jit, static=True)
+            total = total + n_dev[0]
+        else:
+            ri, ts, te, offs = ops.march_aabb(oc, dc, aabb, near_plane, far_plane, render_step_size, jit)
+            total += ts.numel()
+        sigma, rgb, z = ops._VanillaRaysFn.apply(torch.is_grad_enabled(), e, oc, dc, ri, ts, te, n_dev, *e.tensors())
         w, _, _ = ops._WeightsFn.apply(ts, te, sigma.squeeze(-1), offs)
         colors = ops._AccumFn.apply(w, rgb, offs)
         opac = ops._AccumFn.apply(w, None, offs)

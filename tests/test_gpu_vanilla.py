@@ -131,7 +131,7 @@ def test_vanilla_fused_matches_layered(cuda, n, per_ray):
         m = _model(p, cuda, prec)
         if per_ray:
             e = m._engine()
-            sig, rgb, _ = ops._VanillaRaysFn.apply(True, e, o, d, ri, ts, te, *e.tensors())
+            sig, rgb, _ = ops._VanillaRaysFn.apply(True, e, o, d, ri, ts, te, None, *e.tensors())
         else:
             rgb, sig = m(x, d)
         ((rgb * g_rgb).sum() + (sig * g_sig).sum()).backward()
@@ -190,3 +190,32 @@ def test_autograd_nodes_release_their_stash_without_the_cycle_collector(cuda, ki
     finally:
         gc.enable()
     assert grown < 32 * 2**20, f"{grown / 2**20:.0f} MiB still allocated after three more steps"
+
+
+def test_vanilla_graph_step_matches_eager_step(cuda):
+    """VanillaTrainStep: the sync-free step replayed as one CUDA graph (worst-case sized buffers, sample count on the device, flat
+    Adam) against the eager step (exact buffers, host-read count) on the same rays and stratified offsets: sample counts equal,
+    losses and parameters after three steps agree to the order-of-summation noise of the atomics."""
+    from eonerf_code_b200.datasets.synthetic import make_pinhole_rays
+    from eonerf_code_b200.nerfacc_compat import OccGridEstimator
+    from eonerf_code_b200.training import VanillaTrainStep
+    B, step = 512, 1e-2
+    res = {}
+    for mode in ("graph", "eager"):
+        m = _model(O.init_vanilla_params(seed=7, bias_scale=0.05), cuda, "bf16_fused").train()
+        est = OccGridEstimator(roi_aabb=AABB, resolution=16, levels=1).to(cuda)
+        st = VanillaTrainStep(m, est, render_step_size=step, render_bkgd=torch.ones(3, device=cuda), graph=mode == "graph")
+        losses, counts = [], []
+        for i in range(3):
+            o, d, px = (v.to(cuda) for v in make_pinhole_rays(B, seed=20 + i))
+            jit = torch.rand(B, generator=torch.Generator().manual_seed(5 + i)).to(cuda)
+            loss, n = st(o, d, px, jitter=jit)
+            losses.append(float(loss))
+            counts.append(int(n))
+        res[mode] = (losses, counts, torch.cat([p.detach().flatten() for p in m.parameters()]).cpu())
+    assert res["graph"][1] == res["eager"][1] and min(res["eager"][1]) > 0
+    for a, b in zip(res["graph"][0], res["eager"][0]):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (res["graph"][0], res["eager"][0])
+    assert float((res["graph"][2] - res["eager"][2]).abs().max()) <= 3e-3
+    init = torch.cat([p.detach().flatten() for p in _model(O.init_vanilla_params(seed=7, bias_scale=0.05), cuda, "bf16_fused").parameters()]).cpu()
+    assert float((res["graph"][2] - init).abs().max()) > 1e-4                      # the optimiser did step

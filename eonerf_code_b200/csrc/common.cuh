@@ -38,6 +38,18 @@ void count_launch();
 
 // Optional per-launch CUDA-event timing of the GEMM kernels (bench.py's live roofline measurement).
 // kind: 0 = gemm_nt_tc, 1 = gemm_tn_tc, 2 = SIMT GEMMs.  No-ops unless eonerf_profile_enable(1) was called.
+// cudaFuncSetAttribute applies to the CURRENT device: one-time kernel configuration has to happen once per device, not once per process
+struct PerDeviceOnce {
+  bool seen[64] = {};
+  bool operator()() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (seen[d]) return false;
+    seen[d] = true;
+    return true;
+  }
+};
+
 void profile_begin(int kind, double flops, double bytes, cudaStream_t s);
 void profile_end(cudaStream_t s);
 

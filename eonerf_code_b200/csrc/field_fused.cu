@@ -711,11 +711,10 @@ int fused_field_fwd(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   if ((rc = make_blob_map(&wmap, p.wblob, kFwdBlocks)) != EONERF_OK) return rc;
 #define EO_LAUNCH_FWD(CG, MC)                                                                                                   \
   do {                                                                                                                          \
-    static bool configured = false;                                                                                             \
-    if (!configured) {                                                                                                          \
+    static PerDeviceOnce once;                                                                                             \
+    if (once()) {                                                                                                          \
       EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true, CG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));  \
       EO_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false, CG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd)); \
-      configured = true;                                                                                                        \
     }                                                                                                                           \
     profile_begin(3, flops, 0.0, s);                                                                                            \
     rc = train ? launch_fused(fused_fwd_kernel<true, CG, MC>, csz, n_ctas, p, wmap, s, kSmemFwd, kFwdThreads)                \

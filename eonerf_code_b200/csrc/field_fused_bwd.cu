@@ -824,11 +824,10 @@ int fused_field_bwd(const EonerfFieldBwdArgs* a, cudaStream_t s) {
   if ((rc = make_blob_map(&wmap, p.wblob, kBwdBlocks)) != EONERF_OK) return rc;
 #define EO_LAUNCH_BWD(CG, MC)                                                                                                  \
   do {                                                                                                                         \
-    static bool configured = false;                                                                                            \
-    if (!configured) {                                                                                                         \
+    static PerDeviceOnce once;                                                                                            \
+    if (once()) {                                                                                                         \
       EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<CG, MC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));    \
       EO_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<CG, MC, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused));    \
-      configured = true;                                                                                                       \
     }                                                                                                                          \
     profile_begin(4, flops, 0.0, s);                                                                                           \
     rc = (want_x || !deep_ring) ? launch_fused(fused_bwd_kernel<CG, MC, 3>, csz, n_ctas, p, wmap, s)                           \

@@ -484,10 +484,9 @@ int fused_field_fwd_ts(const EonerfFieldFwdArgs* a, cudaStream_t s) {
   CUtensorMap wmap;
   int rc = make_blob_map(&wmap, ext + F.fblob, kFwdBlocks);
   if (rc != EONERF_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once()) {
     EO_CUDA(cudaFuncSetAttribute(fused_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTs));
-    configured = true;
   }
   profile_begin(3, (double)N * (a->density_only ? 982528.0 : 1345280.0), 0.0, s);
   rc = launch_fused(fused_fwd_ts_kernel, 2, n_ctas, p, wmap, s, kSmemTs, kTsThreads);

@@ -427,10 +427,9 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   EO_REQUIRE(!g.addend || (g.ld_add % 8 == 0 && ((uintptr_t)g.addend & 15) == 0), "gemm_nt_tc: misaligned addend");
   EO_REQUIRE(!g.mask || (g.ld_mask % 8 == 0 && ((uintptr_t)g.mask & 15) == 0 && g.mask_cols % 8 == 0), "gemm_nt_tc: misaligned mask");
   EO_REQUIRE(!g.class_bias || g.ld_class % 4 == 0, "gemm_nt_tc: class_bias rows must be 16-byte aligned");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once()) {
     EO_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<kNTStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNT));
-    configured = true;
   }
   NTParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
@@ -462,10 +461,9 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
 
 int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return EONERF_OK;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once()) {
     EO_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<kTNStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTN));
-    configured = true;
   }
   if (g.dbias) {
     EO_REQUIRE(g.N == 64 || g.N == 128 || g.N == 256, "gemm_tn_tc: dbias supports N in {64,128,256} (got %d)", g.N);
@@ -783,10 +781,9 @@ static int tnb_chunk_cost(const GemmTNBlocked& g) {
 }
 
 int gemm_tn_blocked_group(const GemmTNBlocked* list, int n, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once()) {
     EO_CUDA(cudaFuncSetAttribute(gemm_tn_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTNB));
-    configured = true;
   }
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("EONERF_TN_DBG"); dbg = e ? atoi(e) : 0; }
